@@ -1,0 +1,100 @@
+"""Mint golden vectors from the UNMODIFIED reference (test infrastructure).
+
+Run in the build container only (needs /root/reference; the GPU box has none):
+
+    python oracle/make_golden.py            # writes tests/golden/*.npz
+
+The reference (``attention_mechanisms/fastmax.py``) ships no golden vectors for
+this path, so these fixtures *are* the parity pin: each
+holds seeded inputs and the outputs ``o, g, dq, dk, dv`` the reference's own
+``fastattention_einops`` forward/backward produced for them, evaluated in
+float64 so that the fixture is limited by the algorithm, not by the reference's
+working precision.  Inputs are rounded to bf16-representable values (stored as
+their raw upper 16 bits) so one fixture serves both the fp32 and the bf16
+kernels: the protocol of SURVEY.md section 8(c) is "bf16 kernels vs the reference
+evaluated in higher precision on the bf16-rounded inputs".
+
+A second, fp32-working-precision run of the reference is stored for one case
+(``ref32_*`` keys) to document the reference's own fp32 rounding level.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+REF_ROOT = os.environ.get("FASTMAX_REFERENCE_ROOT", "/root/reference")
+OUT_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+
+# (name, B, H, N, D, p, mask, normalize_term, tensors_normalized, seed)
+CASES = [
+    ("p2_causal_d32",      1, 2,  96,  32, 2, True,  8, False, 1),
+    ("p2_causal_d64",      2, 2, 130,  64, 2, True,  8, False, 2),
+    ("p2_causal_d64_long", 1, 1, 600,  64, 2, True,  8, False, 3),
+    ("p2_causal_d128",     1, 1,  70, 128, 2, True,  8, False, 4),
+    ("p2_full_d32",        1, 2,  96,  32, 2, False, 8, False, 5),
+    ("p2_full_d64",        2, 2, 130,  64, 2, False, 8, False, 6),
+    ("p1_causal_d64",      2, 2, 130,  64, 1, True,  8, False, 7),
+    ("p1_full_d64",        2, 2, 130,  64, 1, False, 8, False, 8),
+    ("p1_causal_d128",     1, 1, 257, 128, 1, True,  8, False, 9),
+    ("p2_causal_d64_nt1",  1, 2,  64,  64, 2, True,  1, False, 10),
+    ("p2_causal_d32_tn",   1, 2,  64,  32, 2, True,  8, True,  11),
+    ("p1_causal_d32_odd",  2, 3,  33,  32, 1, True,  8, False, 12),
+]
+
+
+def bf16_round(x: torch.Tensor) -> torch.Tensor:
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+def bf16_bits(x: torch.Tensor) -> np.ndarray:
+    return x.to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
+
+
+def main() -> None:
+    sys.path.insert(0, REF_ROOT)
+    from attention_mechanisms.fastmax import fastmax as ref_fastmax  # the unmodified reference
+
+    os.makedirs(OUT_DIR, exist_ok=True)
+    for name, B, H, N, D, p, mask, nt, tn, seed in CASES:
+        gen = torch.Generator().manual_seed(seed)
+        scale = 0.25 if tn else 1.0   # tensors_normalized => c = 1: keep |s| small like normalised q,k
+        q = bf16_round(torch.randn(B, H, N, D, generator=gen) * scale)
+        k = bf16_round(torch.randn(B, H, N, D, generator=gen) * scale)
+        v = bf16_round(torch.randn(B, H, N, D, generator=gen))
+        do = bf16_round(torch.randn(B, H, N, D, generator=gen))
+
+        def run(dtype):
+            qq, kk, vv = (t.to(dtype).clone().requires_grad_(True) for t in (q, k, v))
+            saved = {}
+            # the reference keeps g only inside ctx; fish it out of the saved tensors
+            with torch.autograd.graph.saved_tensors_hooks(
+                    lambda t: (saved.setdefault("list", []).append(t), t)[1], lambda t: t):
+                o = ref_fastmax(qq, kk, vv, mask=mask, normalize_term=nt,
+                                tensors_normalized=tn, p=p)
+            g = saved["list"][4]          # save_for_backward(q, k, v, o, g)  fastmax.py:106
+            o.backward(do.to(dtype))
+            return o.detach(), g.detach(), qq.grad, kk.grad, vv.grad
+
+        o, g, dq, dk, dv = run(torch.float64)
+        # small cases keep the float64 outputs (pins the oracle to ~1e-13); larger ones
+        # are stored as float32 (pin ~1e-7) to keep the committed fixtures small
+        st = (lambda t: t.double().numpy()) if q.numel() <= 10000 else (lambda t: t.float().numpy())
+        out = dict(
+            B=B, H=H, N=N, D=D, p=p, mask=mask, normalize_term=nt, tensors_normalized=tn,
+            q_bf16=bf16_bits(q), k_bf16=bf16_bits(k), v_bf16=bf16_bits(v), do_bf16=bf16_bits(do),
+            o=st(o), g=st(g), dq=st(dq), dk=st(dk), dv=st(dv),
+        )
+        if name == "p2_causal_d64":
+            o32, g32, dq32, dk32, dv32 = run(torch.float32)
+            out.update(ref32_o=o32.numpy(), ref32_dq=dq32.numpy(), ref32_dk=dk32.numpy(),
+                       ref32_dv=dv32.numpy())
+        path = os.path.join(OUT_DIR, name + ".npz")
+        np.savez_compressed(path, **out)
+        print(f"{name}: wrote {os.path.getsize(path)/1e6:.2f} MB  |o|max={o.abs().max():.4f}")
+
+
+if __name__ == "__main__":
+    main()

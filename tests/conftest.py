@@ -1,0 +1,55 @@
+"""pytest configuration: the ``gpu`` marker and shared fixture helpers."""
+import glob
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def pytest_collection_modifyitems(config, items):
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+def golden_names():
+    return sorted(os.path.splitext(os.path.basename(p))[0]
+                  for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+def _from_bf16_bits(a: np.ndarray) -> torch.Tensor:
+    return torch.from_numpy(a.view(np.int16).copy()).view(torch.bfloat16)
+
+
+def load_golden(name: str) -> dict:
+    """Fixture minted by oracle/make_golden.py from the unmodified reference."""
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    d = {k: z[k] for k in z.files}
+    out = dict(
+        name=name, B=int(d["B"]), H=int(d["H"]), N=int(d["N"]), D=int(d["D"]), p=int(d["p"]),
+        mask=bool(d["mask"]), normalize_term=float(d["normalize_term"]),
+        tensors_normalized=bool(d["tensors_normalized"]),
+    )
+    for key in ("q", "k", "v", "do"):
+        out[key] = _from_bf16_bits(d[key + "_bf16"])          # bf16, exact
+    for key in ("o", "g", "dq", "dk", "dv"):
+        out[key] = torch.from_numpy(d[key]).double()
+    for key in d:
+        if key.startswith("ref32_"):
+            out[key] = torch.from_numpy(d[key])
+    return out
