@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""bench.py -- headline measurement of the FastMax hot path (contract: task brief section 4).
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --steps K --warmup W    # reference CPU algorithm (oracle port)
+
+Workload (BASELINE.json configs[1] at the size `metric` is quoted on):
+    FastMax p=2 causal forward+backward, B=8, H=32, N=16384, D=64, bf16 in / fp32 accumulate,
+    synthetic N(0,1) q, k, v, do.  One "step" = one fwd+bwd over that batch.
+    tokens/s = B*N / t(step).  With N GPUs every rank runs its own batch of 8 sequences
+    ((b,h) units shard with no data-path collective): scaling = "weak".
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "fastmax_p2_causal_fwd_bwd_tokens_per_s"
+UNIT = "tokens/s"
+HL = dict(B=8, H=32, N=16384, D=64, p=2, causal=True)
+
+
+def flops_alg(D: int, p: int = 2) -> tuple[float, float]:
+    """Algorithmic flops per (b,h,token) unit, forward and backward."""
+    A = D + 1
+    if p == 2:
+        return 4 * D * D * A + 4 * D * A, 8 * D * D * A + 2 * D ** 3 + 8 * D * A + 2 * D * D
+    return 4 * D * A, 8 * D * A + 2 * D * D
+
+
+def load_peaks() -> dict:
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(tflops=d["bf16_tflops"], tflops_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    hbm_gbs=d["hbm_gbs"], source="measured")
+    return dict(tflops=1590.0, tflops_sustained=1400.0, hbm_gbs=6650.0, source="fallback")
+
+
+# ----------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown",
+               0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        while self.nv is not None and not self._stop_evt.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def finish(self) -> dict:
+        self._stop_evt.set()
+        self.join(timeout=2)
+        return dict(sm_mhz=statistics.median(self.samples) if self.samples else None,
+                    sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons), samples=len(self.samples))
+
+
+# ----------------------------------------------------------------------------------------------
+def cpu_port_rate(n_sample: int, d: int, repeats: int, threads: int) -> tuple[float, float]:
+    """Times the oracle's factorised restatement (same einsum/cumsum structure as the reference's
+    fastmax.py) on a (1,1,n_sample,d) fp32 slice of the workload.  Returns (tokens/s at H=32,
+    seconds per fwd+bwd of the sample)."""
+    from oracle import fastmax_oracle as orc
+    torch.set_num_threads(threads)
+    gen = torch.Generator().manual_seed(0)
+    q, k, v, do = (torch.randn(1, 1, n_sample, d, generator=gen) for _ in range(4))
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        orc.factorised_fwd_bwd(q, k, v, do, mask=True, p=HL["p"])
+        best = min(best, time.perf_counter() - t0)
+    units_per_s = n_sample / best
+    return units_per_s / HL["H"], best
+
+
+def run_reference(args, rank: int) -> None:
+    """--impl reference: the reference's CPU algorithm (oracle port of fastmax.py; the reference
+    itself is Python and cannot travel to the GPU box) on this box's host cores."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n_sample = 512
+    from oracle import fastmax_oracle as orc
+    torch.set_num_threads(threads)
+    gen = torch.Generator().manual_seed(0)
+    q, k, v, do = (torch.randn(1, 1, n_sample, HL["D"], generator=gen) for _ in range(4))
+    for _ in range(args.warmup):
+        orc.factorised_fwd_bwd(q, k, v, do, mask=True, p=HL["p"])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.factorised_fwd_bwd(q, k, v, do, mask=True, p=HL["p"])
+    dt = (time.perf_counter() - t0) / args.steps
+    value = n_sample / dt / HL["H"]
+    sample = (f"each step = fwd+bwd of a (B=1,H=1,N={n_sample},D={HL['D']}) fp32 slice of the workload "
+              f"(the full shape needs PB-sized intermediates); tokens/s = (b,h,token) units/s / H={HL['H']}")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "fastmax p=2 causal fwd+bwd B=8 H=32 N=16384 D=64 (CPU: bounded sample)", **HL},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ----------------------------------------------------------------------------------------------
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--algo", default="auto", choices=["auto", "exact", "moments"])
+    ap.add_argument("--seq", type=int, default=HL["N"], help="override N (diagnostics only)")
+    ap.add_argument("--batch", type=int, default=HL["B"], help="override B (diagnostics only)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3   # timing rule: at least 3 warm-up steps
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch.distributed as dist
+    from fastmax_experiments_b200 import _lib
+    from fastmax_experiments_b200.fastmax import fastmax_fwd_raw, fastmax_bwd_raw
+    from fastmax_experiments_b200.host import fastmax_fwd_bwd_host
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    B, H, N, D, p = args.batch, HL["H"], args.seq, HL["D"], HL["p"]
+    algo = {"auto": _lib.ALGO_AUTO, "exact": _lib.ALGO_EXACT, "moments": _lib.ALGO_MOMENTS}[args.algo]
+    inv_c = 1.0 / (8 * D ** 0.5)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    q, k, v, do = (torch.randn(B, H, N, D, device=dev, generator=gen).to(torch.bfloat16) for _ in range(4))
+    pl = _lib.plan(B, H, N, D, p, True, _lib.DTYPE_BF16, algo)
+
+    launches = 0
+
+    def step():
+        nonlocal launches
+        o, g = fastmax_fwd_raw(q, k, v, True, inv_c, p, algo)
+        launches += lib.fastmax_last_launch_count()
+        out = fastmax_bwd_raw(q, k, v, o, g, do, True, inv_c, p, algo)
+        launches += lib.fastmax_last_launch_count()
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches = 0
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    clocks = sampler.finish()
+    ms_total = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    tokens = B * N * world
+    value = tokens / (ms_step * 1e-3)
+
+    # ---- per-kernel breakdown with CUDA events on the launching stream (separate pass) ------
+    _lib.profile_enable(True)
+    step()
+    torch.cuda.synchronize()
+    recs = _lib.profile_fetch()
+    _lib.profile_enable(False)
+    kern = {}
+    for name, ms in recs:
+        a = kern.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += ms
+    prof_total = sum(a[1] for a in kern.values()) or 1.0
+    kernels = {n: {"launches": a[0], "ms": round(a[1], 4), "share": round(a[1] / prof_total, 4)}
+               for n, a in sorted(kern.items(), key=lambda kv: -kv[1][1])}
+
+    peaks = load_peaks()
+    U = B * H * N
+    f_fwd, f_bwd = flops_alg(D, p)
+    exec_flops = (pl.fwd_tensor_flops + pl.bwd_tensor_flops) or None
+    counted = U * (f_fwd + f_bwd)
+    if exec_flops:
+        counted = min(counted, exec_flops)       # never overstate utilisation
+    peak_tf = peaks["tflops_sustained"] if ms_step > 100 else peaks["tflops"]
+    achieved_tf = counted / (ms_step * 1e-3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_step")
+    roofline = {
+        "bound": "tensor", "achieved": round(achieved_tf, 3), "peak": peak_tf, "unit": "TFLOP/s",
+        "frac": round(achieved_tf / peak_tf, 5), "traffic": traffic,
+        "scope": "whole fwd+bwd step (all kernels); per-kernel shares in `kernels`",
+        "peak_source": f"MEASURED_PEAKS.json ({peaks['source']}; "
+                       f"{'sustained' if ms_step > 100 else 'burst'} bf16)",
+        "flops_counted": counted, "flops_alg_per_unit": f_fwd + f_bwd,
+    }
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"fastmax p=2 causal fwd+bwd B={B} H={H} N={N} D={D} bf16 (per GPU)",
+                   "B": B, "H": H, "N": N, "D": D, "p": p, "causal": True,
+                   "algo": {1: "exact", 2: "moments"}[pl.algo], "seg_len": pl.seg_len,
+                   "l2": "inputs larger than L2 (q,k,v,do 512 MiB each)",
+                   "sharding": "(b,h) units per rank, no collective"},
+        "clocks": clocks, "gpu_launches": launches, "roofline": roofline, "kernels": kernels,
+    }
+
+    # ---- e2e: host buffers in, host buffers out, copies inside the timed region ---------------
+    if not args.no_e2e:
+        hq, hk, hv, hdo = (t.cpu().pin_memory() for t in (q, k, v, do))
+        outs = tuple(torch.empty_like(hq).pin_memory() for _ in range(4))
+        n_e2e = max(1, min(args.steps, 3))
+        for _ in range(2):
+            fastmax_fwd_bwd_host(hq, hk, hv, hdo, out=outs, p=p, device=dev)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            fastmax_fwd_bwd_host(hq, hk, hv, hdo, out=outs, p=p, device=dev)
+        barrier()
+        dt = (time.perf_counter() - t0) / n_e2e
+        if world > 1:
+            t = torch.tensor([dt], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        nbytes = hq.numel() * hq.element_size()
+        out["e2e"] = {"value": tokens / dt, "unit": UNIT, "h2d_bytes_per_step": 4 * nbytes,
+                      "d2h_bytes_per_step": 4 * nbytes, "ms_per_step": dt * 1e3, "steps": n_e2e,
+                      "api": "fastmax_experiments_b200.host.fastmax_fwd_bwd_host (pinned host q,k,v,do -> "
+                             "pinned host o,dq,dk,dv; copies pipelined over the batch)"}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only) ------------------------------------------------
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        rate, secs = cpu_port_rate(512, D, repeats=3, threads=threads)
+        out["cpu_baseline"] = {
+            "value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"oracle port of fastmax.py (factorised einsum/cumsum), fp32, best of 3 fwd+bwd on a "
+                      f"(B=1,H=1,N=512,D={D}) slice = {secs:.2f} s; tokens/s = units/s / H={H}"}
+
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

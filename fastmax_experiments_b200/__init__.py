@@ -1,0 +1,5 @@
+"""fastmax_experiments_b200 -- B200-native FastMax attention (one hot path)."""
+from .fastmax import fastmax, fastattention_einops, FastmaxFunction  # noqa: F401
+from . import _lib  # noqa: F401
+
+__all__ = ["fastmax", "fastattention_einops", "FastmaxFunction"]

@@ -1,0 +1,153 @@
+// fm_api.cu -- the C ABI of include/fastmax_b200.h: argument checks, planning, dispatch.
+#include "fm_common.cuh"
+
+#include <vector>
+#include <string>
+
+namespace fm {
+ThreadStatus& status() {
+  static thread_local ThreadStatus s = {{0}, 0};
+  return s;
+}
+
+// ---- optional per-launch CUDA-event profiling (bench.py uses it for the roofline object) -----
+struct ProfRecord {
+  const char* name;
+  cudaEvent_t a, b;
+};
+static thread_local bool g_prof_on = false;
+static thread_local std::vector<ProfRecord> g_prof;
+
+void prof_begin(const char* name, cudaStream_t stream) {
+  if (!g_prof_on) return;
+  ProfRecord r{name, nullptr, nullptr};
+  cudaEventCreate(&r.a);
+  cudaEventCreate(&r.b);
+  cudaEventRecord(r.a, stream);
+  g_prof.push_back(r);
+}
+void prof_end(cudaStream_t stream) {
+  if (!g_prof_on || g_prof.empty()) return;
+  cudaEventRecord(g_prof.back().b, stream);
+}
+}  // namespace fm
+
+using fm::Problem;
+
+static int check_common(int B, int H, int N, int D, int p, int dtype) {
+  if (B <= 0 || H <= 0 || N <= 0 || D <= 0) return FASTMAX_ERR_BAD_ARG;
+  if (p != 1 && p != 2) return FASTMAX_ERR_BAD_ARG;  // reference raises ValueError (fastmax.py:428)
+  if (dtype != FASTMAX_DTYPE_F32 && dtype != FASTMAX_DTYPE_BF16) return FASTMAX_ERR_BAD_ARG;
+  if (D > 128) return FASTMAX_ERR_UNSUPPORTED;
+  return FASTMAX_OK;
+}
+
+extern "C" {
+
+int fastmax_abi_version(void) { return FASTMAX_B200_ABI_VERSION; }
+
+const char* fastmax_error_string(int code) {
+  switch (code) {
+    case FASTMAX_OK: return "ok";
+    case FASTMAX_ERR_BAD_ARG: return "bad argument";
+    case FASTMAX_ERR_UNSUPPORTED: return "unsupported shape or dtype";
+    case FASTMAX_ERR_WORKSPACE: return "workspace too small or misaligned";
+    case FASTMAX_ERR_CUDA: return "CUDA error";
+    default: return "unknown error";
+  }
+}
+
+const char* fastmax_last_cuda_error(void) { return fm::status().cuda_err; }
+int fastmax_last_launch_count(void) { return fm::status().launches; }
+
+void fastmax_profile_enable(int on) {
+  for (auto& r : fm::g_prof) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  fm::g_prof.clear();
+  fm::g_prof_on = on != 0;
+}
+
+int fastmax_profile_fetch(char* names, size_t names_cap, float* ms, int cap) {
+  int n = 0;
+  size_t used = 0;
+  if (names && names_cap) names[0] = 0;
+  for (auto& r : fm::g_prof) {
+    if (n >= cap) break;
+    if (cudaEventSynchronize(r.b) != cudaSuccess) return FASTMAX_ERR_CUDA;
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) != cudaSuccess) return FASTMAX_ERR_CUDA;
+    ms[n] = t;
+    size_t len = strlen(r.name);
+    if (names && used + len + 2 <= names_cap) {
+      memcpy(names + used, r.name, len);
+      names[used + len] = '\n';
+      names[used + len + 1] = 0;
+      used += len + 1;
+    }
+    ++n;
+  }
+  return n;
+}
+
+int fastmax_plan_make(fastmax_plan* plan, int B, int H, int N, int D, int p, int causal, int dtype, int algo) {
+  if (!plan) return FASTMAX_ERR_BAD_ARG;
+  int rc = check_common(B, H, N, D, p, dtype);
+  if (rc) return rc;
+  memset(plan, 0, sizeof(*plan));
+  (void)causal;
+  if (algo != FASTMAX_ALGO_AUTO && algo != FASTMAX_ALGO_EXACT && algo != FASTMAX_ALGO_MOMENTS)
+    return FASTMAX_ERR_BAD_ARG;
+  if (algo == FASTMAX_ALGO_MOMENTS) return FASTMAX_ERR_UNSUPPORTED;  // tcgen05 path lands next
+  plan->algo = FASTMAX_ALGO_EXACT;
+  plan->seg_len = 0;
+  plan->n_seg = 1;
+  plan->fwd_workspace_bytes = 0;
+  plan->bwd_workspace_bytes = 0;
+  return FASTMAX_OK;
+}
+
+size_t fastmax_fwd_workspace_bytes(int B, int H, int N, int D, int p, int causal, int dtype, int algo) {
+  fastmax_plan pl;
+  if (fastmax_plan_make(&pl, B, H, N, D, p, causal, dtype, algo)) return 0;
+  return (size_t)pl.fwd_workspace_bytes;
+}
+
+size_t fastmax_bwd_workspace_bytes(int B, int H, int N, int D, int p, int causal, int dtype, int algo) {
+  fastmax_plan pl;
+  if (fastmax_plan_make(&pl, B, H, N, D, p, causal, dtype, algo)) return 0;
+  return (size_t)pl.bwd_workspace_bytes;
+}
+
+int fastmax_fwd(const void* q, const void* k, const void* v, void* o, float* g, int B, int H, int N, int D,
+                int p, int causal, float inv_c, int dtype, int algo, void* workspace, size_t workspace_bytes,
+                void* stream) {
+  fm::status().launches = 0;
+  fm::status().cuda_err[0] = 0;
+  if (!q || !k || !v || !o || !g) return FASTMAX_ERR_BAD_ARG;
+  fastmax_plan pl;
+  int rc = fastmax_plan_make(&pl, B, H, N, D, p, causal, dtype, algo);
+  if (rc) return rc;
+  if (pl.fwd_workspace_bytes > workspace_bytes || (pl.fwd_workspace_bytes && !workspace))
+    return FASTMAX_ERR_WORKSPACE;
+  Problem pb{B, H, N, D, p, causal ? 1 : 0, dtype, inv_c, (cudaStream_t)stream};
+  return fm::exact_fwd(pb, q, k, v, o, g);
+}
+
+int fastmax_bwd(const void* q, const void* k, const void* v, const void* o, const float* g, const void* d_o,
+                void* dq, void* dk, void* dv, int B, int H, int N, int D, int p, int causal, float inv_c,
+                int dtype, int algo, void* workspace, size_t workspace_bytes, void* stream) {
+  fm::status().launches = 0;
+  fm::status().cuda_err[0] = 0;
+  if (!q || !k || !v || !o || !g || !d_o || !dq || !dk || !dv) return FASTMAX_ERR_BAD_ARG;
+  fastmax_plan pl;
+  int rc = fastmax_plan_make(&pl, B, H, N, D, p, causal, dtype, algo);
+  if (rc) return rc;
+  if (pl.bwd_workspace_bytes > workspace_bytes || (pl.bwd_workspace_bytes && !workspace))
+    return FASTMAX_ERR_WORKSPACE;
+  Problem pb{B, H, N, D, p, causal ? 1 : 0, dtype, inv_c, (cudaStream_t)stream};
+  return fm::exact_bwd(pb, q, k, v, o, g, d_o, dq, dk, dv);
+}
+
+}  // extern "C"

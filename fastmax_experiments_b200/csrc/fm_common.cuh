@@ -1,0 +1,73 @@
+// fm_common.cuh -- shared host/device helpers for libfastmax_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/fastmax_b200.h"
+
+namespace fm {
+
+// ---- per-thread status -------------------------------------------------------------------
+struct ThreadStatus {
+  char cuda_err[256];
+  int launches;
+};
+ThreadStatus& status();
+
+inline int cuda_fail(cudaError_t e, const char* what) {
+  ThreadStatus& s = status();
+  snprintf(s.cuda_err, sizeof(s.cuda_err), "%s: %s", what, cudaGetErrorString(e));
+  return FASTMAX_ERR_CUDA;
+}
+
+#define FM_CUDA(call)                                            \
+  do {                                                           \
+    cudaError_t e__ = (call);                                    \
+    if (e__ != cudaSuccess) return fm::cuda_fail(e__, #call);    \
+  } while (0)
+
+// Launch wrapper: counts the launch, optionally brackets it with CUDA events on the launching
+// stream (fastmax_profile_enable), and turns launch errors into FASTMAX_ERR_CUDA.
+void prof_begin(const char* name, cudaStream_t stream);
+void prof_end(cudaStream_t stream);
+
+#define FM_LAUNCH(name, stream, ...)                             \
+  do {                                                           \
+    fm::prof_begin(name, stream);                                \
+    __VA_ARGS__;                                                 \
+    fm::prof_end(stream);                                        \
+    fm::status().launches++;                                     \
+    cudaError_t e__ = cudaGetLastError();                        \
+    if (e__ != cudaSuccess) return fm::cuda_fail(e__, name);     \
+  } while (0)
+
+// ---- problem description passed between the API layer and the kernels ---------------------
+struct Problem {
+  int B, H, N, D, p, causal, dtype;
+  float inv_c;
+  cudaStream_t stream;
+};
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- device helpers -------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ float to_f32(T x);
+template <> __device__ __forceinline__ float to_f32<float>(float x) { return x; }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 x) { return __bfloat162float(x); }
+
+template <typename T> __device__ __forceinline__ T from_f32(float x);
+template <> __device__ __forceinline__ float from_f32<float>(float x) { return x; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float x) { return __float2bfloat16_rn(x); }
+
+// f(s) and f'(s) of the reference (fastmax.py:357-360): p=1: 1+s ; p=2: 1+s+s^2/2
+__device__ __forceinline__ float poly_f(float s, int p) { return p == 2 ? fmaf(s, fmaf(0.5f, s, 1.f), 1.f) : 1.f + s; }
+__device__ __forceinline__ float poly_df(float s, int p) { return p == 2 ? 1.f + s : 1.f; }
+
+// ---- kernel families (defined in their own .cu files) ---------------------------------------
+int exact_fwd(const Problem& pb, const void* q, const void* k, const void* v, void* o, float* g);
+int exact_bwd(const Problem& pb, const void* q, const void* k, const void* v, const void* o,
+              const float* g, const void* d_o, void* dq, void* dk, void* dv);
+
+}  // namespace fm

@@ -1,0 +1,126 @@
+"""FastMax attention op -- drop-in for the reference's ``attention_mechanisms/fastmax.py``.
+
+``fastmax(q, k, v, mask=True, normalize_term=8, tensors_normalized=False, p=1,
+dropout_rate=0.0, create_attn=False)`` has the reference's signature and defaults
+(fastmax.py:7-17) and the same autograd contract (``fastattention_einops.apply`` with nine
+positional arguments, fastmax.py:24-26; gradients for q, k, v only, fastmax.py:182), but runs
+hand-written sm_100a kernels through the C ABI of ``include/fastmax_b200.h``.
+
+Behavioural notes:
+* ``mask`` is tested with ``is False`` exactly like fastmax.py:85,132 -- only the literal
+  ``False`` selects the non-causal branch.
+* ``c = 1`` if ``tensors_normalized is True`` else ``normalize_term * sqrt(D)`` (fastmax.py:78-82).
+* ``dropout_rate`` is accepted and ignored, as in the reference (fastmax.py:185-216 never use it).
+* ``p`` outside {1,2} raises ``ValueError`` -- in forward (the reference silently computes
+  p=1 forward and raises only in backward, fastmax.py:210,428: quirk Q3).
+* ``create_attn=True`` raises ``NotImplementedError`` (the reference's backward for it is
+  broken: quirk Q5).
+* Inputs must be CUDA tensors: there is no CPU or PyTorch fallback.  Output dtype = input
+  dtype (fp32 or bf16); accumulation is always fp32; ``g`` is saved in fp32.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import _lib
+
+__all__ = ["fastmax", "fastattention_einops", "FastmaxFunction", "fastmax_fwd_raw", "fastmax_bwd_raw"]
+
+_DTYPES = {torch.float32: _lib.DTYPE_F32, torch.bfloat16: _lib.DTYPE_BF16}
+
+
+def _check_inputs(q, k, v):
+    if not (q.is_cuda and k.is_cuda and v.is_cuda):
+        raise _lib.FastmaxError("fastmax_experiments_b200.fastmax needs CUDA tensors "
+                                "(no CPU fallback; the CPU restatement lives in oracle/ for tests only)")
+    if q.dim() != 4 or q.shape != k.shape or q.shape != v.shape:
+        raise ValueError(f"q, k, v must share one (B, H, N, D) shape, got {tuple(q.shape)}, "
+                         f"{tuple(k.shape)}, {tuple(v.shape)}")
+    if q.dtype not in _DTYPES or k.dtype != q.dtype or v.dtype != q.dtype:
+        raise TypeError(f"q, k, v must all be float32 or all bfloat16, got {q.dtype}, {k.dtype}, {v.dtype}")
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor | None:
+    if nbytes == 0:
+        return None
+    return torch.empty(nbytes, dtype=torch.uint8, device=device)
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def fastmax_fwd_raw(q, k, v, causal: bool, inv_c: float, p: int, algo: int = _lib.ALGO_AUTO):
+    """One call of the C ABI ``fastmax_fwd`` on contiguous (B,H,N,D) CUDA tensors -> (o, g)."""
+    lib = _lib.load()
+    B, H, N, D = q.shape
+    dt = _DTYPES[q.dtype]
+    o = torch.empty_like(q)
+    g = torch.empty(B, H, N, dtype=torch.float32, device=q.device)
+    nbytes = lib.fastmax_fwd_workspace_bytes(B, H, N, D, p, int(causal), dt, algo)
+    ws = _workspace(nbytes, q.device)
+    with torch.cuda.device(q.device):
+        rc = lib.fastmax_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), g.data_ptr(),
+                             B, H, N, D, p, int(causal), inv_c, dt, algo,
+                             ws.data_ptr() if ws is not None else None, nbytes, _stream_ptr(q.device))
+    _lib.check(rc, "fastmax_fwd")
+    return o, g
+
+
+def fastmax_bwd_raw(q, k, v, o, g, do, causal: bool, inv_c: float, p: int, algo: int = _lib.ALGO_AUTO):
+    """One call of the C ABI ``fastmax_bwd`` -> (dq, dk, dv)."""
+    lib = _lib.load()
+    B, H, N, D = q.shape
+    dt = _DTYPES[q.dtype]
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
+    nbytes = lib.fastmax_bwd_workspace_bytes(B, H, N, D, p, int(causal), dt, algo)
+    ws = _workspace(nbytes, q.device)
+    with torch.cuda.device(q.device):
+        rc = lib.fastmax_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), g.data_ptr(),
+                             do.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
+                             B, H, N, D, p, int(causal), inv_c, dt, algo,
+                             ws.data_ptr() if ws is not None else None, nbytes, _stream_ptr(q.device))
+    _lib.check(rc, "fastmax_bwd")
+    return dq, dk, dv
+
+
+class FastmaxFunction(torch.autograd.Function):
+    """Autograd wrapper with the reference's nine-argument ``apply`` (fastmax.py:42-53)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, mask=True, normalize_term=8, tensors_normalized=False, p=1,
+                dropout_rate=0.0, create_attn=False):
+        if p not in (1, 2):
+            raise ValueError(f"p should be 1 or 2, got p={p}")
+        if create_attn is not False:
+            raise NotImplementedError("create_attn=True (dense debug path, fastmax.py:99-104) is not "
+                                      "provided; its backward is broken in the reference as well")
+        _check_inputs(q, k, v)
+        D = q.shape[-1]
+        c = 1.0 if tensors_normalized is True else normalize_term * math.sqrt(D)   # fastmax.py:79-82
+        causal = mask is not False                                                 # fastmax.py:85
+        q_, k_, v_ = q.contiguous(), k.contiguous(), v.contiguous()
+        o, g = fastmax_fwd_raw(q_, k_, v_, causal, 1.0 / c, p)
+        ctx.save_for_backward(q_, k_, v_, o, g)                                    # fastmax.py:106
+        ctx.causal, ctx.inv_c, ctx.p = causal, 1.0 / c, p
+        return o
+
+    @staticmethod
+    def backward(ctx, o_grad):
+        q, k, v, o, g = ctx.saved_tensors
+        do = o_grad.to(q.dtype).contiguous()
+        dq, dk, dv = fastmax_bwd_raw(q, k, v, o, g, do, ctx.causal, ctx.inv_c, ctx.p)
+        return dq, dk, dv, None, None, None, None, None, None                      # fastmax.py:182
+
+
+# the reference's class name, for code that calls ``fastattention_einops.apply`` directly
+fastattention_einops = FastmaxFunction
+
+
+def fastmax(q, k, v, mask=True, normalize_term=8, tensors_normalized=False, p=1, dropout_rate=0.0,
+            create_attn=False):
+    """Drop-in for ``attention_mechanisms.fastmax.fastmax`` (fastmax.py:7-27)."""
+    return FastmaxFunction.apply(q, k, v, mask, normalize_term, tensors_normalized, p, dropout_rate,
+                                 create_attn)

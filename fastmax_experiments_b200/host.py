@@ -1,0 +1,64 @@
+"""Host-buffer entry of the hot path: the call the reference's dispatch makes.
+
+``CausalSelfAttention.fastmax`` in the reference (lit_gpt/model.py:475-487) moves q, k, v to the
+host, runs ``fastmax(q, k, v, p=2, mask=...)`` there and moves ``o`` back.  The drop-in keeps
+the data on the GPU (``attention.py``); this module provides the same *host-in / host-out*
+contract for callers that really hold host tensors (and for ``bench.py``'s ``e2e`` number):
+pinned host q, k, v (and do) -> device -> kernels -> pinned host o (and dq, dk, dv).
+
+The copies are pipelined against the kernels over slices of the batch dimension on three
+streams (H2D, compute, D2H), so the end-to-end time approaches max(copy, compute) instead of
+their sum.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import _lib
+from .fastmax import fastmax_fwd_raw, fastmax_bwd_raw
+
+__all__ = ["fastmax_fwd_bwd_host"]
+
+
+def fastmax_fwd_bwd_host(q, k, v, do, out=None, mask=True, normalize_term=8, tensors_normalized=False,
+                         p=2, device="cuda", chunks=None):
+    """q, k, v, do: pinned host tensors (B,H,N,D).  Returns pinned host (o, dq, dk, dv).
+
+    ``out``: optional tuple of four pre-allocated pinned host tensors to write into.
+    Returns after all device work and copies have completed (host-synchronous, like the
+    reference's CPU call)."""
+    if p not in (1, 2):
+        raise ValueError(f"p should be 1 or 2, got p={p}")
+    if q.is_cuda:
+        raise _lib.FastmaxError("fastmax_fwd_bwd_host takes host tensors; use fastmax() for device tensors")
+    B, H, N, D = q.shape
+    c = 1.0 if tensors_normalized is True else normalize_term * math.sqrt(D)
+    causal = mask is not False
+    dev = torch.device(device)
+    if out is None:
+        out = tuple(torch.empty_like(q).pin_memory() for _ in range(4))
+    chunks = min(B, chunks or B)
+    bounds = [(i * B // chunks, (i + 1) * B // chunks) for i in range(chunks)]
+    s_in, s_cmp, s_out = (torch.cuda.Stream(dev) for _ in range(3))
+    ev_in = [torch.cuda.Event() for _ in bounds]
+    ev_cmp = [torch.cuda.Event() for _ in bounds]
+    keep = []
+    for i, (b0, b1) in enumerate(bounds):
+        with torch.cuda.stream(s_in):
+            dq_, dk_, dv_, ddo = (t[b0:b1].to(dev, non_blocking=True) for t in (q, k, v, do))
+            ev_in[i].record(s_in)
+        with torch.cuda.stream(s_cmp):
+            s_cmp.wait_event(ev_in[i])
+            o, g = fastmax_fwd_raw(dq_, dk_, dv_, causal, 1.0 / c, p)
+            gq, gk, gv = fastmax_bwd_raw(dq_, dk_, dv_, o, g, ddo, causal, 1.0 / c, p)
+            ev_cmp[i].record(s_cmp)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ev_cmp[i])
+            for dst, src in zip(out, (o, gq, gk, gv)):
+                dst[b0:b1].copy_(src, non_blocking=True)
+        keep.append((dq_, dk_, dv_, ddo, o, g, gq, gk, gv))   # keep alive until the streams drain
+    s_out.synchronize()
+    s_cmp.synchronize()
+    return out

@@ -1,0 +1,113 @@
+/*
+ * fastmax_b200.h -- C ABI of the B200-native FastMax attention library
+ * (libfastmax_b200.so, built from fastmax_experiments_b200/csrc/).
+ *
+ * This is the drop-in boundary of the hot path.  What each entry point replaces
+ * in the reference (ryansynk/fastmax-experiments):
+ *
+ *   fastmax_fwd   <- fastattention_einops.forward   attention_mechanisms/fastmax.py:42-111
+ *                    (compute_F_{un,}masked :185-250, compute_g_{un,}masked :253-322, o=F/g :97)
+ *                    and the never-vendored  fastmax_cuda.forwardpass   lit_gpt/model.py:82-84
+ *   fastmax_bwd   <- fastattention_einops.backward  attention_mechanisms/fastmax.py:114-182
+ *                    (gradient_o_{q,k,v}_{un,}masked :384-691)
+ *                    and                     fastmax_cuda.backwardpass  lit_gpt/model.py:116
+ *   fastmax_*_workspace_bytes / fastmax_plan_* -- no counterpart (the reference
+ *                    allocates its (B,H,N,D,D,D) intermediates implicitly through torch).
+ *   fastmax_sp_*  <- no counterpart: sequence-parallel state exchange (BASELINE.json
+ *                    north_star).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types; every function returns
+ *     FASTMAX_OK (0) or a negative FASTMAX_ERR_* code and never throws.
+ *   - all tensor pointers are DEVICE pointers, layout (B, H, N, D) contiguous
+ *     ("b h n d" of fastmax.py:61-63), element type given by `dtype`;
+ *     g is float32 (B, H, N) regardless of dtype.
+ *   - stream-ordered on `stream` (a cudaStream_t passed as void*), re-entrant, no
+ *     global mutable state besides lazily created per-device kernel attributes.
+ *   - caller owns every buffer including the workspace (size from *_workspace_bytes,
+ *     256-byte aligned).  Workspace contents are scratch; nothing persists.
+ *   - score divisor: inv_c = 1/c with c = normalize_term*sqrt(D), or 1 if
+ *     tensors_normalized (fastmax.py:78-82).  p in {1,2} (fastmax.py:68-69).
+ *     causal != 0 is the reference's `mask is not False`.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point
+ *     returns FASTMAX_ERR_CUDA.
+ */
+#ifndef FASTMAX_B200_H_
+#define FASTMAX_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FASTMAX_B200_ABI_VERSION 1
+
+/* error codes */
+#define FASTMAX_OK              0
+#define FASTMAX_ERR_BAD_ARG    -1   /* null pointer, non-positive size, p not in {1,2} ... */
+#define FASTMAX_ERR_UNSUPPORTED -2  /* shape/dtype outside what the kernels cover (D > 128, ...) */
+#define FASTMAX_ERR_WORKSPACE  -3   /* workspace too small / misaligned */
+#define FASTMAX_ERR_CUDA       -4   /* a CUDA runtime/driver call failed (see fastmax_last_cuda_error) */
+
+/* element types of q,k,v,o,do,dq,dk,dv */
+#define FASTMAX_DTYPE_F32   0
+#define FASTMAX_DTYPE_BF16  1
+
+/* algorithm selection (fastmax_plan.algo / `algo` arguments) */
+#define FASTMAX_ALGO_AUTO     0  /* cost-model choice                                          */
+#define FASTMAX_ALGO_EXACT    1  /* fp32 CUDA-core tiles of the dense formula (any D<=128)      */
+#define FASTMAX_ALGO_MOMENTS  2  /* tcgen05 chunked scan: intra-segment scores + moment states  */
+
+typedef struct fastmax_plan {
+  int32_t algo;           /* resolved FASTMAX_ALGO_*                                   */
+  int32_t seg_len;        /* tokens per scan segment (MOMENTS), 0 for EXACT            */
+  int32_t n_seg;          /* segments per (b,h) sequence                               */
+  int32_t reserved;
+  uint64_t fwd_workspace_bytes;
+  uint64_t bwd_workspace_bytes;
+  double fwd_tensor_flops; /* MMA flops the plan executes (not the algorithmic count)  */
+  double bwd_tensor_flops;
+} fastmax_plan;
+
+int         fastmax_abi_version(void);
+const char* fastmax_error_string(int code);
+/* text of the last CUDA error seen by the calling thread ("" if none) */
+const char* fastmax_last_cuda_error(void);
+
+/* Resolve the algorithm / segmentation for a problem and report workspace needs. */
+int fastmax_plan_make(fastmax_plan* plan, int B, int H, int N, int D, int p, int causal,
+                      int dtype, int algo);
+
+size_t fastmax_fwd_workspace_bytes(int B, int H, int N, int D, int p, int causal, int dtype, int algo);
+size_t fastmax_bwd_workspace_bytes(int B, int H, int N, int D, int p, int causal, int dtype, int algo);
+
+/* o (B,H,N,D) dtype, g (B,H,N) float32.  g is the normaliser the reference saves for
+ * backward (fastmax.py:106). */
+int fastmax_fwd(const void* q, const void* k, const void* v, void* o, float* g,
+                int B, int H, int N, int D, int p, int causal, float inv_c, int dtype, int algo,
+                void* workspace, size_t workspace_bytes, void* stream);
+
+/* dq,dk,dv (B,H,N,D) dtype from saved q,k,v,o,g and the upstream gradient d_o. */
+int fastmax_bwd(const void* q, const void* k, const void* v, const void* o, const float* g,
+                const void* d_o, void* dq, void* dk, void* dv,
+                int B, int H, int N, int D, int p, int causal, float inv_c, int dtype, int algo,
+                void* workspace, size_t workspace_bytes, void* stream);
+
+/* number of kernel launches the last fastmax_fwd / fastmax_bwd call of this thread issued
+ * (bench.py reports it as gpu_launches) */
+int fastmax_last_launch_count(void);
+
+/* Optional per-launch timing for measurement harnesses (no reference counterpart).
+ * While enabled, every kernel launch of the calling thread is bracketed by CUDA events on the
+ * launching stream.  fastmax_profile_fetch waits for them and writes up to `cap` durations (ms)
+ * plus the '\n'-separated kernel names; returns the number of records or a negative error.
+ * Enabling (or disabling) clears earlier records. */
+void fastmax_profile_enable(int on);
+int  fastmax_profile_fetch(char* names, size_t names_cap, float* ms, int cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FASTMAX_B200_H_ */
