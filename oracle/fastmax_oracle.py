@@ -292,8 +292,10 @@ def dense_fwd_bwd(q, k, v, do, mask=True, normalize_term=8, tensors_normalized=F
     return o, g, dq, dk, dv
 
 
-def rel_err(x: torch.Tensor, ref: torch.Tensor) -> float:
-    """Tolerance protocol of SURVEY.md section 8(c): max|x-ref| / max|ref|."""
+def rel_err(x: torch.Tensor, ref: torch.Tensor, floor: float = 1e-300) -> float:
+    """Tolerance protocol of SURVEY.md section 8(c): max|x-ref| / max|ref|.
+    ``floor`` bounds the denominator for tensors that are identically ~0 in the reference
+    (e.g. dq of a single-token causal sequence)."""
     x = x.detach().double().cpu()
     ref = ref.detach().double().cpu()
-    return float((x - ref).abs().max() / ref.abs().max().clamp_min(1e-300))
+    return float((x - ref).abs().max() / ref.abs().max().clamp_min(floor))

@@ -88,7 +88,7 @@ def test_seeded_parity_vs_oracle(shape, p, causal, dtype, algo):
     c = orc.denominator_c(D)
     out = _run_raw(*(t.to("cuda", dtype) for t in (q, k, v, do)), causal, 1.0 / c, p, ALGOS[algo])
     for nm, x, r in zip(("o", "g", "dq", "dk", "dv"), out, ref):
-        err = orc.rel_err(x, r)
+        err = orc.rel_err(x, r, floor=1e-3)     # N=1 causal has dq = dk = 0 exactly
         assert err <= TOL[dtype], (shape, p, causal, nm, err)
 
 
