@@ -99,7 +99,19 @@ int fastmax_plan_make(fastmax_plan* plan, int B, int H, int N, int D, int p, int
   (void)causal;
   if (algo != FASTMAX_ALGO_AUTO && algo != FASTMAX_ALGO_EXACT && algo != FASTMAX_ALGO_MOMENTS)
     return FASTMAX_ERR_BAD_ARG;
-  if (algo == FASTMAX_ALGO_MOMENTS) return FASTMAX_ERR_UNSUPPORTED;  // tcgen05 path lands next
+  const bool mom_ok = dtype == FASTMAX_DTYPE_BF16 && D == 64;
+  if (algo == FASTMAX_ALGO_MOMENTS && !mom_ok) return FASTMAX_ERR_UNSUPPORTED;
+  // cost model: below ~1k tokens the dense tiles are cheaper than building moment states
+  const bool use_mom = algo == FASTMAX_ALGO_MOMENTS || (algo == FASTMAX_ALGO_AUTO && mom_ok && N >= 1024);
+  if (use_mom) {
+    plan->algo = FASTMAX_ALGO_MOMENTS;
+    plan->seg_len = fm::moments_seg_len(N);
+    plan->n_seg = (N + plan->seg_len - 1) / plan->seg_len;
+    plan->fwd_workspace_bytes = fm::moments_workspace_bytes(B, H, N, causal, false);
+    plan->bwd_workspace_bytes = fm::moments_workspace_bytes(B, H, N, causal, true);
+    fm::moments_flops(B, H, N, p, causal, &plan->fwd_tensor_flops, &plan->bwd_tensor_flops);
+    return FASTMAX_OK;
+  }
   plan->algo = FASTMAX_ALGO_EXACT;
   plan->seg_len = 0;
   plan->n_seg = 1;
@@ -132,6 +144,10 @@ int fastmax_fwd(const void* q, const void* k, const void* v, void* o, float* g, 
   if (pl.fwd_workspace_bytes > workspace_bytes || (pl.fwd_workspace_bytes && !workspace))
     return FASTMAX_ERR_WORKSPACE;
   Problem pb{B, H, N, D, p, causal ? 1 : 0, dtype, inv_c, (cudaStream_t)stream};
+  if (pl.algo == FASTMAX_ALGO_MOMENTS) {
+    if (((uintptr_t)workspace & 255) != 0) return FASTMAX_ERR_WORKSPACE;
+    return fm::moments_fwd(pb, q, k, v, o, g, workspace);
+  }
   return fm::exact_fwd(pb, q, k, v, o, g);
 }
 
@@ -147,6 +163,10 @@ int fastmax_bwd(const void* q, const void* k, const void* v, const void* o, cons
   if (pl.bwd_workspace_bytes > workspace_bytes || (pl.bwd_workspace_bytes && !workspace))
     return FASTMAX_ERR_WORKSPACE;
   Problem pb{B, H, N, D, p, causal ? 1 : 0, dtype, inv_c, (cudaStream_t)stream};
+  if (pl.algo == FASTMAX_ALGO_MOMENTS) {
+    if (((uintptr_t)workspace & 255) != 0) return FASTMAX_ERR_WORKSPACE;
+    return fm::moments_bwd(pb, q, k, v, o, g, d_o, dq, dk, dv, workspace);
+  }
   return fm::exact_bwd(pb, q, k, v, o, g, d_o, dq, dk, dv);
 }
 

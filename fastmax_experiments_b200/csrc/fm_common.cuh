@@ -70,4 +70,18 @@ int exact_fwd(const Problem& pb, const void* q, const void* k, const void* v, vo
 int exact_bwd(const Problem& pb, const void* q, const void* k, const void* v, const void* o,
               const float* g, const void* d_o, void* dq, void* dk, void* dv);
 
+int exact_fwd_partial(const Problem& pb, const void* q, const void* k, const void* v, int seg_len, float* o_part,
+                      float* g_part);
+int exact_bwd_partial(const Problem& pb, const void* q, const void* k, const void* v, const void* o,
+                      const float* g, const void* d_o, int seg_len, float* dq_part, float* dk_part,
+                      float* dv_part);
+
+// tcgen05 moment-scan path (fm_moments.cu): bf16, D = 64
+int moments_seg_len(int N);
+size_t moments_workspace_bytes(int B, int H, int N, int causal, bool bwd);
+void moments_flops(int B, int H, int N, int p, int causal, double* fwd, double* bwd);
+int moments_fwd(const Problem& pb, const void* q, const void* k, const void* v, void* o, float* g, void* ws);
+int moments_bwd(const Problem& pb, const void* q, const void* k, const void* v, const void* o, const float* g,
+                const void* d_o, void* dq, void* dk, void* dv, void* ws);
+
 }  // namespace fm

@@ -44,7 +44,10 @@ template <int DMAX, typename T>
 __global__ void __launch_bounds__(NT) exact_fwd_kernel(const T* __restrict__ q, const T* __restrict__ k,
                                                         const T* __restrict__ v, T* __restrict__ o,
                                                         float* __restrict__ g, int N, int D, int p,
-                                                        int causal, float inv_c) {
+                                                        int causal, float inv_c, int seg_len,
+                                                        float* __restrict__ o_part) {
+  // seg_len > 0 (causal only): keys are restricted to the query's own segment and the
+  // unnormalised numerator / partial normaliser go to o_part / g (fp32) for the moment path.
   constexpr int DP = DMAX + 1;
   constexpr int NC = DMAX / 16;
   extern __shared__ float smem[];
@@ -68,7 +71,8 @@ __global__ void __launch_bounds__(NT) exact_fwd_kernel(const T* __restrict__ q, 
     for (int c = 0; c < NC; ++c) acc[r][c] = 0.f;
 
   const int jend = causal ? min(row0 + BM, N) : N;
-  for (int col0 = 0; col0 < jend; col0 += BN) {
+  const int jbeg = seg_len > 0 ? (row0 / seg_len) * seg_len : 0;
+  for (int col0 = jbeg; col0 < jend; col0 += BN) {
     __syncthreads();
     load_tile<T>(Ks, DP, DMAX, k + base, col0, N, D, 1.f, nullptr);
     load_tile<T>(Vs, DP, DMAX, v + base, col0, N, D, 1.f, nullptr);
@@ -122,7 +126,10 @@ __global__ void __launch_bounds__(NT) exact_fwd_kernel(const T* __restrict__ q, 
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       int d = tx + 16 * c;
-      if (d < D) o[base + (size_t)i * D + d] = from_f32<T>(acc[r][c] * inv);
+      if (d < D) {
+        if (o_part) o_part[base + (size_t)i * D + d] = acc[r][c];
+        else o[base + (size_t)i * D + d] = from_f32<T>(acc[r][c] * inv);
+      }
     }
   }
 }
@@ -154,7 +161,7 @@ __global__ void __launch_bounds__(NT) exact_bwd_dq_kernel(const T* __restrict__ 
                                                            const T* __restrict__ v, const T* __restrict__ o,
                                                            const float* __restrict__ g, const T* __restrict__ d_o,
                                                            T* __restrict__ dq, int N, int D, int p, int causal,
-                                                           float inv_c) {
+                                                           float inv_c, int seg_len, float* __restrict__ dq_part) {
   constexpr int DP = DMAX + 1;
   constexpr int NC = DMAX / 16;
   extern __shared__ float smem[];
@@ -187,7 +194,8 @@ __global__ void __launch_bounds__(NT) exact_bwd_dq_kernel(const T* __restrict__ 
     for (int c = 0; c < NC; ++c) acc[r][c] = 0.f;
 
   const int jend = causal ? min(row0 + BM, N) : N;
-  for (int col0 = 0; col0 < jend; col0 += BN) {
+  const int jbeg = seg_len > 0 ? (row0 / seg_len) * seg_len : 0;
+  for (int col0 = jbeg; col0 < jend; col0 += BN) {
     __syncthreads();
     load_tile<T>(Ks, DP, DMAX, k + base, col0, N, D, 1.f, nullptr);
     load_tile<T>(Vs, DP, DMAX, v + base, col0, N, D, 1.f, nullptr);
@@ -240,7 +248,10 @@ __global__ void __launch_bounds__(NT) exact_bwd_dq_kernel(const T* __restrict__ 
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       int d = tx + 16 * c;
-      if (d < D) dq[base + (size_t)i * D + d] = from_f32<T>(acc[r][c] * inv_c);
+      if (d < D) {
+        if (dq_part) dq_part[base + (size_t)i * D + d] = acc[r][c];   // unscaled; the apply kernel folds 1/c
+        else dq[base + (size_t)i * D + d] = from_f32<T>(acc[r][c] * inv_c);
+      }
     }
   }
 }
@@ -252,7 +263,8 @@ __global__ void __launch_bounds__(NT) exact_bwd_dkdv_kernel(const T* __restrict_
                                                              const T* __restrict__ v, const T* __restrict__ o,
                                                              const float* __restrict__ g, const T* __restrict__ d_o,
                                                              T* __restrict__ dk, T* __restrict__ dv, int N, int D,
-                                                             int p, int causal, float inv_c) {
+                                                             int p, int causal, float inv_c, int seg_len,
+                                                             float* __restrict__ dk_part, float* __restrict__ dv_part) {
   constexpr int DP = DMAX + 1;
   constexpr int NC = DMAX / 16;
   extern __shared__ float smem[];
@@ -279,7 +291,8 @@ __global__ void __launch_bounds__(NT) exact_bwd_dkdv_kernel(const T* __restrict_
 #pragma unroll
     for (int c = 0; c < NC; ++c) ak[r][c] = 0.f, av[r][c] = 0.f;
 
-  for (int row0 = causal ? col0 : 0; row0 < N; row0 += BM) {
+  const int iend = seg_len > 0 ? min(N, (col0 / seg_len + 1) * seg_len) : N;
+  for (int row0 = causal ? col0 : 0; row0 < iend; row0 += BM) {
     __syncthreads();
     row_stats<T>(inv_g, delta, d_o + base, o + base, g + (size_t)bh * N, row0, N, D);
     load_tile<T>(Qs, DP, DMAX, q + base, row0, N, D, 1.f, nullptr);
@@ -344,8 +357,13 @@ __global__ void __launch_bounds__(NT) exact_bwd_dkdv_kernel(const T* __restrict_
     for (int c = 0; c < NC; ++c) {
       int d = tx + 16 * c;
       if (d < D) {
-        dv[base + (size_t)j * D + d] = from_f32<T>(av[r][c]);
-        dk[base + (size_t)j * D + d] = from_f32<T>(ak[r][c] * inv_c);
+        if (dk_part) {
+          dv_part[base + (size_t)j * D + d] = av[r][c];
+          dk_part[base + (size_t)j * D + d] = ak[r][c];               // unscaled
+        } else {
+          dv[base + (size_t)j * D + d] = from_f32<T>(av[r][c]);
+          dk[base + (size_t)j * D + d] = from_f32<T>(ak[r][c] * inv_c);
+        }
       }
     }
   }
@@ -356,19 +374,21 @@ template <int DMAX> constexpr size_t dq_smem() { return sizeof(float) * (4 * 64 
 template <int DMAX> constexpr size_t dkdv_smem() { return sizeof(float) * (4 * 64 * (DMAX + 1) + 2 * 64 * PP + 128); }
 
 template <int DMAX, typename T>
-int launch_fwd(const Problem& pb, const void* q, const void* k, const void* v, void* o, float* g) {
+int launch_fwd(const Problem& pb, const void* q, const void* k, const void* v, void* o, float* g, int seg_len,
+               float* o_part) {
   auto kern = exact_fwd_kernel<DMAX, T>;
   FM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<DMAX>()));
   dim3 grid((pb.N + BM - 1) / BM, pb.B * pb.H);
   FM_LAUNCH("exact_fwd", pb.stream,
             kern<<<grid, NT, fwd_smem<DMAX>(), pb.stream>>>((const T*)q, (const T*)k, (const T*)v, (T*)o, g, pb.N,
-                                                             pb.D, pb.p, pb.causal, pb.inv_c));
+                                                             pb.D, pb.p, pb.causal, pb.inv_c, seg_len, o_part));
   return FASTMAX_OK;
 }
 
 template <int DMAX, typename T>
 int launch_bwd(const Problem& pb, const void* q, const void* k, const void* v, const void* o, const float* g,
-               const void* d_o, void* dq, void* dk, void* dv) {
+               const void* d_o, void* dq, void* dk, void* dv, int seg_len, float* dq_part, float* dk_part,
+               float* dv_part) {
   auto k1 = exact_bwd_dq_kernel<DMAX, T>;
   auto k2 = exact_bwd_dkdv_kernel<DMAX, T>;
   FM_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dq_smem<DMAX>()));
@@ -377,11 +397,11 @@ int launch_bwd(const Problem& pb, const void* q, const void* k, const void* v, c
   FM_LAUNCH("exact_bwd_dq", pb.stream,
             k1<<<grid, NT, dq_smem<DMAX>(), pb.stream>>>((const T*)q, (const T*)k, (const T*)v, (const T*)o, g,
                                                           (const T*)d_o, (T*)dq, pb.N, pb.D, pb.p, pb.causal,
-                                                          pb.inv_c));
+                                                          pb.inv_c, seg_len, dq_part));
   FM_LAUNCH("exact_bwd_dkdv", pb.stream,
             k2<<<grid, NT, dkdv_smem<DMAX>(), pb.stream>>>((const T*)q, (const T*)k, (const T*)v, (const T*)o, g,
                                                             (const T*)d_o, (T*)dk, (T*)dv, pb.N, pb.D, pb.p,
-                                                            pb.causal, pb.inv_c));
+                                                            pb.causal, pb.inv_c, seg_len, dk_part, dv_part));
   return FASTMAX_OK;
 }
 
@@ -397,12 +417,25 @@ int launch_bwd(const Problem& pb, const void* q, const void* k, const void* v, c
   } while (0)
 
 int exact_fwd(const Problem& pb, const void* q, const void* k, const void* v, void* o, float* g) {
-  FM_DISPATCH_EXACT(launch_fwd, pb, q, k, v, o, g);
+  FM_DISPATCH_EXACT(launch_fwd, pb, q, k, v, o, g, 0, nullptr);
 }
 
 int exact_bwd(const Problem& pb, const void* q, const void* k, const void* v, const void* o, const float* g,
               const void* d_o, void* dq, void* dk, void* dv) {
-  FM_DISPATCH_EXACT(launch_bwd, pb, q, k, v, o, g, d_o, dq, dk, dv);
+  FM_DISPATCH_EXACT(launch_bwd, pb, q, k, v, o, g, d_o, dq, dk, dv, 0, nullptr, nullptr, nullptr);
+}
+
+// Segment-restricted fp32 partials (bring-up / fallback intra-segment path of the moment scan).
+int exact_fwd_partial(const Problem& pb, const void* q, const void* k, const void* v, int seg_len, float* o_part,
+                      float* g_part) {
+  FM_DISPATCH_EXACT(launch_fwd, pb, q, k, v, nullptr, g_part, seg_len, o_part);
+}
+
+int exact_bwd_partial(const Problem& pb, const void* q, const void* k, const void* v, const void* o,
+                      const float* g, const void* d_o, int seg_len, float* dq_part, float* dk_part,
+                      float* dv_part) {
+  FM_DISPATCH_EXACT(launch_bwd, pb, q, k, v, o, g, d_o, nullptr, nullptr, nullptr, seg_len, dq_part, dk_part,
+                    dv_part);
 }
 
 }  // namespace fm

@@ -1,0 +1,782 @@
+// fm_moments.cu -- FASTMAX_ALGO_MOMENTS: the chunked causal scan of FastMax on tcgen05/TMEM/TMA.
+//
+// A sequence is cut into segments of L tokens.  Within a segment the causal polynomial scores
+// are evaluated directly (intra part); everything before the segment enters through the moment
+// state (fm_moments.cuh) of the segment boundary:
+//
+//   build : one pass over the tokens keeps S1,S2 (fp32) resident in tensor memory, adds
+//           Phi(k_j)^T [v_j] per 64-token step with tcgen05.mma (A = Khatri-Rao rows k[x]*k[y]
+//           generated in registers and written to TMEM, B = the V tile brought by TMA) and
+//           snapshots the running state as bf16 at every segment boundary.
+//   apply : per 512 tokens, streams the 65 slabs of the boundary state through shared memory
+//           with TMA and contracts them with A = q[x]*q[y] rows (again generated into TMEM).
+//   The same two kernels serve the backward pass with other operands (see moments_bwd).
+//
+// Reference functions covered: compute_F_masked / compute_g_masked (fastmax.py:219-322) and
+// gradient_o_{q,k,v}_masked (fastmax.py:433-691); the non-causal variants use one whole-sequence
+// state (fastmax.py:185-285, 384-645).
+#include "fm_common.cuh"
+#include "fm_sm100.cuh"
+#include "fm_moments.cuh"
+
+namespace fm {
+namespace mom {
+using namespace sm100;
+
+typedef __nv_bfloat16 bf16;
+
+// =============================================================================================
+// prep: transpose (B*H, N, 64) -> (B*H, 64, Npad) so that the build kernel can read token-major
+// runs of one feature with 16-byte shared loads.  HBM-bound (reads + writes the tensor once).
+// =============================================================================================
+__global__ void __launch_bounds__(256) transpose_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int N,
+                                                        int Npad) {
+  __shared__ bf16 tile[64][66];
+  const int bh = blockIdx.y, n0 = blockIdx.x * 64;
+  const bf16* src = in + (size_t)bh * N * 64;
+  bf16* dst = out + (size_t)bh * 64 * Npad;
+  for (int idx = threadIdx.x; idx < 64 * 32; idx += 256) {
+    int r = idx >> 5, c2 = idx & 31;
+    __nv_bfloat162 v = __floats2bfloat162_rn(0.f, 0.f);
+    if (n0 + r < N) v = *reinterpret_cast<const __nv_bfloat162*>(src + (size_t)(n0 + r) * 64 + 2 * c2);
+    tile[r][2 * c2] = v.x;
+    tile[r][2 * c2 + 1] = v.y;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 64 * 32; idx += 256) {
+    int d = idx >> 5, t2 = idx & 31;
+    __nv_bfloat162 v;
+    v.x = tile[2 * t2][d];
+    v.y = tile[2 * t2 + 1][d];
+    *reinterpret_cast<__nv_bfloat162*>(dst + (size_t)d * Npad + n0 + 2 * t2) = v;
+  }
+}
+
+// =============================================================================================
+// build kernel
+// =============================================================================================
+struct BuildParams {
+  int N, nblk, nproc, Lb, nseg, reverse, causal, p;
+  uint8_t* state;  // records: causal -> [bh][nseg], else [bh]
+};
+
+constexpr int B_STAGES = 3;
+constexpr int B_STAGE_BYTES = 3 * 8192;
+constexpr int B_SMEM = B_STAGES * B_STAGE_BYTES + 1024 /*barriers*/ + 1024 /*align slack*/;
+constexpr int B_ACOL = 448;  // two 32-column A buffers at the top of tensor memory
+
+__device__ __forceinline__ bool build_boundary(const BuildParams& P, int it, int& seg) {
+  const int b = P.reverse ? P.nblk - 1 - it : it;
+  if (!P.causal) {
+    seg = 0;
+    return it == P.nproc - 1;
+  }
+  if (P.reverse) {
+    seg = b / P.Lb - 1;
+    return (b % P.Lb) == 0;
+  }
+  seg = (b + 1) / P.Lb;
+  return ((b + 1) % P.Lb) == 0;
+}
+
+// 16-byte chunk c of 128-byte row `row` inside a 128B-swizzled tile
+__device__ __forceinline__ uint4 lds_swz(const uint8_t* tile, int row, int c) {
+  return *reinterpret_cast<const uint4*>(tile + row * 128 + ((c ^ (row & 7)) << 4));
+}
+
+__global__ void __launch_bounds__(512, 1)
+build_kernel(const __grid_constant__ CUtensorMap tmXT, const __grid_constant__ CUtensorMap tmW,
+             const __grid_constant__ CUtensorMap tmW2, const BuildParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B_STAGES * B_STAGE_BYTES);
+  uint64_t* full = bars;                 // [3]
+  uint64_t* empty = bars + 3;            // [3]
+  uint64_t* a_full = bars + 6;           // [2]
+  uint64_t* a_empty = bars + 8;          // [2]
+  uint64_t* acc_full = bars + 10;        // [8]
+  uint64_t* acc_free = bars + 18;        // [8]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int bh = blockIdx.y, cx = blockIdx.x;
+
+  // tile ownership: 32 regular tiles (2 slabs x 64 y each) + 1 special tile (S1 | normaliser)
+  int first_tile, nreg;
+  bool special;
+  if (P.p == 2) {
+    first_tile = 7 * cx;
+    nreg = cx < 4 ? 7 : 4;
+    special = cx == 4;
+  } else {
+    first_tile = 0, nreg = 0, special = true;
+  }
+  const int ntile = nreg + (special ? 1 : 0);
+  const uint32_t stage_tx = special ? 3 * 8192 : 2 * 8192;
+
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  if (tid == 0) {
+    for (int i = 0; i < B_STAGES; ++i) mbar_init(&full[i], 1), mbar_init(&empty[i], 1);
+    for (int i = 0; i < 2; ++i) mbar_init(&a_full[i], 128), mbar_init(&a_empty[i], 1);
+    for (int i = 0; i < 8; ++i) mbar_init(&acc_full[i], 1), mbar_init(&acc_free[i], 128);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmXT);
+    tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmW2);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      for (int it = 0; it < P.nproc; ++it) {
+        const int s = it % B_STAGES, ph = (it / B_STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        const int b = P.reverse ? P.nblk - 1 - it : it;
+        uint8_t* st = smem + s * B_STAGE_BYTES;
+        mbar_arrive_expect_tx(&full[s], stage_tx);
+        tma_load_3d(st, &tmXT, &full[s], b * 64, 0, bh);
+        tma_load_3d(st + 8192, &tmW, &full[s], 0, b * 64, bh);
+        if (special) tma_load_3d(st + 16384, &tmW2, &full[s], 0, b * 64, bh);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, 64, false, true);
+      int snaps = 0;
+      bool pending = false;
+      for (int it = 0; it < P.nproc; ++it) {
+        const int s = it % B_STAGES, ph = (it / B_STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        int seg;
+        const bool bnd = build_boundary(P, it, seg);
+        const uint32_t sbase = smem_u32(smem + s * B_STAGE_BYTES);
+        const uint64_t dW = desc_mnmajor_sw128(sbase + 8192, 8192);
+        const uint64_t dW2 = desc_mnmajor_sw128(sbase + 16384, 8192);
+        for (int ti = 0; ti < ntile; ++ti) {
+          const int c = it * ntile + ti, g = c & 1, use = c >> 1;
+          if (pending) mbar_wait(&acc_free[ti], (snaps - 1) & 1);
+          mbar_wait(&a_full[g], use & 1);
+          tc_fence_after();
+          const uint32_t a_t = tmem + B_ACOL + 32 * g;
+          if (ti < nreg) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) umma_ts(tmem + 64 * ti, a_t + kk * 8, dW + kk * 128, idesc, (it | kk) != 0);
+          } else {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) umma_ts(tmem + 64 * nreg, a_t + kk * 8, dW + kk * 128, idesc, (it | kk) != 0);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_ts(tmem + 64 * nreg + 64, a_t + kk * 8, dW2 + kk * 128, idesc, (it | kk) != 0);
+          }
+          umma_commit(&a_empty[g]);
+          if (bnd) umma_commit(&acc_full[ti]);
+        }
+        umma_commit(&empty[s]);
+        if (bnd) ++snaps;
+        pending = bnd;
+      }
+    }
+  } else if (warp >= 4 && warp < 12) {
+    // ------------------------------------------------------------------ A-operand generators
+    const int g = (warp - 4) >> 2, q = warp & 3;
+    const int row = 32 * q + lane;          // TMEM lane == feature row of the tile
+    const int xsel = row >> 6, y = row & 63;
+    const uint32_t a_addr = tmem + ((uint32_t)(32 * q) << 16) + B_ACOL + 32 * g;
+    for (int it = 0; it < P.nproc; ++it) {
+      const int s = it % B_STAGES, ph = (it / B_STAGES) & 1;
+      if (((it * ntile) & 1) != g && ntile == 1) continue;   // nothing for this group in this block
+      mbar_wait(&full[s], ph);
+      const uint8_t* xt = smem + s * B_STAGE_BYTES;
+      uint32_t yr[32];
+#pragma unroll
+      for (int c8 = 0; c8 < 8; ++c8) {
+        uint4 v = lds_swz(xt, y, c8);
+        yr[4 * c8] = v.x, yr[4 * c8 + 1] = v.y, yr[4 * c8 + 2] = v.z, yr[4 * c8 + 3] = v.w;
+      }
+      for (int ti = 0; ti < ntile; ++ti) {
+        const int c = it * ntile + ti;
+        if ((c & 1) != g) continue;
+        const int use = c >> 1;
+        uint32_t a[32];
+        if (ti < nreg) {
+          const int x = 2 * (first_tile + ti) + xsel;
+#pragma unroll
+          for (int c8 = 0; c8 < 8; ++c8) {
+            uint4 v = lds_swz(xt, x, c8);
+            a[4 * c8] = mul_bf16x2(v.x, yr[4 * c8]);
+            a[4 * c8 + 1] = mul_bf16x2(v.y, yr[4 * c8 + 1]);
+            a[4 * c8 + 2] = mul_bf16x2(v.z, yr[4 * c8 + 2]);
+            a[4 * c8 + 3] = mul_bf16x2(v.w, yr[4 * c8 + 3]);
+          }
+        } else {
+          // special tile: rows 0..63 = Y (S1 / normaliser matrix), row 64 = ones (S0 / normaliser vector)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) a[i] = row < 64 ? yr[i] : (row == 64 ? 0x3F803F80u : 0u);
+        }
+        mbar_wait(&a_empty[g], (use & 1) ^ 1);
+        tc_fence_after();
+        tmem_st32(a_addr, a);
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(&a_full[g]);
+      }
+    }
+  } else if (warp >= 12) {
+    // ------------------------------------------------------------------ snapshot writers
+    const int q = warp & 3;
+    const int row = 32 * q + lane;
+    const int xsel = row >> 6, y = row & 63;
+    const uint32_t lane_addr = tmem + ((uint32_t)(32 * q) << 16);
+    int k = 0;
+    for (int it = 0; it < P.nproc; ++it) {
+      int seg;
+      if (!build_boundary(P, it, seg)) continue;
+      uint8_t* rec = P.state + (size_t)(P.causal ? bh * P.nseg + seg : bh) * REC_BYTES;
+      for (int ti = 0; ti < ntile; ++ti) {
+        mbar_wait(&acc_full[ti], k & 1);
+        tc_fence_after();
+        const int nacc = ti < nreg ? 1 : 2;
+        for (int a2 = 0; a2 < nacc; ++a2) {
+          uint32_t v[64];
+          tmem_ld32(lane_addr + 64 * (ti + a2), v);
+          tmem_ld32(lane_addr + 64 * (ti + a2) + 32, v + 32);
+          tmem_wait_ld();
+          if (a2 == nacc - 1) {
+            tc_fence_before();
+            mbar_arrive(&acc_free[ti]);
+          }
+          int slab;
+          if (ti < nreg) slab = 2 * (first_tile + ti) + xsel;
+          else slab = 64 + a2;
+          const bool is_vec_row = (ti >= nreg) && row == 64;
+          const bool is_mat_row = (ti < nreg) || row < 64;
+          if (is_mat_row) {
+            uint4* dst = reinterpret_cast<uint4*>(rec + (size_t)slab * SLAB_BYTES + (size_t)y * 128);
+#pragma unroll
+            for (int c8 = 0; c8 < 8; ++c8) {
+              uint4 o;
+              o.x = pack_bf16x2(__uint_as_float(v[8 * c8]), __uint_as_float(v[8 * c8 + 1]));
+              o.y = pack_bf16x2(__uint_as_float(v[8 * c8 + 2]), __uint_as_float(v[8 * c8 + 3]));
+              o.z = pack_bf16x2(__uint_as_float(v[8 * c8 + 4]), __uint_as_float(v[8 * c8 + 5]));
+              o.w = pack_bf16x2(__uint_as_float(v[8 * c8 + 6]), __uint_as_float(v[8 * c8 + 7]));
+              dst[c8] = o;
+            }
+            if (slab == 65) {  // fp32 copy of the normaliser matrix
+              uint4* d32 = reinterpret_cast<uint4*>(rec + VEC_OFF + (size_t)(128 + y * 64) * 4);
+#pragma unroll
+              for (int c4 = 0; c4 < 16; ++c4) d32[c4] = make_uint4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+            }
+          } else if (is_vec_row) {
+            uint4* d32 = reinterpret_cast<uint4*>(rec + VEC_OFF + (size_t)(a2 * 64) * 4);
+#pragma unroll
+            for (int c4 = 0; c4 < 16; ++c4) d32[c4] = make_uint4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+          }
+        }
+      }
+      ++k;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+// =============================================================================================
+// apply kernel
+// =============================================================================================
+enum ApplyMode { APPLY_FWD = 0, APPLY_DQ = 1, APPLY_DV = 2, APPLY_DK = 3 };
+
+struct ApplyParams {
+  int N, L, nseg, causal, p, mode;
+  int state_reverse;        // 1: records are exclusive suffixes (last segment has none)
+  int b_kmajor;             // 1: contraction over the slab's contiguous index (dq, dk)
+  int use65;                // 1: slab 65 joins the accumulator with A = coef65 * X (dk)
+  float coef_reg, coef64, coef65, out_scale;
+  int vec_sel;              // -1 none, 0: vec[0:64), 1: vec[64:128)
+  const bf16* X;
+  const bf16* Y;
+  const float* partial;     // (BH, N, 64) fp32 intra-segment partial (nullable)
+  const float* gden;        // (BH, N) fp32: divide rows by it (forward) (nullable)
+  bf16* out;
+  const uint8_t* state;
+};
+
+constexpr int A_STAGES = 6;
+constexpr int A_SMEM = A_STAGES * 8192 + 1024 + 1024;
+
+__device__ __forceinline__ void load_row64(const bf16* base, size_t row, bool valid, uint32_t* r) {
+  const uint4* src = reinterpret_cast<const uint4*>(base + row * 64);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    uint4 v = valid ? __ldg(src + i) : make_uint4(0, 0, 0, 0);
+    r[4 * i] = v.x, r[4 * i + 1] = v.y, r[4 * i + 2] = v.z, r[4 * i + 3] = v.w;
+  }
+}
+
+__global__ void __launch_bounds__(640, 1)
+apply_kernel(const __grid_constant__ CUtensorMap tmS, const ApplyParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A_STAGES * 8192);
+  uint64_t* full = bars;            // [6]
+  uint64_t* empty = bars + 6;       // [6]
+  uint64_t* a_full = bars + 12;     // [4][2]
+  uint64_t* a_empty = bars + 20;    // [4][2]
+  uint64_t* acc_full = bars + 28;   // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
+  float* vec_s = reinterpret_cast<float*>(bars + 32);  // [64]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int bh = blockIdx.y;
+  const int t0 = blockIdx.x * APPLY_TOK;
+  const int seg = t0 / P.L;
+  const bool has_state = !P.causal || (P.state_reverse ? seg < P.nseg - 1 : seg > 0);
+  const int rec_idx = P.causal ? bh * P.nseg + seg : bh;
+  const int s_begin = P.p == 2 ? 0 : 64;
+  const int s_end = P.use65 ? 66 : 65;
+  const int nslab = s_end - s_begin;
+
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  if (tid == 0) {
+    for (int i = 0; i < A_STAGES; ++i) mbar_init(&full[i], 1), mbar_init(&empty[i], 1);
+    for (int i = 0; i < 8; ++i) mbar_init(&a_full[i], 128), mbar_init(&a_empty[i], 1);
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmS);
+  }
+  if (tid >= 64 && tid < 128) {
+    float v = 0.f;
+    if (has_state && P.vec_sel >= 0)
+      v = reinterpret_cast<const float*>(P.state + (size_t)rec_idx * REC_BYTES + VEC_OFF)[P.vec_sel * 64 + tid - 64];
+    vec_s[tid - 64] = v;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0 && has_state) {
+      for (int n = 0; n < nslab; ++n) {
+        const int st = n % A_STAGES, ph = (n / A_STAGES) & 1;
+        mbar_wait(&empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&full[st], 8192);
+        tma_load_3d(smem + st * 8192, &tmS, &full[st], 0, (s_begin + n) * 64, rec_idx);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && has_state) {
+      const uint32_t idesc = make_idesc_bf16(128, 64, false, !P.b_kmajor);
+      for (int n = 0; n < nslab; ++n) {
+        const int st = n % A_STAGES, ph = (n / A_STAGES) & 1;
+        mbar_wait(&full[st], ph);
+        tc_fence_after();
+        const uint32_t sb = smem_u32(smem + st * 8192);
+        const uint64_t bd = P.b_kmajor ? desc_kmajor_sw128(sb) : desc_mnmajor_sw128(sb, 8192);
+        const uint32_t kstep = P.b_kmajor ? 2 : 128;
+        const int buf = n & 1, use = n >> 1;
+#pragma unroll 1
+        for (int t = 0; t < 4; ++t) {
+          mbar_wait(&a_full[t * 2 + buf], use & 1);
+          tc_fence_after();
+          const uint32_t a_t = tmem + 256 + (t * 2 + buf) * 32;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) umma_ts(tmem + 64 * t, a_t + kk * 8, bd + kk * kstep, idesc, (n | kk) != 0);
+          umma_commit(&a_empty[t * 2 + buf]);
+        }
+        umma_commit(&empty[st]);
+      }
+      umma_commit(acc_full);
+    }
+  } else if (warp >= 4) {
+    // ---------------------------------------------------------------- generators + epilogue
+    const int t = (warp - 4) >> 2, q = warp & 3;
+    const int i = t0 + 128 * t + 32 * q + lane;   // token row of this thread
+    const bool valid = i < P.N;
+    const size_t grow = (size_t)bh * P.N + i;
+    const uint32_t lane_addr = tmem + ((uint32_t)(32 * q) << 16);
+    if (has_state) {
+      // Y row lives in registers; X is re-read two features at a time through L1 (a runtime-indexed
+      // register array would be demoted to local memory)
+      uint32_t yr[32];
+      load_row64(P.Y, grow, valid, yr);
+      const uint32_t* xrow = reinterpret_cast<const uint32_t*>(P.X + (valid ? grow : 0) * 64);
+      const uint32_t creg = pack_bf16x2(P.coef_reg, P.coef_reg);
+      const uint32_t c64 = pack_bf16x2(P.coef64, P.coef64);
+#pragma unroll 1
+      for (int n = 0; n < nslab; ++n) {
+        const int s = s_begin + n, buf = n & 1, use = n >> 1;
+        // scalar of this slab (bf16x2, both halves equal); slab 65 multiplies the X row itself
+        uint32_t xs;
+        if (s < 64) {
+          const uint32_t xw = valid ? __ldg(xrow + (s >> 1)) : 0u;
+          xs = (s & 1) ? __byte_perm(xw, 0, 0x3232) : __byte_perm(xw, 0, 0x1010);
+          xs = mul_bf16x2(xs, creg);
+        } else {
+          xs = s == 64 ? c64 : pack_bf16x2(P.coef65, P.coef65);
+        }
+        mbar_wait(&a_empty[t * 2 + buf], (use & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t a_dst = lane_addr + 256 + (t * 2 + buf) * 32;
+        if (s != 65) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t a[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) a[j] = mul_bf16x2(xs, yr[16 * h + j]);
+            tmem_st16(a_dst + 16 * h, a);
+          }
+        } else {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t a[16];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 xv = valid ? __ldg(reinterpret_cast<const uint4*>(xrow) + 4 * h + j) : make_uint4(0, 0, 0, 0);
+              a[4 * j] = mul_bf16x2(xs, xv.x), a[4 * j + 1] = mul_bf16x2(xs, xv.y);
+              a[4 * j + 2] = mul_bf16x2(xs, xv.z), a[4 * j + 3] = mul_bf16x2(xs, xv.w);
+            }
+            tmem_st16(a_dst + 16 * h, a);
+          }
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(&a_full[t * 2 + buf]);
+      }
+      mbar_wait(acc_full, 0);
+      tc_fence_after();
+    }
+    float scale = P.out_scale;
+    if (valid && P.gden) scale *= 1.f / P.gden[grow];
+    const float4* part = P.partial ? reinterpret_cast<const float4*>(P.partial + grow * 64) : nullptr;
+    uint4* dst = reinterpret_cast<uint4*>(P.out + grow * 64);
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+      uint32_t v[32];
+      if (has_state) {
+        tmem_ld32(lane_addr + 64 * t + 32 * h, v);   // warp-collective: every lane takes part
+        tmem_wait_ld();
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) v[c] = 0u;
+      }
+      if (valid) {
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) {
+          float r[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) r[j] = __uint_as_float(v[8 * c8 + j]) + vec_s[32 * h + 8 * c8 + j];
+          if (part) {
+            float4 p0 = __ldg(part + 8 * h + 2 * c8), p1 = __ldg(part + 8 * h + 2 * c8 + 1);
+            r[0] += p0.x, r[1] += p0.y, r[2] += p0.z, r[3] += p0.w;
+            r[4] += p1.x, r[5] += p1.y, r[6] += p1.z, r[7] += p1.w;
+          }
+          uint4 o;
+          o.x = pack_bf16x2(r[0] * scale, r[1] * scale);
+          o.y = pack_bf16x2(r[2] * scale, r[3] * scale);
+          o.z = pack_bf16x2(r[4] * scale, r[5] * scale);
+          o.w = pack_bf16x2(r[6] * scale, r[7] * scale);
+          dst[4 * h + c8] = o;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+// =============================================================================================
+// norm terms: the normaliser column of the state applied on CUDA cores (1/65 of the work).
+//   forward : g_i (+)= count + a q.N1 + (a^2/2) q^T N2 q                 (fastmax.py:304-322)
+//   dq      : part_i[l] -= dlt_i ( N1[l] + a (N2 q)[l] )                 (z2, z4 of fastmax.py:457-477)
+// One warp per row; N2 (fp32, 16 KiB) staged in shared memory per CTA (rows of one segment).
+// =============================================================================================
+struct NormParams {
+  int N, L, nseg, causal, p, mode /*0 fwd, 1 dq*/, accumulate;
+  float a;
+  const bf16* Q;
+  const float* dlt;       // (BH,N) dq mode
+  float* g;               // fwd mode: (BH,N)
+  float* part;            // dq mode: (BH,N,64)
+  const uint8_t* state;   // forward-direction records
+};
+
+__global__ void __launch_bounds__(256) norm_kernel(const NormParams P) {
+  __shared__ float n2[64][65];
+  __shared__ float n1[64];
+  const int bh = blockIdx.y;
+  const int r0 = blockIdx.x * 64;          // 64 rows per CTA, all in one segment (L % 64 == 0)
+  const int seg = r0 / P.L;
+  const bool has_state = !P.causal || seg > 0;
+  if (!has_state) return;                   // uniform per CTA
+  const float* vec = reinterpret_cast<const float*>(P.state + (size_t)(P.causal ? bh * P.nseg + seg : bh) * REC_BYTES + VEC_OFF);
+  for (int idx = threadIdx.x; idx < 4096; idx += 256) n2[idx >> 6][idx & 63] = P.p == 2 ? vec[128 + idx] : 0.f;
+  if (threadIdx.x < 64) n1[threadIdx.x] = vec[64 + threadIdx.x];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float count = P.causal ? (float)(seg * P.L) : (float)P.N;
+  for (int r = warp; r < 64; r += 8) {
+    const int i = r0 + r;
+    if (i >= P.N) break;
+    const size_t grow = (size_t)bh * P.N + i;
+    const float q0 = __bfloat162float(P.Q[grow * 64 + lane]), q1 = __bfloat162float(P.Q[grow * 64 + lane + 32]);
+    // w[l] = sum_m N2[l][m] q[m] for l = lane, lane+32
+    float w0 = 0.f, w1 = 0.f;
+    if (P.p == 2) {
+      for (int m = 0; m < 32; ++m) {
+        const float qa = __shfl_sync(0xffffffffu, q0, m), qb = __shfl_sync(0xffffffffu, q1, m);
+        w0 = fmaf(n2[lane][m], qa, fmaf(n2[lane][m + 32], qb, w0));
+        w1 = fmaf(n2[lane + 32][m], qa, fmaf(n2[lane + 32][m + 32], qb, w1));
+      }
+    }
+    if (P.mode == 0) {
+      float s = P.a * (q0 * n1[lane] + q1 * n1[lane + 32]) + 0.5f * P.a * P.a * (q0 * w0 + q1 * w1);
+#pragma unroll
+      for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) P.g[grow] = (P.accumulate ? P.g[grow] : 0.f) + count + s;
+    } else {
+      const float d = P.dlt[grow];
+      float* pr = P.part + grow * 64;
+      const float b0 = P.accumulate ? pr[lane] : 0.f, b1 = P.accumulate ? pr[lane + 32] : 0.f;
+      pr[lane] = b0 - d * (n1[lane] + P.a * w0);
+      pr[lane + 32] = b1 - d * (n1[lane + 32] + P.a * w1);
+    }
+  }
+}
+
+// =============================================================================================
+// backward prep: u = do/g (bf16), dlt = (do.o)/g (fp32), qd = -dlt*q (bf16).  HBM-bound pass.
+// =============================================================================================
+__global__ void __launch_bounds__(256) prep_bwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ o,
+                                                        const bf16* __restrict__ d_o, const float* __restrict__ g,
+                                                        bf16* __restrict__ u, float* __restrict__ dlt,
+                                                        bf16* __restrict__ qd, size_t rows) {
+  const size_t row = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float ig = 1.f / g[row];
+  const __nv_bfloat162 dv = reinterpret_cast<const __nv_bfloat162*>(d_o + row * 64)[lane];
+  const __nv_bfloat162 ov = reinterpret_cast<const __nv_bfloat162*>(o + row * 64)[lane];
+  const __nv_bfloat162 qv = reinterpret_cast<const __nv_bfloat162*>(q + row * 64)[lane];
+  const float d0 = __low2float(dv), d1 = __high2float(dv);
+  float s = d0 * __low2float(ov) + d1 * __high2float(ov);
+#pragma unroll
+  for (int x = 16; x; x >>= 1) s += __shfl_xor_sync(0xffffffffu, s, x);
+  const float dl = s * ig;
+  reinterpret_cast<__nv_bfloat162*>(u + row * 64)[lane] = __floats2bfloat162_rn(d0 * ig, d1 * ig);
+  reinterpret_cast<__nv_bfloat162*>(qd + row * 64)[lane] =
+      __floats2bfloat162_rn(-dl * __low2float(qv), -dl * __high2float(qv));
+  if (lane == 0) dlt[row] = dl;
+}
+
+}  // namespace mom
+
+// =============================================================================================
+// host orchestration
+// =============================================================================================
+using namespace mom;
+
+struct MomLayout {
+  int BH, N, Npad, L, nseg, nrec;
+  size_t off_xt, off_xt2, off_state, off_state2, off_part, off_part2, off_part3, off_u, off_qd, off_dlt, total;
+};
+
+static MomLayout mom_layout(int B, int H, int N, int L, int causal, bool bwd) {
+  MomLayout m{};
+  m.BH = B * H, m.N = N, m.Npad = (int)align_up(N, 64), m.L = L;
+  m.nseg = (N + L - 1) / L;
+  m.nrec = causal ? m.nseg : 1;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += align_up(bytes, 1024);
+    return o;
+  };
+  const size_t tens = (size_t)m.BH * N * 64;
+  m.off_xt = take((size_t)m.BH * 64 * m.Npad * 2);
+  m.off_state = take((size_t)m.BH * m.nrec * REC_BYTES);
+  m.off_part = take(tens * 4);
+  if (bwd) {
+    m.off_xt2 = take((size_t)m.BH * 64 * m.Npad * 2);
+    m.off_state2 = take((size_t)m.BH * m.nrec * REC_BYTES);
+    m.off_part2 = take(tens * 4);
+    m.off_part3 = take(tens * 4);
+    m.off_u = take(tens * 2);
+    m.off_qd = take(tens * 2);
+    m.off_dlt = take((size_t)m.BH * N * 4);
+  }
+  m.total = off;
+  return m;
+}
+
+int moments_seg_len(int N) {
+  int L = 512;
+  while ((long long)L * 64 < N) L *= 2;   // keep <= 64 boundary states per sequence
+  return L;
+}
+
+size_t moments_workspace_bytes(int B, int H, int N, int causal, bool bwd) {
+  return mom_layout(B, H, N, moments_seg_len(N), causal, bwd).total;
+}
+
+static int launch_transpose(const Problem& pb, const void* in, void* out, int Npad) {
+  dim3 grid(Npad / 64, pb.B * pb.H);
+  FM_LAUNCH("mom_transpose", pb.stream,
+            transpose_kernel<<<grid, 256, 0, pb.stream>>>((const bf16*)in, (bf16*)out, pb.N, Npad));
+  return FASTMAX_OK;
+}
+
+static int launch_build(const Problem& pb, const MomLayout& m, const void* xt, const void* w, const void* w2,
+                        uint8_t* state, int reverse) {
+  CUtensorMap tmXT, tmW, tmW2;
+  int rc;
+  if ((rc = make_tmap_bf16_3d(&tmXT, xt, m.Npad, 64, m.BH, (uint64_t)m.Npad * 2, (uint64_t)m.Npad * 128, 64, 64))) return rc;
+  if ((rc = make_tmap_bf16_3d(&tmW, w, 64, m.N, m.BH, 128, (uint64_t)m.N * 128, 64, 64))) return rc;
+  if ((rc = make_tmap_bf16_3d(&tmW2, w2, 64, m.N, m.BH, 128, (uint64_t)m.N * 128, 64, 64))) return rc;
+  BuildParams P{};
+  P.N = m.N, P.nblk = (m.N + 63) / 64, P.Lb = m.L / 64, P.nseg = m.nseg, P.reverse = reverse, P.causal = pb.causal;
+  P.p = pb.p, P.state = state;
+  if (!pb.causal) P.nproc = P.nblk;
+  else if (reverse) P.nproc = P.nblk - P.Lb;
+  else P.nproc = (m.nseg - 1) * P.Lb;
+  if (P.nproc <= 0) return FASTMAX_OK;   // single segment: no boundary state needed
+  FM_CUDA(cudaFuncSetAttribute(build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
+  dim3 grid(pb.p == 2 ? 5 : 1, m.BH);
+  FM_LAUNCH(reverse ? "mom_build_rev" : "mom_build", pb.stream,
+            build_kernel<<<grid, 512, B_SMEM, pb.stream>>>(tmXT, tmW, tmW2, P));
+  return FASTMAX_OK;
+}
+
+static int launch_apply(const Problem& pb, const MomLayout& m, const char* name, ApplyParams P) {
+  CUtensorMap tmS;
+  int rc;
+  if ((rc = make_tmap_bf16_3d(&tmS, P.state, 64, NSLAB * 64, (uint64_t)m.BH * m.nrec, 128, REC_BYTES, 64, 64))) return rc;
+  P.N = m.N, P.L = m.L, P.nseg = m.nseg, P.causal = pb.causal, P.p = pb.p;
+  FM_CUDA(cudaFuncSetAttribute(apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A_SMEM));
+  dim3 grid((m.N + APPLY_TOK - 1) / APPLY_TOK, m.BH);
+  FM_LAUNCH(name, pb.stream, apply_kernel<<<grid, 640, A_SMEM, pb.stream>>>(tmS, P));
+  return FASTMAX_OK;
+}
+
+static int launch_norm(const Problem& pb, const MomLayout& m, NormParams P) {
+  P.N = m.N, P.L = m.L, P.nseg = m.nseg, P.causal = pb.causal, P.p = pb.p, P.a = pb.inv_c;
+  dim3 grid((m.N + 63) / 64, m.BH);
+  FM_LAUNCH(P.mode == 0 ? "mom_norm_fwd" : "mom_norm_dq", pb.stream, norm_kernel<<<grid, 256, 0, pb.stream>>>(P));
+  return FASTMAX_OK;
+}
+
+int moments_fwd(const Problem& pb, const void* q, const void* k, const void* v, void* o, float* g, void* ws) {
+  const MomLayout m = mom_layout(pb.B, pb.H, pb.N, moments_seg_len(pb.N), pb.causal, false);
+  uint8_t* w8 = (uint8_t*)ws;
+  int rc;
+  const float a = pb.inv_c;
+  uint8_t* state = w8 + m.off_state;
+  float* part = (float*)(w8 + m.off_part);
+  // 1. K^T and the boundary states (forward direction)
+  if ((rc = launch_transpose(pb, k, w8 + m.off_xt, m.Npad))) return rc;
+  if ((rc = launch_build(pb, m, w8 + m.off_xt, v, k, state, 0))) return rc;
+  // 2. intra-segment part (causal only) and the normaliser
+  if (pb.causal) {
+    if ((rc = exact_fwd_partial(pb, q, k, v, m.L, part, g))) return rc;
+  }
+  NormParams np{};
+  np.mode = 0, np.accumulate = pb.causal, np.Q = (const bf16*)q, np.g = g, np.state = state;
+  if ((rc = launch_norm(pb, m, np))) return rc;
+  // 3. inter-segment part + normalisation
+  ApplyParams ap{};
+  ap.mode = APPLY_FWD, ap.state_reverse = 0, ap.b_kmajor = 0, ap.use65 = 0;
+  ap.coef_reg = 0.5f * a * a, ap.coef64 = a, ap.coef65 = 0.f, ap.out_scale = 1.f, ap.vec_sel = 0;
+  ap.X = (const bf16*)q, ap.Y = (const bf16*)q, ap.partial = pb.causal ? part : nullptr, ap.gden = g;
+  ap.out = (bf16*)o, ap.state = state;
+  return launch_apply(pb, m, "mom_apply_fwd", ap);
+}
+
+int moments_bwd(const Problem& pb, const void* q, const void* k, const void* v, const void* o, const float* g,
+                const void* d_o, void* dq, void* dk, void* dv, void* ws) {
+  const MomLayout m = mom_layout(pb.B, pb.H, pb.N, moments_seg_len(pb.N), pb.causal, true);
+  uint8_t* w8 = (uint8_t*)ws;
+  int rc;
+  const float a = pb.inv_c;
+  uint8_t* S = w8 + m.off_state;
+  uint8_t* R = w8 + m.off_state2;
+  float* dq_part = (float*)(w8 + m.off_part);
+  float* dk_part = (float*)(w8 + m.off_part2);
+  float* dv_part = (float*)(w8 + m.off_part3);
+  bf16* u = (bf16*)(w8 + m.off_u);
+  bf16* qd = (bf16*)(w8 + m.off_qd);
+  float* dlt = (float*)(w8 + m.off_dlt);
+  const size_t rows = (size_t)m.BH * m.N;
+  // 1. u = do/g, dlt = (do.o)/g, qd = -dlt*q
+  FM_LAUNCH("mom_prep_bwd", pb.stream,
+            prep_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, pb.stream>>>((const bf16*)q, (const bf16*)o,
+                                                                                (const bf16*)d_o, g, u, dlt, qd, rows));
+  // 2. forward-direction states of (k, v) (recomputed, not saved) and reverse-direction states of (q, u)
+  if ((rc = launch_transpose(pb, k, w8 + m.off_xt, m.Npad))) return rc;
+  if ((rc = launch_build(pb, m, w8 + m.off_xt, v, k, S, 0))) return rc;
+  if ((rc = launch_transpose(pb, q, w8 + m.off_xt2, m.Npad))) return rc;
+  if ((rc = launch_build(pb, m, w8 + m.off_xt2, u, qd, R, 1))) return rc;
+  // 3. intra-segment partials
+  if (pb.causal) {
+    if ((rc = exact_bwd_partial(pb, q, k, v, o, g, d_o, m.L, dq_part, dk_part, dv_part))) return rc;
+  }
+  NormParams np{};
+  np.mode = 1, np.accumulate = pb.causal, np.Q = (const bf16*)q, np.dlt = dlt, np.part = dq_part, np.state = S;
+  if ((rc = launch_norm(pb, m, np))) return rc;
+  // 4. inter-segment parts
+  ApplyParams ap{};
+  ap.mode = APPLY_DQ, ap.state_reverse = 0, ap.b_kmajor = 1, ap.use65 = 0;
+  ap.coef_reg = a, ap.coef64 = 1.f, ap.coef65 = 0.f, ap.out_scale = a, ap.vec_sel = -1;
+  ap.X = (const bf16*)q, ap.Y = u, ap.partial = dq_part, ap.gden = nullptr, ap.out = (bf16*)dq, ap.state = S;
+  if (!pb.causal) {
+    // non-causal: the norm kernel wrote every row of dq_part (accumulate = 0)
+  }
+  if ((rc = launch_apply(pb, m, "mom_apply_dq", ap))) return rc;
+
+  ap = ApplyParams{};
+  ap.mode = APPLY_DV, ap.state_reverse = 1, ap.b_kmajor = 0, ap.use65 = 0;
+  ap.coef_reg = 0.5f * a * a, ap.coef64 = a, ap.coef65 = 0.f, ap.out_scale = 1.f, ap.vec_sel = 0;
+  ap.X = (const bf16*)k, ap.Y = (const bf16*)k, ap.partial = pb.causal ? dv_part : nullptr, ap.gden = nullptr;
+  ap.out = (bf16*)dv, ap.state = R;
+  if ((rc = launch_apply(pb, m, "mom_apply_dv", ap))) return rc;
+
+  ap = ApplyParams{};
+  ap.mode = APPLY_DK, ap.state_reverse = 1, ap.b_kmajor = 1, ap.use65 = 1;
+  ap.coef_reg = a, ap.coef64 = 1.f, ap.coef65 = a, ap.out_scale = a, ap.vec_sel = 1;
+  ap.X = (const bf16*)k, ap.Y = (const bf16*)v, ap.partial = pb.causal ? dk_part : nullptr, ap.gden = nullptr;
+  ap.out = (bf16*)dk, ap.state = R;
+  return launch_apply(pb, m, "mom_apply_dk", ap);
+}
+
+// executed tensor-core flops of the plan (for the utilisation report; never the algorithmic count)
+void moments_flops(int B, int H, int N, int p, int causal, double* fwd, double* bwd) {
+  const int L = moments_seg_len(N);
+  const MomLayout m = mom_layout(B, H, N, L, causal, false);
+  const double mma = 2.0 * 128 * 64 * 16;
+  const int nblk = (N + 63) / 64, Lb = L / 64;
+  const double acc = p == 2 ? 34 : 2;
+  const double nproc_f = causal ? (double)(m.nseg - 1) * Lb : nblk;
+  const double nproc_r = causal ? (double)(nblk - Lb) : nblk;
+  const double build_f = m.BH * (nproc_f > 0 ? nproc_f : 0) * acc * 4 * mma;
+  const double build_r = m.BH * (nproc_r > 0 ? nproc_r : 0) * acc * 4 * mma;
+  const double ctas = (double)((N + APPLY_TOK - 1) / APPLY_TOK);
+  const double with_state = causal ? (ctas - (double)L / APPLY_TOK > 0 ? ctas - (double)L / APPLY_TOK : 0) : ctas;
+  const double slabs = p == 2 ? 65 : 1;
+  const double apply = m.BH * with_state * slabs * 16 * mma;
+  *fwd = build_f + apply;
+  *bwd = build_f + build_r + 3 * apply + m.BH * with_state * 16 * mma /*slab 65 of dk*/;
+}
+
+}  // namespace fm

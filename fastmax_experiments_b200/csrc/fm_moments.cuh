@@ -1,0 +1,35 @@
+// fm_moments.cuh -- layout of the moment-state records shared by the build / apply / norm kernels.
+//
+// FastMax p=2 factorises  sum_j f(q.k_j/c) v'_j  (v' = [v, 1]) over the running moments
+//   S0 = sum v'_j,  S1 = sum k_j (x) v'_j,  S2 = sum k_j (x) k_j (x) v'_j        
+// One *state record* holds these for one (b,h) at one segment boundary (exclusive prefix of the
+// tokens before the segment, or exclusive suffix for the reverse scan of the backward pass):
+//
+//   slab x in [0,64):  bf16 [y][a]  = sum X[x] Y[y] W[a]      (S2; forward: X=Y=k, W=v)
+//   slab 64:           bf16 [y][a]  = sum Y[y] W[a]           (S1)
+//   slab 65:           bf16 [y][x'] = sum Y[y] W2[x']         (normaliser part of S2; fwd: W2=k)
+//   vec  fp32: [0,64)   = sum W[a]     (S0 value part)
+//              [64,128) = sum W2[x']   (normaliser part of S1)
+//              [128, 128+4096) = fp32 copy of slab 65
+// Each slab is a 64x64 bf16 row-major tile (128-byte rows) so one TMA box with 128B swizzle
+// brings it to shared memory as a canonical UMMA B operand -- MN-major when the contraction
+// runs over y (forward o, dv) and K-major when it runs over a (dq, dk).
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+namespace fm {
+namespace mom {
+
+constexpr int D = 64;                       // head size of the tcgen05 path
+constexpr int NSLAB = 66;
+constexpr size_t SLAB_BYTES = 64 * 64 * 2;  // 8 KiB
+constexpr size_t VEC_OFF = NSLAB * SLAB_BYTES;
+constexpr int VEC_FLOATS = 128 + 64 * 64;
+constexpr size_t REC_BYTES = ((VEC_OFF + VEC_FLOATS * 4 + 1023) / 1024) * 1024;
+constexpr int TILE_TOK = 128;               // rows of one MMA tile
+constexpr int APPLY_TOK = 512;              // tokens per apply CTA (4 tiles)
+constexpr int BLK_TOK = 64;                 // tokens per build step
+
+}  // namespace mom
+}  // namespace fm
