@@ -1,0 +1,366 @@
+// fm_intra.cu -- intra-segment part of the FastMax chunked scan on tcgen05 (bf16, D = 64).
+//
+// Inside one segment the causal polynomial scores are evaluated directly, flash-attention style
+// but with no running max / exp: P = f(Q K^T / c) o mask needs only two FMAs per score.
+//
+//   MODE_FWD : O_i  += f(S) V_j ,  g_i += rowsum f(S)          S = Q_i K_j^T
+//   MODE_DQ  : dQ_i += E K_j ,     E = f'(S) o (U_i V_j^T - dlt_i)           (unscaled by 1/c)
+//   MODE_DKDV: dV_j += P'^T-form:  P' = f(S') , E' = f'(S') o (V_j U_i^T - dlt_i),  S' = K_j Q_i^T
+//              dV_j += P' U_i ,  dK_j += E' Q_i                               (dK unscaled by 1/c)
+//
+// with U = dO/g, dlt = (dO.O)/g (fm_moments.cu prep kernel).  These are the j-in-segment terms of
+// compute_F_masked / compute_g_masked (fastmax.py:219-322) and gradient_o_{q,k,v}_masked
+// (fastmax.py:433-691); the out-of-segment terms come from the moment states.
+//
+// One CTA owns four 128-row output tiles (two for DKDV) of one (b,h) and streams 64-token tiles of
+// the other operand pair through a TMA ring.  Two compute warpgroups each own half of the output
+// tiles; per (output tile, stream tile) pair a warpgroup's elected thread issues the score MMAs
+// (operands from shared memory) into tensor memory, the 128 threads read their score row, apply the
+// polynomial + mask, write the bf16 result back to tensor memory as the A operand, and the elected
+// thread issues the second MMAs that accumulate into the output tile's fp32 accumulator.
+// Outputs are fp32 partials in the workspace (the apply kernel adds the moment part).
+#include "fm_common.cuh"
+#include "fm_sm100.cuh"
+#include "fm_moments.cuh"
+
+namespace fm {
+namespace mom {
+using namespace sm100;
+typedef __nv_bfloat16 bf16;
+
+enum IntraMode { INTRA_FWD = 0, INTRA_DQ = 1, INTRA_DKDV = 2 };
+
+struct IntraParams {
+  int N, Npad, L, p;
+  float a;                 // 1/c
+  const float* dlt;        // (BH, Npad) fp32, zero padded
+  float* out0;             // FWD: O partial; DQ: dQ partial; DKDV: dV partial   (BH,N,64) fp32
+  float* out1;             // DKDV: dK partial
+  float* g;                // FWD: partial normaliser (BH,N)
+};
+
+template <int MODE> struct IntraCfg {
+  static constexpr int OUT_TILES = MODE == INTRA_DKDV ? 2 : 4;
+  static constexpr int RES_OPS = MODE == INTRA_FWD ? 1 : 2;      // resident operand tensors
+  static constexpr int STAGES = MODE == INTRA_DQ ? 4 : 6;
+  static constexpr int STAGE_BYTES = 2 * 8192 + (MODE == INTRA_DKDV ? 256 : 0);
+  static constexpr int STAGE_STRIDE = 2 * 8192 + 1024;            // keeps every tile 1024-aligned
+  static constexpr int RES_BYTES = OUT_TILES * RES_OPS * 16384;
+  static constexpr int SMEM = RES_BYTES + STAGES * STAGE_STRIDE + 1024 + 1024;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(384, 1)
+intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ CUtensorMap tmR2,
+             const __grid_constant__ CUtensorMap tmT1, const __grid_constant__ CUtensorMap tmT2, const IntraParams P) {
+  using C = IntraCfg<MODE>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* res = smem;                         // [RES_OPS][OUT_TILES][16 KiB]
+  uint8_t* ring = smem + C::RES_BYTES;         // STAGES x (T1 8 KiB | T2 8 KiB | dlt 256 B)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + C::STAGES * C::STAGE_STRIDE);
+  uint64_t* full = bars;              // [STAGES]
+  uint64_t* empty = bars + 8;         // [STAGES]   count 2 (one arrival per warpgroup)
+  uint64_t* res_full = bars + 16;     // [1]
+  uint64_t* s_full = bars + 17;       // [2] score tile of warpgroup w is in tensor memory
+  uint64_t* s_free = bars + 19;       // [2] second MMAs of the previous pair have drained the buffer
+  uint64_t* acc_done = bars + 21;     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int bh = blockIdx.y;
+  constexpr int CT = C::OUT_TILES * 128;       // tokens of the output chunk
+  const int c0 = blockIdx.x * CT;              // first output row of the CTA
+  const int seg_start = (c0 / P.L) * P.L;
+  const int seg_end = min(seg_start + P.L, P.N);
+  // stream range (absolute token index of the first stream tile, number of 64-token tiles)
+  const int st0 = MODE == INTRA_DKDV ? c0 : seg_start;
+  const int st1 = MODE == INTRA_DKDV ? seg_end : min(c0 + CT, P.N);
+  const int nstream = (st1 - st0 + 63) / 64;
+
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  if (tid == 0) {
+    for (int i = 0; i < C::STAGES; ++i) mbar_init(&full[i], 1), mbar_init(&empty[i], 2);
+    mbar_init(res_full, 1);
+    for (int i = 0; i < 2; ++i) mbar_init(&s_full[i], 1), mbar_init(&s_free[i], 1), mbar_init(&acc_done[i], 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmR1);
+    tma_prefetch_desc(&tmT1);
+    tma_prefetch_desc(&tmT2);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      mbar_arrive_expect_tx(res_full, C::RES_BYTES);
+      for (int o = 0; o < C::OUT_TILES; ++o)
+        for (int h = 0; h < 2; ++h) {
+          tma_load_3d(res + o * 16384 + h * 8192, &tmR1, res_full, 0, c0 + o * 128 + h * 64, bh);
+          if (C::RES_OPS == 2)
+            tma_load_3d(res + (C::OUT_TILES + o) * 16384 + h * 8192, &tmR2, res_full, 0, c0 + o * 128 + h * 64, bh);
+        }
+      for (int jt = 0; jt < nstream; ++jt) {
+        const int st = jt % C::STAGES, ph = (jt / C::STAGES) & 1;
+        mbar_wait(&empty[st], ph ^ 1);
+        uint8_t* sp = ring + st * C::STAGE_STRIDE;
+        mbar_arrive_expect_tx(&full[st], C::STAGE_BYTES);
+        tma_load_3d(sp, &tmT1, &full[st], 0, st0 + jt * 64, bh);
+        tma_load_3d(sp + 8192, &tmT2, &full[st], 0, st0 + jt * 64, bh);
+        if (MODE == INTRA_DKDV) {
+          const float* src = P.dlt + (size_t)bh * P.Npad + st0 + jt * 64;
+          asm volatile(
+              "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                  smem_u32(sp + 16384)),
+              "l"(src), "r"(256), "r"(smem_u32(&full[st]))
+              : "memory");
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------------------------------------------------------- compute warpgroups
+    const int w = (warp - 4) >> 2, q = warp & 3;
+    const bool issuer = (warp & 3) == 0 && lane == 0;
+    const int rloc = 32 * q + lane;                        // row inside a 128-row output tile
+    const uint32_t lane_addr = tmem + ((uint32_t)(32 * q) << 16);
+    const uint32_t sbuf = lane_addr + 256 + 128 * w;      // score buffer of this warpgroup (128 cols)
+    // output tiles of this warpgroup
+    int otile[2];
+    int n_ot;
+    if (MODE == INTRA_DKDV) otile[0] = w, otile[1] = -1, n_ot = 1;
+    else otile[0] = w == 0 ? 0 : 1, otile[1] = w == 0 ? 3 : 2, n_ot = 2;
+
+    const float a = P.a, c2 = 0.5f * P.a * P.a;
+    float gsum[2] = {0.f, 0.f};
+    float dlt_row[2] = {0.f, 0.f};
+    if constexpr (MODE == INTRA_DQ) {
+#pragma unroll
+      for (int x = 0; x < 2; ++x) {
+        const int r = c0 + otile[x] * 128 + rloc;
+        dlt_row[x] = r < P.N ? P.dlt[(size_t)bh * P.Npad + r] : 0.f;
+      }
+    }
+    const uint32_t id_kk = make_idesc_bf16(128, 64, false, false);
+    const uint32_t id_kn = make_idesc_bf16(128, 64, false, true);
+
+    mbar_wait(res_full, 0);
+    int npair = 0;
+    for (int jt = 0; jt < nstream; ++jt) {
+      const int st = jt % C::STAGES, ph = (jt / C::STAGES) & 1;
+      const int ts = st0 + jt * 64;                       // absolute index of the first stream token
+      uint8_t* sp = ring + st * C::STAGE_STRIDE;
+      bool used = false;
+#pragma unroll
+      for (int x = 0; x < 2; ++x) {
+        if (x >= n_ot) break;
+        const int o = otile[x];
+        const int ob = c0 + o * 128;                      // first row of the output tile
+        // does output tile o interact with this stream tile?
+        bool need;
+        if (MODE == INTRA_DKDV) need = ts + 63 >= ob;     // query tile reaches the key tile
+        else need = ts <= ob + 127;                       // key tile starts at or before the last row
+        if (ob >= P.N) need = false;
+        if (!need) continue;
+        if (!used) {
+          mbar_wait(&full[st], ph);
+          used = true;
+        }
+        // ---- score MMAs: S = R1_o . T1^T  (and dP = R2_o . T2^T)
+        if (issuer) {
+          if (npair > 0) mbar_wait(&s_free[w], (npair - 1) & 1);
+          tc_fence_after();
+          const uint64_t dA1 = desc_kmajor_sw128(smem_u32(res + o * 16384));
+          const uint64_t dB1 = desc_kmajor_sw128(smem_u32(sp));
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) umma_ss(tmem + 256 + 128 * w, dA1 + kk * 2, dB1 + kk * 2, id_kk, kk > 0);
+          if constexpr (MODE != INTRA_FWD) {
+            const uint64_t dA2 = desc_kmajor_sw128(smem_u32(res + (C::OUT_TILES + o) * 16384));
+            const uint64_t dB2 = desc_kmajor_sw128(smem_u32(sp + 8192));
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_ss(tmem + 256 + 128 * w + 64, dA2 + kk * 2, dB2 + kk * 2, id_kk, kk > 0);
+          }
+          umma_commit(&s_full[w]);
+        }
+        mbar_wait(&s_full[w], npair & 1);
+        tc_fence_after();
+        // ---- polynomial on CUDA cores: thread = output row, 64 stream columns
+        const int r_abs = ob + rloc;
+        const bool diag = MODE == INTRA_DKDV ? (ts < ob + 128) : (ts + 63 > ob);   // tile needs the mask
+        uint32_t pk[32];
+        uint32_t pe[MODE == INTRA_DKDV ? 32 : 1];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t sv[32];
+          tmem_ld32(sbuf + 32 * h, sv);
+          uint32_t dv[MODE == INTRA_FWD ? 1 : 32];
+          if constexpr (MODE != INTRA_FWD) tmem_ld32(sbuf + 64 + 32 * h, dv);
+          tmem_wait_ld();
+          float dl[MODE == INTRA_DKDV ? 32 : 1];
+          if constexpr (MODE == INTRA_DKDV) {
+            const float4* dsrc = reinterpret_cast<const float4*>(sp + 16384) + 8 * h;
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4) {
+              float4 t4 = dsrc[c4];
+              dl[4 * c4] = t4.x, dl[4 * c4 + 1] = t4.y, dl[4 * c4 + 2] = t4.z, dl[4 * c4 + 3] = t4.w;
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) {
+            float r0, r1, e0 = 0.f, e1 = 0.f;
+            const float s0 = __uint_as_float(sv[c]), s1 = __uint_as_float(sv[c + 1]);
+            const int col = ts + 32 * h + c;
+            bool v0 = true, v1 = true;
+            if (diag) {
+              if constexpr (MODE == INTRA_DKDV) v0 = col >= r_abs, v1 = col + 1 >= r_abs;   // query >= key
+              else v0 = col <= r_abs, v1 = col + 1 <= r_abs;                                // key <= query
+            }
+            if constexpr (MODE == INTRA_FWD) {
+              r0 = P.p == 2 ? fmaf(s0, fmaf(c2, s0, a), 1.f) : fmaf(a, s0, 1.f);
+              r1 = P.p == 2 ? fmaf(s1, fmaf(c2, s1, a), 1.f) : fmaf(a, s1, 1.f);
+              r0 = v0 ? r0 : 0.f, r1 = v1 ? r1 : 0.f;
+              gsum[x] += r0 + r1;
+            } else if constexpr (MODE == INTRA_DQ) {
+              const float d0 = __uint_as_float(dv[c]) - dlt_row[x], d1 = __uint_as_float(dv[c + 1]) - dlt_row[x];
+              r0 = P.p == 2 ? fmaf(a, s0, 1.f) * d0 : d0;
+              r1 = P.p == 2 ? fmaf(a, s1, 1.f) * d1 : d1;
+              r0 = v0 ? r0 : 0.f, r1 = v1 ? r1 : 0.f;
+            } else {
+              const float d0 = __uint_as_float(dv[c]) - dl[c], d1 = __uint_as_float(dv[c + 1]) - dl[c + 1];
+              r0 = P.p == 2 ? fmaf(s0, fmaf(c2, s0, a), 1.f) : fmaf(a, s0, 1.f);
+              r1 = P.p == 2 ? fmaf(s1, fmaf(c2, s1, a), 1.f) : fmaf(a, s1, 1.f);
+              e0 = P.p == 2 ? fmaf(a, s0, 1.f) * d0 : d0;
+              e1 = P.p == 2 ? fmaf(a, s1, 1.f) * d1 : d1;
+              r0 = v0 ? r0 : 0.f, r1 = v1 ? r1 : 0.f;
+              e0 = v0 ? e0 : 0.f, e1 = v1 ? e1 : 0.f;
+            }
+            pk[16 * h + (c >> 1)] = pack_bf16x2(r0, r1);
+            if constexpr (MODE == INTRA_DKDV) pe[16 * h + (c >> 1)] = pack_bf16x2(e0, e1);
+          }
+        }
+        // ---- result back to tensor memory as the A operand of the accumulating MMAs
+        tmem_st32(sbuf, pk);
+        if constexpr (MODE == INTRA_DKDV) tmem_st32(sbuf + 32, pe);
+        tmem_wait_st();
+        tc_fence_before();
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + w) : "memory");
+        if (issuer) {
+          tc_fence_after();
+          const uint32_t a_t = tmem + 256 + 128 * w;
+          if constexpr (MODE == INTRA_FWD) {
+            const uint64_t dV = desc_mnmajor_sw128(smem_u32(sp + 8192), 8192);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) umma_ts(tmem + 64 * o, a_t + kk * 8, dV + kk * 128, id_kn, (jt | kk) != 0);
+          } else if constexpr (MODE == INTRA_DQ) {
+            const uint64_t dK = desc_mnmajor_sw128(smem_u32(sp), 8192);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) umma_ts(tmem + 64 * o, a_t + kk * 8, dK + kk * 128, id_kn, (jt | kk) != 0);
+          } else {
+            // first stream tile of output tile o is jt == 2*o
+            const bool first = jt == 2 * o;
+            const uint64_t dU = desc_mnmajor_sw128(smem_u32(sp + 8192), 8192);
+            const uint64_t dQ = desc_mnmajor_sw128(smem_u32(sp), 8192);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_ts(tmem + 128 * o, a_t + kk * 8, dU + kk * 128, id_kn, !(first && kk == 0));
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_ts(tmem + 128 * o + 64, a_t + 32 + kk * 8, dQ + kk * 128, id_kn, !(first && kk == 0));
+          }
+          umma_commit(&s_free[w]);
+        }
+        ++npair;
+      }
+      // release the ring stage: both warpgroups arrive, with or without work on it.  A warpgroup
+      // that skips the tile still waits for it to land first, so that its arrival cannot be counted
+      // towards the previous use of the stage.
+      if (issuer) {
+        if (used) umma_commit(&empty[st]);
+        else {
+          mbar_wait(&full[st], ph);
+          mbar_arrive(&empty[st]);
+        }
+      }
+    }
+    if (issuer) umma_commit(&acc_done[w]);
+    mbar_wait(&acc_done[w], 0);
+    tc_fence_after();
+    // ---------------------------------------------------------------- epilogue: fp32 partials
+#pragma unroll
+    for (int x = 0; x < 2; ++x) {
+      if (x >= n_ot) break;
+      const int o = otile[x];
+      const int r_abs = c0 + o * 128 + rloc;
+      const bool tile_live = c0 + o * 128 < P.N;          // warp-uniform
+      if (!tile_live) continue;
+      const size_t grow = (size_t)bh * P.N + r_abs;
+      const int nacc = MODE == INTRA_DKDV ? 2 : 1;
+      for (int a2 = 0; a2 < nacc; ++a2) {
+        float* outp = a2 == 0 ? P.out0 : P.out1;
+        const uint32_t col = MODE == INTRA_DKDV ? 128 * o + 64 * a2 : 64 * o;
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          uint32_t v[32];
+          tmem_ld32(lane_addr + col + 32 * h, v);
+          tmem_wait_ld();
+          if (r_abs < P.N) {
+            uint4* dst = reinterpret_cast<uint4*>(outp + grow * 64 + 32 * h);
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4) dst[c4] = make_uint4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+          }
+        }
+      }
+      if (MODE == INTRA_FWD && r_abs < P.N) P.g[grow] = gsum[x];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace mom
+
+using namespace mom;
+
+// R1/R2: resident operands (rows = output rows), T1/T2: streamed operands.  All (BH, N, 64) bf16.
+template <int MODE>
+static int launch_intra_t(const Problem& pb, int L, int Npad, const void* r1, const void* r2, const void* t1,
+                          const void* t2, const float* dlt, float* out0, float* out1, float* g, const char* name) {
+  using C = IntraCfg<MODE>;
+  const int BH = pb.B * pb.H;
+  CUtensorMap m[4];
+  const void* ptr[4] = {r1, r2 ? r2 : r1, t1, t2};
+  for (int i = 0; i < 4; ++i) {
+    int rc = make_tmap_bf16_3d(&m[i], ptr[i], 64, pb.N, BH, 128, (uint64_t)pb.N * 128, 64, 64);
+    if (rc) return rc;
+  }
+  IntraParams P{};
+  P.N = pb.N, P.Npad = Npad, P.L = L, P.p = pb.p, P.a = pb.inv_c, P.dlt = dlt, P.out0 = out0, P.out1 = out1, P.g = g;
+  auto kern = intra_kernel<MODE>;
+  FM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+  constexpr int CT = C::OUT_TILES * 128;
+  dim3 grid((pb.N + CT - 1) / CT, BH);
+  FM_LAUNCH(name, pb.stream, kern<<<grid, 384, C::SMEM, pb.stream>>>(m[0], m[1], m[2], m[3], P));
+  return FASTMAX_OK;
+}
+
+int intra_fwd(const Problem& pb, int L, int Npad, const void* q, const void* k, const void* v, float* o_part,
+              float* g_part) {
+  return launch_intra_t<INTRA_FWD>(pb, L, Npad, q, nullptr, k, v, nullptr, o_part, nullptr, g_part, "mom_intra_fwd");
+}
+int intra_dq(const Problem& pb, int L, int Npad, const void* q, const void* u, const void* k, const void* v,
+             const float* dlt, float* dq_part) {
+  return launch_intra_t<INTRA_DQ>(pb, L, Npad, q, u, k, v, dlt, dq_part, nullptr, nullptr, "mom_intra_dq");
+}
+int intra_dkdv(const Problem& pb, int L, int Npad, const void* k, const void* v, const void* q, const void* u,
+               const float* dlt, float* dk_part, float* dv_part) {
+  return launch_intra_t<INTRA_DKDV>(pb, L, Npad, k, v, q, u, dlt, dv_part, dk_part, nullptr, "mom_intra_dkdv");
+}
+
+}  // namespace fm

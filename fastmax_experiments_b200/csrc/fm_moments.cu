@@ -548,7 +548,7 @@ __global__ void __launch_bounds__(256) norm_kernel(const NormParams P) {
       for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
       if (lane == 0) P.g[grow] = (P.accumulate ? P.g[grow] : 0.f) + count + s;
     } else {
-      const float d = P.dlt[grow];
+      const float d = P.dlt[(size_t)bh * ((P.N + 63) / 64 * 64) + i];
       float* pr = P.part + grow * 64;
       const float b0 = P.accumulate ? pr[lane] : 0.f, b1 = P.accumulate ? pr[lane + 32] : 0.f;
       pr[lane] = b0 - d * (n1[lane] + P.a * w0);
@@ -563,7 +563,7 @@ __global__ void __launch_bounds__(256) norm_kernel(const NormParams P) {
 __global__ void __launch_bounds__(256) prep_bwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ o,
                                                         const bf16* __restrict__ d_o, const float* __restrict__ g,
                                                         bf16* __restrict__ u, float* __restrict__ dlt,
-                                                        bf16* __restrict__ qd, size_t rows) {
+                                                        bf16* __restrict__ qd, size_t rows, int N, int Npad) {
   const size_t row = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -579,7 +579,7 @@ __global__ void __launch_bounds__(256) prep_bwd_kernel(const bf16* __restrict__ 
   reinterpret_cast<__nv_bfloat162*>(u + row * 64)[lane] = __floats2bfloat162_rn(d0 * ig, d1 * ig);
   reinterpret_cast<__nv_bfloat162*>(qd + row * 64)[lane] =
       __floats2bfloat162_rn(-dl * __low2float(qv), -dl * __high2float(qv));
-  if (lane == 0) dlt[row] = dl;
+  if (lane == 0) dlt[(row / N) * Npad + row % N] = dl;   // (BH, Npad) layout, pad stays zero
 }
 
 }  // namespace mom
@@ -616,7 +616,7 @@ static MomLayout mom_layout(int B, int H, int N, int L, int causal, bool bwd) {
     m.off_part3 = take(tens * 4);
     m.off_u = take(tens * 2);
     m.off_qd = take(tens * 2);
-    m.off_dlt = take((size_t)m.BH * N * 4);
+    m.off_dlt = take((size_t)m.BH * m.Npad * 4);
   }
   m.total = off;
   return m;
@@ -690,7 +690,7 @@ int moments_fwd(const Problem& pb, const void* q, const void* k, const void* v, 
   if ((rc = launch_build(pb, m, w8 + m.off_xt, v, k, state, 0))) return rc;
   // 2. intra-segment part (causal only) and the normaliser
   if (pb.causal) {
-    if ((rc = exact_fwd_partial(pb, q, k, v, m.L, part, g))) return rc;
+    if ((rc = intra_fwd(pb, m.L, m.Npad, q, k, v, part, g))) return rc;
   }
   NormParams np{};
   np.mode = 0, np.accumulate = pb.causal, np.Q = (const bf16*)q, np.g = g, np.state = state;
@@ -720,9 +720,10 @@ int moments_bwd(const Problem& pb, const void* q, const void* k, const void* v, 
   float* dlt = (float*)(w8 + m.off_dlt);
   const size_t rows = (size_t)m.BH * m.N;
   // 1. u = do/g, dlt = (do.o)/g, qd = -dlt*q
+  FM_CUDA(cudaMemsetAsync(dlt, 0, (size_t)m.BH * m.Npad * 4, pb.stream));
   FM_LAUNCH("mom_prep_bwd", pb.stream,
-            prep_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, pb.stream>>>((const bf16*)q, (const bf16*)o,
-                                                                                (const bf16*)d_o, g, u, dlt, qd, rows));
+            prep_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, pb.stream>>>(
+                (const bf16*)q, (const bf16*)o, (const bf16*)d_o, g, u, dlt, qd, rows, m.N, m.Npad));
   // 2. forward-direction states of (k, v) (recomputed, not saved) and reverse-direction states of (q, u)
   if ((rc = launch_transpose(pb, k, w8 + m.off_xt, m.Npad))) return rc;
   if ((rc = launch_build(pb, m, w8 + m.off_xt, v, k, S, 0))) return rc;
@@ -730,7 +731,8 @@ int moments_bwd(const Problem& pb, const void* q, const void* k, const void* v, 
   if ((rc = launch_build(pb, m, w8 + m.off_xt2, u, qd, R, 1))) return rc;
   // 3. intra-segment partials
   if (pb.causal) {
-    if ((rc = exact_bwd_partial(pb, q, k, v, o, g, d_o, m.L, dq_part, dk_part, dv_part))) return rc;
+    if ((rc = intra_dq(pb, m.L, m.Npad, q, u, k, v, dlt, dq_part))) return rc;
+    if ((rc = intra_dkdv(pb, m.L, m.Npad, k, v, q, u, dlt, dk_part, dv_part))) return rc;
   }
   NormParams np{};
   np.mode = 1, np.accumulate = pb.causal, np.Q = (const bf16*)q, np.dlt = dlt, np.part = dq_part, np.state = S;
