@@ -78,9 +78,9 @@ int exact_bwd_partial(const Problem& pb, const void* q, const void* k, const voi
 
 // tcgen05 moment-scan path (fm_moments.cu): bf16, D = 64
 int intra_fwd(const Problem& pb, int L, int Npad, const void* q, const void* k, const void* v, float* o_part,
-              float* g_part);
+              float* g, const uint8_t* state);
 int intra_dq(const Problem& pb, int L, int Npad, const void* q, const void* u, const void* k, const void* v,
-             const float* dlt, float* dq_part);
+             const float* dlt, float* dq_part, const uint8_t* state);
 int intra_dkdv(const Problem& pb, int L, int Npad, const void* k, const void* v, const void* q, const void* u,
                const float* dlt, float* dk_part, float* dv_part);
 int moments_seg_len(int N);

@@ -36,7 +36,9 @@ struct IntraParams {
   const float* dlt;        // (BH, Npad) fp32, zero padded
   float* out0;             // FWD: O partial; DQ: dQ partial; DKDV: dV partial   (BH,N,64) fp32
   float* out1;             // DKDV: dK partial
-  float* g;                // FWD: partial normaliser (BH,N)
+  float* g;                // FWD: normaliser (BH,N): intra rowsum + moment part of the segment boundary
+  const uint8_t* state;    // forward-direction boundary states (normaliser column), nullable
+  int nseg;
 };
 
 template <int MODE> struct IntraCfg {
@@ -46,19 +48,22 @@ template <int MODE> struct IntraCfg {
   static constexpr int STAGE_BYTES = 2 * 8192 + (MODE == INTRA_DKDV ? 256 : 0);
   static constexpr int STAGE_STRIDE = 2 * 8192 + 1024;            // keeps every tile 1024-aligned
   static constexpr int RES_BYTES = OUT_TILES * RES_OPS * 16384;
-  static constexpr int SMEM = RES_BYTES + STAGES * STAGE_STRIDE + 1024 + 1024;
+  static constexpr int NORM_BYTES = MODE == INTRA_DKDV ? 0 : 8192 + 1024;   // slab 65 (bf16) + N1 (fp32)
+  static constexpr int SMEM = RES_BYTES + STAGES * STAGE_STRIDE + NORM_BYTES + 1024 + 1024;
 };
 
 template <int MODE>
 __global__ void __launch_bounds__(384, 1)
 intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ CUtensorMap tmR2,
-             const __grid_constant__ CUtensorMap tmT1, const __grid_constant__ CUtensorMap tmT2, const IntraParams P) {
+             const __grid_constant__ CUtensorMap tmT1, const __grid_constant__ CUtensorMap tmT2,
+             const __grid_constant__ CUtensorMap tmS, const IntraParams P) {
   using C = IntraCfg<MODE>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* res = smem;                         // [RES_OPS][OUT_TILES][16 KiB]
   uint8_t* ring = smem + C::RES_BYTES;         // STAGES x (T1 8 KiB | T2 8 KiB | dlt 256 B)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + C::STAGES * C::STAGE_STRIDE);
+  uint8_t* norm_s = ring + C::STAGES * C::STAGE_STRIDE;   // [8 KiB normaliser matrix | 256 B vector]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(norm_s + C::NORM_BYTES);
   uint64_t* full = bars;              // [STAGES]
   uint64_t* empty = bars + 8;         // [STAGES]   count 2 (one arrival per warpgroup)
   uint64_t* res_full = bars + 16;     // [1]
@@ -77,6 +82,11 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
   const int st0 = MODE == INTRA_DKDV ? c0 : seg_start;
   const int st1 = MODE == INTRA_DKDV ? seg_end : min(c0 + CT, P.N);
   const int nstream = (st1 - st0 + 63) / 64;
+  // moment part of the normaliser column (FWD: g, DQ: the -dlt (N1 + a N2 q) term): only segments
+  // that have a boundary state
+  const int seg = c0 / P.L;
+  const bool has_norm = MODE != INTRA_DKDV && P.state != nullptr && seg > 0;
+  const int rec_idx = bh * P.nseg + seg;
 
   if (warp == 0) {
     tmem_alloc(tmem_slot, 512);
@@ -99,7 +109,8 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer
     if (lane == 0) {
-      mbar_arrive_expect_tx(res_full, C::RES_BYTES);
+      mbar_arrive_expect_tx(res_full, C::RES_BYTES + (has_norm ? 8192 : 0));
+      if (has_norm) tma_load_3d(norm_s, &tmS, res_full, 0, 65 * 64, rec_idx);
       for (int o = 0; o < C::OUT_TILES; ++o)
         for (int h = 0; h < 2; ++h) {
           tma_load_3d(res + o * 16384 + h * 8192, &tmR1, res_full, 0, c0 + o * 128 + h * 64, bh);
@@ -288,6 +299,22 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
         }
       }
     }
+    // ---- moment part of the normaliser column: T_o = R1_o . N2 (one more score-like MMA per output
+    // tile, into the two halves of the warpgroup's score buffer)
+    if constexpr (MODE != INTRA_DKDV) {
+      if (has_norm && issuer) {
+        if (npair > 0) mbar_wait(&s_free[w], (npair - 1) & 1);
+        tc_fence_after();
+        const uint64_t dN = desc_kmajor_sw128(smem_u32(norm_s));
+#pragma unroll
+        for (int x = 0; x < 2; ++x) {
+          const uint64_t dA = desc_kmajor_sw128(smem_u32(res + otile[x] * 16384));
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_ss(tmem + 256 + 128 * w + 64 * x, dA + kk * 2, dN + kk * 2, id_kk, kk > 0);
+        }
+      }
+    }
     if (issuer) umma_commit(&acc_done[w]);
     mbar_wait(&acc_done[w], 0);
     tc_fence_after();
@@ -301,6 +328,8 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
       if (!tile_live) continue;
       const size_t grow = (size_t)bh * P.N + r_abs;
       const int nacc = MODE == INTRA_DKDV ? 2 : 1;
+      const float* vec = has_norm ? reinterpret_cast<const float*>(P.state + (size_t)rec_idx * REC_BYTES + VEC_OFF) : nullptr;
+      float gmom = 0.f;   // FWD: a q.N1 + (a^2/2) q.T
       for (int a2 = 0; a2 < nacc; ++a2) {
         float* outp = a2 == 0 ? P.out0 : P.out1;
         const uint32_t col = MODE == INTRA_DKDV ? 128 * o + 64 * a2 : 64 * o;
@@ -308,6 +337,36 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
         for (int h = 0; h < 2; ++h) {
           uint32_t v[32];
           tmem_ld32(lane_addr + col + 32 * h, v);
+          if constexpr (MODE != INTRA_DKDV) {
+            if (has_norm) {   // CTA-uniform
+              uint32_t tn[32];
+              tmem_ld32(sbuf + 64 * x + 32 * h, tn);
+              tmem_wait_ld();
+              if constexpr (MODE == INTRA_DQ) {
+                // dq_part[l] -= dlt (N1[l] + a T[l])
+#pragma unroll
+                for (int c = 0; c < 32; ++c)
+                  v[c] = __float_as_uint(__uint_as_float(v[c]) -
+                                         dlt_row[x] * fmaf(P.p == 2 ? a : 0.f, __uint_as_float(tn[c]), __ldg(vec + 64 + 32 * h + c)));
+              } else {
+                // g += a q.N1 + (a^2/2) q.T  with the thread's own q row read back from the resident tile
+                const uint8_t* qrow = res + o * 16384 + rloc * 128;
+#pragma unroll
+                for (int c8 = 0; c8 < 4; ++c8) {
+                  const uint4 qv = *reinterpret_cast<const uint4*>(qrow + (((4 * h + c8) ^ (rloc & 7)) << 4));
+                  const uint32_t qw[4] = {qv.x, qv.y, qv.z, qv.w};
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const int c = 8 * c8 + 2 * j;
+                    const float q0 = __uint_as_float(qw[j] << 16), q1 = __uint_as_float(qw[j] & 0xffff0000u);
+                    const float c2n = P.p == 2 ? c2 : 0.f;
+                    gmom += q0 * fmaf(c2n, __uint_as_float(tn[c]), a * __ldg(vec + 64 + 32 * h + c));
+                    gmom += q1 * fmaf(c2n, __uint_as_float(tn[c + 1]), a * __ldg(vec + 64 + 32 * h + c + 1));
+                  }
+                }
+              }
+            }
+          }
           tmem_wait_ld();
           if (r_abs < P.N) {
             uint4* dst = reinterpret_cast<uint4*>(outp + grow * 64 + 32 * h);
@@ -316,7 +375,7 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
           }
         }
       }
-      if (MODE == INTRA_FWD && r_abs < P.N) P.g[grow] = gsum[x];
+      if (MODE == INTRA_FWD && r_abs < P.N) P.g[grow] = gsum[x] + (has_norm ? (float)(seg * P.L) + gmom : 0.f);
     }
   }
   tc_fence_before();
@@ -331,7 +390,8 @@ using namespace mom;
 // R1/R2: resident operands (rows = output rows), T1/T2: streamed operands.  All (BH, N, 64) bf16.
 template <int MODE>
 static int launch_intra_t(const Problem& pb, int L, int Npad, const void* r1, const void* r2, const void* t1,
-                          const void* t2, const float* dlt, float* out0, float* out1, float* g, const char* name) {
+                          const void* t2, const float* dlt, float* out0, float* out1, float* g,
+                          const uint8_t* state, const char* name) {
   using C = IntraCfg<MODE>;
   const int BH = pb.B * pb.H;
   CUtensorMap m[4];
@@ -342,25 +402,32 @@ static int launch_intra_t(const Problem& pb, int L, int Npad, const void* r1, co
   }
   IntraParams P{};
   P.N = pb.N, P.Npad = Npad, P.L = L, P.p = pb.p, P.a = pb.inv_c, P.dlt = dlt, P.out0 = out0, P.out1 = out1, P.g = g;
+  P.nseg = (pb.N + L - 1) / L;
+  P.state = P.nseg > 1 ? state : nullptr;
+  CUtensorMap tmS = m[0];
+  if (P.state) {
+    int rc = make_tmap_bf16_3d(&tmS, state, 64, NSLAB * 64, (uint64_t)BH * P.nseg, 128, REC_BYTES, 64, 64);
+    if (rc) return rc;
+  }
   auto kern = intra_kernel<MODE>;
   FM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
   constexpr int CT = C::OUT_TILES * 128;
   dim3 grid((pb.N + CT - 1) / CT, BH);
-  FM_LAUNCH(name, pb.stream, kern<<<grid, 384, C::SMEM, pb.stream>>>(m[0], m[1], m[2], m[3], P));
+  FM_LAUNCH(name, pb.stream, kern<<<grid, 384, C::SMEM, pb.stream>>>(m[0], m[1], m[2], m[3], tmS, P));
   return FASTMAX_OK;
 }
 
 int intra_fwd(const Problem& pb, int L, int Npad, const void* q, const void* k, const void* v, float* o_part,
-              float* g_part) {
-  return launch_intra_t<INTRA_FWD>(pb, L, Npad, q, nullptr, k, v, nullptr, o_part, nullptr, g_part, "mom_intra_fwd");
+              float* g, const uint8_t* state) {
+  return launch_intra_t<INTRA_FWD>(pb, L, Npad, q, nullptr, k, v, nullptr, o_part, nullptr, g, state, "mom_intra_fwd");
 }
 int intra_dq(const Problem& pb, int L, int Npad, const void* q, const void* u, const void* k, const void* v,
-             const float* dlt, float* dq_part) {
-  return launch_intra_t<INTRA_DQ>(pb, L, Npad, q, u, k, v, dlt, dq_part, nullptr, nullptr, "mom_intra_dq");
+             const float* dlt, float* dq_part, const uint8_t* state) {
+  return launch_intra_t<INTRA_DQ>(pb, L, Npad, q, u, k, v, dlt, dq_part, nullptr, nullptr, state, "mom_intra_dq");
 }
 int intra_dkdv(const Problem& pb, int L, int Npad, const void* k, const void* v, const void* q, const void* u,
                const float* dlt, float* dk_part, float* dv_part) {
-  return launch_intra_t<INTRA_DKDV>(pb, L, Npad, k, v, q, u, dlt, dv_part, dk_part, nullptr, "mom_intra_dkdv");
+  return launch_intra_t<INTRA_DKDV>(pb, L, Npad, k, v, q, u, dlt, dv_part, dk_part, nullptr, nullptr, "mom_intra_dkdv");
 }
 
 }  // namespace fm

@@ -18,6 +18,7 @@
 #include "fm_common.cuh"
 #include "fm_sm100.cuh"
 #include "fm_moments.cuh"
+#include <stdlib.h>
 
 namespace fm {
 namespace mom {
@@ -26,15 +27,16 @@ using namespace sm100;
 typedef __nv_bfloat16 bf16;
 
 // =============================================================================================
-// prep: transpose (B*H, N, 64) -> (B*H, 64, Npad) so that the build kernel can read token-major
-// runs of one feature with 16-byte shared loads.  HBM-bound (reads + writes the tensor once).
+// prep: blocked transpose (B*H, N, 64) -> (B*H, N/64, 64 features, 64 tokens) so that the build
+// kernel can read token-major runs of one feature with 16-byte shared loads and every 64-token
+// block is one contiguous 8 KiB TMA box.  HBM-bound (reads + writes the tensor once).
 // =============================================================================================
 __global__ void __launch_bounds__(256) transpose_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int N,
                                                         int Npad) {
   __shared__ bf16 tile[64][66];
   const int bh = blockIdx.y, n0 = blockIdx.x * 64;
   const bf16* src = in + (size_t)bh * N * 64;
-  bf16* dst = out + (size_t)bh * 64 * Npad;
+  bf16* dst = out + ((size_t)bh * (Npad / 64) + blockIdx.x) * 4096;
   for (int idx = threadIdx.x; idx < 64 * 32; idx += 256) {
     int r = idx >> 5, c2 = idx & 31;
     __nv_bfloat162 v = __floats2bfloat162_rn(0.f, 0.f);
@@ -48,7 +50,7 @@ __global__ void __launch_bounds__(256) transpose_kernel(const bf16* __restrict__
     __nv_bfloat162 v;
     v.x = tile[2 * t2][d];
     v.y = tile[2 * t2 + 1][d];
-    *reinterpret_cast<__nv_bfloat162*>(dst + (size_t)d * Npad + n0 + 2 * t2) = v;
+    *reinterpret_cast<__nv_bfloat162*>(dst + d * 64 + 2 * t2) = v;
   }
 }
 
@@ -57,71 +59,81 @@ __global__ void __launch_bounds__(256) transpose_kernel(const bf16* __restrict__
 // =============================================================================================
 struct BuildParams {
   int N, nblk, nproc, Lb, nseg, reverse, causal, p;
-  uint8_t* state;  // records: causal -> [bh][nseg], else [bh]
+  int special_cx;   // blockIdx.x of the CTA that owns the special tile (S1 | normaliser): 8 for p=2, 0 for p=1
+  uint8_t* state;   // records: causal -> [bh][nseg], else [bh]
 };
 
-constexpr int B_STAGES = 3;
+// CTA layout of the build kernel (p = 2): 8 "regular" CTAs per (b,h), each owning 4 tiles
+// (= 8 slabs x 64 y rows, four 64-column fp32 accumulators) plus one "special" CTA with the two
+// accumulators of the special tile.  Tensor memory: accumulators in columns [0,256), A operand
+// buffers (4 tiles x 2 stages x 32 columns) in [256,512).
+//
+// Roles (25 warps): generator group g = warps 4g..4g+3 owns tile g for the whole kernel and turns
+// each 64-token block into the tile's bf16 Khatri-Rao rows in tensor memory; issuer warp 16+g issues
+// that tile's four MMAs per block (measured with tools/mmarate.py: one thread sustains only one
+// tcgen05.mma per ~110 cycles while a 128x64x16 MMA occupies the tensor pipe for ~32, so four
+// threads issue concurrently; each issues every MMA of "its" accumulator, so its tcgen05.commit
+// covers that accumulator exactly); warp 20 is the TMA producer; warps 21..24 write the bf16
+// snapshots at segment boundaries.
+constexpr int B_STAGES = 4;
 constexpr int B_STAGE_BYTES = 3 * 8192;
 constexpr int B_SMEM = B_STAGES * B_STAGE_BYTES + 1024 /*barriers*/ + 1024 /*align slack*/;
-constexpr int B_ACOL = 448;  // two 32-column A buffers at the top of tensor memory
+constexpr int B_ACOL = 256;
+constexpr int B_CTAS_P2 = 9;
+constexpr int B_THREADS = 25 * 32;
 
-__device__ __forceinline__ bool build_boundary(const BuildParams& P, int it, int& seg) {
-  const int b = P.reverse ? P.nblk - 1 - it : it;
-  if (!P.causal) {
-    seg = 0;
-    return it == P.nproc - 1;
+// Segment-boundary schedule of the scan without integer division in the hot loops.
+struct BoundaryIter {
+  int c, Lb, reverse, causal, last;
+  __device__ BoundaryIter(const BuildParams& P) : Lb(P.Lb), reverse(P.reverse), causal(P.causal), last(P.nproc - 1) {
+    c = P.reverse ? (P.nblk - 1) % P.Lb : 0;
   }
-  if (P.reverse) {
-    seg = b / P.Lb - 1;
-    return (b % P.Lb) == 0;
+  // true if a snapshot is due after block number `it` of the scan
+  __device__ bool step(int it) {
+    if (!causal) return it == last;
+    bool bnd;
+    if (reverse) {
+      bnd = c == 0;
+      c = bnd ? Lb - 1 : c - 1;
+    } else {
+      bnd = c == Lb - 1;
+      c = bnd ? 0 : c + 1;
+    }
+    return bnd;
   }
-  seg = (b + 1) / P.Lb;
-  return ((b + 1) % P.Lb) == 0;
+};
+
+__device__ __forceinline__ void lds128(uint32_t saddr, uint32_t* r) {
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
 }
 
-// 16-byte chunk c of 128-byte row `row` inside a 128B-swizzled tile
-__device__ __forceinline__ uint4 lds_swz(const uint8_t* tile, int row, int c) {
-  return *reinterpret_cast<const uint4*>(tile + row * 128 + ((c ^ (row & 7)) << 4));
-}
-
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(B_THREADS, 1)
 build_kernel(const __grid_constant__ CUtensorMap tmXT, const __grid_constant__ CUtensorMap tmW,
              const __grid_constant__ CUtensorMap tmW2, const BuildParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B_STAGES * B_STAGE_BYTES);
-  uint64_t* full = bars;                 // [3]
-  uint64_t* empty = bars + 3;            // [3]
-  uint64_t* a_full = bars + 6;           // [2]
-  uint64_t* a_empty = bars + 8;          // [2]
-  uint64_t* acc_full = bars + 10;        // [8]
-  uint64_t* acc_free = bars + 18;        // [8]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
+  uint64_t* full = bars;                 // [4] block operands landed (TMA)
+  uint64_t* done = bars + 4;             // [4] every MMA of the block in this ring slot complete (count ntile)
+  uint64_t* a_ready = bars + 8;          // [4 tiles][2] A buffer written by the 4 warps of the group (count 4)
+  uint64_t* acc_full = bars + 16;        // [4 tiles] accumulator final for this segment boundary
+  uint64_t* acc_free = bars + 20;        // [4 tiles] snapshot writers have read it (count 128)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int bh = blockIdx.y, cx = blockIdx.x;
-
-  // tile ownership: 32 regular tiles (2 slabs x 64 y each) + 1 special tile (S1 | normaliser)
-  int first_tile, nreg;
-  bool special;
-  if (P.p == 2) {
-    first_tile = 7 * cx;
-    nreg = cx < 4 ? 7 : 4;
-    special = cx == 4;
-  } else {
-    first_tile = 0, nreg = 0, special = true;
-  }
-  const int ntile = nreg + (special ? 1 : 0);
+  const bool special = cx == P.special_cx;
+  const int ntile = special ? 1 : 4;
   const uint32_t stage_tx = special ? 3 * 8192 : 2 * 8192;
 
-  if (warp == 2) {
+  if (warp == 20) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
   if (tid == 0) {
-    for (int i = 0; i < B_STAGES; ++i) mbar_init(&full[i], 1), mbar_init(&empty[i], 1);
-    for (int i = 0; i < 2; ++i) mbar_init(&a_full[i], 128), mbar_init(&a_empty[i], 1);
-    for (int i = 0; i < 8; ++i) mbar_init(&acc_full[i], 1), mbar_init(&acc_free[i], 128);
+    for (int i = 0; i < B_STAGES; ++i) mbar_init(&full[i], 1), mbar_init(&done[i], ntile);
+    for (int i = 0; i < 8; ++i) mbar_init(&a_ready[i], 4);
+    for (int i = 0; i < 4; ++i) mbar_init(&acc_full[i], 1), mbar_init(&acc_free[i], 128);
     fence_barrier_init();
     tma_prefetch_desc(&tmXT);
     tma_prefetch_desc(&tmW);
@@ -132,162 +144,161 @@ build_kernel(const __grid_constant__ CUtensorMap tmXT, const __grid_constant__ C
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp < 16) {
+    // ------------------------------------------------------------------ generator groups
+    const int g = warp >> 2, q = warp & 3;
+    if (g < ntile) {
+      const int row = 32 * q + lane;          // TMEM lane == feature row (xsel, y) of the tile
+      const int xsel = row >> 6, y = row & 63;
+      const int x = (8 * cx + 2 * g + xsel) & 63;
+      const uint32_t a_dst = tmem + ((uint32_t)(32 * q) << 16) + B_ACOL + 64 * g;
+      // byte offsets of the 16-byte chunks of rows y and x inside the 128B-swizzled XT tile
+      uint32_t yo[8], xo[8];
+#pragma unroll
+      for (int c8 = 0; c8 < 8; ++c8) {
+        yo[c8] = (uint32_t)y * 128 + ((uint32_t)(c8 ^ (y & 7)) << 4);
+        xo[c8] = (uint32_t)x * 128 + ((uint32_t)(c8 ^ (x & 7)) << 4);
+      }
+      const uint32_t fill = row == 64 ? 0x3F803F80u : 0u;
+      const uint32_t smem0 = smem_u32(smem);
+#pragma unroll 1
+      for (int it = 0; it < P.nproc; ++it) {
+        const int s = it & 3, ph = (it >> 2) & 1, buf = it & 1;
+        mbar_wait(&full[s], ph);
+        const uint32_t xt = smem0 + s * B_STAGE_BYTES;
+        uint32_t a[32];
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) lds128(xt + yo[c8], a + 4 * c8);
+        if (!special) {
+#pragma unroll
+          for (int c8 = 0; c8 < 8; ++c8) {
+            uint32_t v[4];
+            lds128(xt + xo[c8], v);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[4 * c8 + i] = mul_bf16x2(v[i], a[4 * c8 + i]);
+          }
+        } else if (row >= 64) {
+          // special tile: rows 0..63 = Y (S1 / normaliser matrix), row 64 = ones (S0 / normaliser vector)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) a[i] = fill;
+        }
+        // A buffer `buf` was last read by the MMAs of block it-2
+        if (it >= 2) mbar_wait(&done[(it - 2) & 3], ((it - 2) >> 2) & 1);
+        tc_fence_after();
+        tmem_st32(a_dst + 32 * buf, a);
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_ready[g * 2 + buf]);
+      }
+    }
+  } else if (warp < 20) {
+    // ------------------------------------------------------------------ MMA issuers
+    const int g = warp - 16;
+    if (lane == 0 && g < ntile) {
+      const uint32_t idesc = make_idesc_bf16(128, 64, false, true);
+      const uint64_t dW0 = desc_mnmajor_sw128(smem_u32(smem) + 8192, 8192);
+      const uint32_t acc = tmem + 64 * g;
+      const uint32_t a0 = tmem + B_ACOL + 64 * g;
+      BoundaryIter bi(P);
+      int snaps = 0;
+      bool pending = false;
+#pragma unroll 1
+      for (int it = 0; it < P.nproc; ++it) {
+        const int s = it & 3, ph = (it >> 2) & 1, buf = it & 1;
+        const bool bnd = bi.step(it);
+        const uint64_t dW = dW0 + (uint64_t)(s * (B_STAGE_BYTES >> 4));
+        const uint32_t a_t = a0 + 32 * buf;
+        mbar_wait(&full[s], ph);
+        if (pending) mbar_wait(&acc_free[g], (snaps - 1) & 1);
+        mbar_wait(&a_ready[g * 2 + buf], (it >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) umma_ts(acc, a_t + kk * 8, dW + kk * 128, idesc, (it | kk) != 0);
+        if (special) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) umma_ts(tmem + 64, a_t + kk * 8, dW + 512 + kk * 128, idesc, (it | kk) != 0);
+        }
+        umma_commit(&done[s]);
+        if (bnd) {
+          umma_commit(&acc_full[g]);
+          ++snaps;
+        }
+        pending = bnd;
+      }
+    }
+  } else if (warp == 20) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       for (int it = 0; it < P.nproc; ++it) {
-        const int s = it % B_STAGES, ph = (it / B_STAGES) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
+        const int s = it & 3;
+        if (it >= B_STAGES) mbar_wait(&done[s], ((it - B_STAGES) >> 2) & 1);   // MMAs of block it-4 complete
         const int b = P.reverse ? P.nblk - 1 - it : it;
         uint8_t* st = smem + s * B_STAGE_BYTES;
         mbar_arrive_expect_tx(&full[s], stage_tx);
-        tma_load_3d(st, &tmXT, &full[s], b * 64, 0, bh);
+        tma_load_3d(st, &tmXT, &full[s], 0, b * 64, bh);
         tma_load_3d(st + 8192, &tmW, &full[s], 0, b * 64, bh);
         if (special) tma_load_3d(st + 16384, &tmW2, &full[s], 0, b * 64, bh);
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, 64, false, true);
-      int snaps = 0;
-      bool pending = false;
-      for (int it = 0; it < P.nproc; ++it) {
-        const int s = it % B_STAGES, ph = (it / B_STAGES) & 1;
-        mbar_wait(&full[s], ph);
-        tc_fence_after();
-        int seg;
-        const bool bnd = build_boundary(P, it, seg);
-        const uint32_t sbase = smem_u32(smem + s * B_STAGE_BYTES);
-        const uint64_t dW = desc_mnmajor_sw128(sbase + 8192, 8192);
-        const uint64_t dW2 = desc_mnmajor_sw128(sbase + 16384, 8192);
-        for (int ti = 0; ti < ntile; ++ti) {
-          const int c = it * ntile + ti, g = c & 1, use = c >> 1;
-          if (pending) mbar_wait(&acc_free[ti], (snaps - 1) & 1);
-          mbar_wait(&a_full[g], use & 1);
-          tc_fence_after();
-          const uint32_t a_t = tmem + B_ACOL + 32 * g;
-          if (ti < nreg) {
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) umma_ts(tmem + 64 * ti, a_t + kk * 8, dW + kk * 128, idesc, (it | kk) != 0);
-          } else {
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) umma_ts(tmem + 64 * nreg, a_t + kk * 8, dW + kk * 128, idesc, (it | kk) != 0);
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              umma_ts(tmem + 64 * nreg + 64, a_t + kk * 8, dW2 + kk * 128, idesc, (it | kk) != 0);
-          }
-          umma_commit(&a_empty[g]);
-          if (bnd) umma_commit(&acc_full[ti]);
-        }
-        umma_commit(&empty[s]);
-        if (bnd) ++snaps;
-        pending = bnd;
-      }
-    }
-  } else if (warp >= 4 && warp < 12) {
-    // ------------------------------------------------------------------ A-operand generators
-    const int g = (warp - 4) >> 2, q = warp & 3;
-    const int row = 32 * q + lane;          // TMEM lane == feature row of the tile
-    const int xsel = row >> 6, y = row & 63;
-    const uint32_t a_addr = tmem + ((uint32_t)(32 * q) << 16) + B_ACOL + 32 * g;
-    for (int it = 0; it < P.nproc; ++it) {
-      const int s = it % B_STAGES, ph = (it / B_STAGES) & 1;
-      if (((it * ntile) & 1) != g && ntile == 1) continue;   // nothing for this group in this block
-      mbar_wait(&full[s], ph);
-      const uint8_t* xt = smem + s * B_STAGE_BYTES;
-      uint32_t yr[32];
-#pragma unroll
-      for (int c8 = 0; c8 < 8; ++c8) {
-        uint4 v = lds_swz(xt, y, c8);
-        yr[4 * c8] = v.x, yr[4 * c8 + 1] = v.y, yr[4 * c8 + 2] = v.z, yr[4 * c8 + 3] = v.w;
-      }
-      for (int ti = 0; ti < ntile; ++ti) {
-        const int c = it * ntile + ti;
-        if ((c & 1) != g) continue;
-        const int use = c >> 1;
-        uint32_t a[32];
-        if (ti < nreg) {
-          const int x = 2 * (first_tile + ti) + xsel;
-#pragma unroll
-          for (int c8 = 0; c8 < 8; ++c8) {
-            uint4 v = lds_swz(xt, x, c8);
-            a[4 * c8] = mul_bf16x2(v.x, yr[4 * c8]);
-            a[4 * c8 + 1] = mul_bf16x2(v.y, yr[4 * c8 + 1]);
-            a[4 * c8 + 2] = mul_bf16x2(v.z, yr[4 * c8 + 2]);
-            a[4 * c8 + 3] = mul_bf16x2(v.w, yr[4 * c8 + 3]);
-          }
-        } else {
-          // special tile: rows 0..63 = Y (S1 / normaliser matrix), row 64 = ones (S0 / normaliser vector)
-#pragma unroll
-          for (int i = 0; i < 32; ++i) a[i] = row < 64 ? yr[i] : (row == 64 ? 0x3F803F80u : 0u);
-        }
-        mbar_wait(&a_empty[g], (use & 1) ^ 1);
-        tc_fence_after();
-        tmem_st32(a_addr, a);
-        tmem_wait_st();
-        tc_fence_before();
-        mbar_arrive(&a_full[g]);
-      }
-    }
-  } else if (warp >= 12) {
-    // ------------------------------------------------------------------ snapshot writers
+  } else {
+    // ------------------------------------------------------------------ snapshot writers (warps 21..24)
     const int q = warp & 3;
     const int row = 32 * q + lane;
     const int xsel = row >> 6, y = row & 63;
     const uint32_t lane_addr = tmem + ((uint32_t)(32 * q) << 16);
-    int k = 0;
+    BoundaryIter bi(P);
+    int kq = 0;
     for (int it = 0; it < P.nproc; ++it) {
-      int seg;
-      if (!build_boundary(P, it, seg)) continue;
+      if (!bi.step(it)) continue;
+      const int b = P.reverse ? P.nblk - 1 - it : it;
+      const int seg = !P.causal ? 0 : (P.reverse ? b / P.Lb - 1 : (b + 1) / P.Lb);
       uint8_t* rec = P.state + (size_t)(P.causal ? bh * P.nseg + seg : bh) * REC_BYTES;
-      for (int ti = 0; ti < ntile; ++ti) {
-        mbar_wait(&acc_full[ti], k & 1);
+      for (int g = 0; g < ntile; ++g) {
+        mbar_wait(&acc_full[g], kq & 1);
         tc_fence_after();
-        const int nacc = ti < nreg ? 1 : 2;
+        const int nacc = special ? 2 : 1;
         for (int a2 = 0; a2 < nacc; ++a2) {
-          uint32_t v[64];
-          tmem_ld32(lane_addr + 64 * (ti + a2), v);
-          tmem_ld32(lane_addr + 64 * (ti + a2) + 32, v + 32);
-          tmem_wait_ld();
-          if (a2 == nacc - 1) {
-            tc_fence_before();
-            mbar_arrive(&acc_free[ti]);
-          }
-          int slab;
-          if (ti < nreg) slab = 2 * (first_tile + ti) + xsel;
-          else slab = 64 + a2;
-          const bool is_vec_row = (ti >= nreg) && row == 64;
-          const bool is_mat_row = (ti < nreg) || row < 64;
-          if (is_mat_row) {
-            uint4* dst = reinterpret_cast<uint4*>(rec + (size_t)slab * SLAB_BYTES + (size_t)y * 128);
-#pragma unroll
-            for (int c8 = 0; c8 < 8; ++c8) {
-              uint4 o;
-              o.x = pack_bf16x2(__uint_as_float(v[8 * c8]), __uint_as_float(v[8 * c8 + 1]));
-              o.y = pack_bf16x2(__uint_as_float(v[8 * c8 + 2]), __uint_as_float(v[8 * c8 + 3]));
-              o.z = pack_bf16x2(__uint_as_float(v[8 * c8 + 4]), __uint_as_float(v[8 * c8 + 5]));
-              o.w = pack_bf16x2(__uint_as_float(v[8 * c8 + 6]), __uint_as_float(v[8 * c8 + 7]));
-              dst[c8] = o;
+          const int slab = special ? 64 + a2 : 8 * cx + 2 * g + xsel;
+#pragma unroll 1
+          for (int h = 0; h < 2; ++h) {
+            uint32_t v[32];
+            tmem_ld32(lane_addr + 64 * (g + a2) + 32 * h, v);
+            tmem_wait_ld();
+            if (a2 == nacc - 1 && h == 1) {
+              tc_fence_before();
+              mbar_arrive(&acc_free[g]);
             }
-            if (slab == 65) {  // fp32 copy of the normaliser matrix
-              uint4* d32 = reinterpret_cast<uint4*>(rec + VEC_OFF + (size_t)(128 + y * 64) * 4);
+            if (!special || row < 64) {
+              uint4* dst = reinterpret_cast<uint4*>(rec + (size_t)slab * SLAB_BYTES + (size_t)y * 128 + 64 * h);
 #pragma unroll
-              for (int c4 = 0; c4 < 16; ++c4) d32[c4] = make_uint4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+              for (int c8 = 0; c8 < 4; ++c8) {
+                uint4 o;
+                o.x = pack_bf16x2(__uint_as_float(v[8 * c8]), __uint_as_float(v[8 * c8 + 1]));
+                o.y = pack_bf16x2(__uint_as_float(v[8 * c8 + 2]), __uint_as_float(v[8 * c8 + 3]));
+                o.z = pack_bf16x2(__uint_as_float(v[8 * c8 + 4]), __uint_as_float(v[8 * c8 + 5]));
+                o.w = pack_bf16x2(__uint_as_float(v[8 * c8 + 6]), __uint_as_float(v[8 * c8 + 7]));
+                dst[c8] = o;
+              }
+              if (slab == 65) {  // fp32 copy of the normaliser matrix
+                uint4* d32 = reinterpret_cast<uint4*>(rec + VEC_OFF + (size_t)(128 + y * 64 + 32 * h) * 4);
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4) d32[c4] = make_uint4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+              }
+            } else if (row == 64) {
+              uint4* d32 = reinterpret_cast<uint4*>(rec + VEC_OFF + (size_t)(a2 * 64 + 32 * h) * 4);
+#pragma unroll
+              for (int c4 = 0; c4 < 8; ++c4) d32[c4] = make_uint4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
             }
-          } else if (is_vec_row) {
-            uint4* d32 = reinterpret_cast<uint4*>(rec + VEC_OFF + (size_t)(a2 * 64) * 4);
-#pragma unroll
-            for (int c4 = 0; c4 < 16; ++c4) d32[c4] = make_uint4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
           }
         }
       }
-      ++k;
+      ++kq;
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem, 512);
+  if (warp == 20) tmem_dealloc(tmem, 512);
 }
 
 // =============================================================================================
@@ -322,18 +333,63 @@ __device__ __forceinline__ void load_row64(const bf16* base, size_t row, bool va
   }
 }
 
-__global__ void __launch_bounds__(640, 1)
+// One slab step of a tile warpgroup: write A = xs * src (bf16x2 scalar times the 64-wide row held in
+// registers) into the tile's A buffer `buf`, publish it, and -- on the warp whose turn it is --
+// issue the tile's four MMAs for this slab.
+struct ApplyCtx {
+  uint64_t *full, *empty, *a_empty, *a_ready;
+  uint8_t* smem;
+  uint32_t tmem, lane_addr, idesc, kstep;
+  int t, q, lane, b_kmajor;
+};
+
+__device__ __forceinline__ void apply_slab_step(const ApplyCtx& c, int n, uint32_t xs, const uint32_t* src) {
+  const int buf = n & 1, use = n >> 1;
+  mbar_wait(&c.a_empty[c.t * 2 + buf], (use & 1) ^ 1);
+  tc_fence_after();
+  const uint32_t a_dst = c.lane_addr + 256 + (c.t * 2 + buf) * 32;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    uint32_t a[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a[j] = mul_bf16x2(xs, src[16 * h + j]);
+    tmem_st16(a_dst + 16 * h, a);
+  }
+  tmem_wait_st();
+  tc_fence_before();
+  __syncwarp();
+  if (c.lane == 0) mbar_arrive(&c.a_ready[c.t * 2 + buf]);
+  if ((n & 3) == c.q) {
+    if (c.lane == 0) {
+      const int st = n % A_STAGES, ph = (n / A_STAGES) & 1;
+      mbar_wait(&c.a_ready[c.t * 2 + buf], use & 1);
+      mbar_wait(&c.full[st], ph);
+      tc_fence_after();
+      const uint32_t sb = smem_u32(c.smem + st * 8192);
+      const uint64_t bd = c.b_kmajor ? desc_kmajor_sw128(sb) : desc_mnmajor_sw128(sb, 8192);
+      const uint32_t a_t = c.tmem + 256 + (c.t * 2 + buf) * 32;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)
+        umma_ts(c.tmem + 64 * c.t, a_t + kk * 8, bd + kk * c.kstep, c.idesc, (n | kk) != 0);
+      umma_commit(&c.a_empty[c.t * 2 + buf]);
+      umma_commit(&c.empty[st]);
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(544, 1)
 apply_kernel(const __grid_constant__ CUtensorMap tmS, const ApplyParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A_STAGES * 8192);
-  uint64_t* full = bars;            // [6]
-  uint64_t* empty = bars + 6;       // [6]
-  uint64_t* a_full = bars + 12;     // [4][2]
-  uint64_t* a_empty = bars + 20;    // [4][2]
-  uint64_t* acc_full = bars + 28;   // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
-  float* vec_s = reinterpret_cast<float*>(bars + 32);  // [64]
+  uint64_t* full = bars;            // [6]  slab landed (TMA)
+  uint64_t* empty = bars + 6;       // [6]  slab consumed by the MMAs of all four tiles (count 4)
+  uint64_t* a_empty = bars + 12;    // [4][2] A buffer of tile t drained by its MMAs
+  uint64_t* a_ready = bars + 20;    // [4][2] A buffer of tile t written by its 4 warps (count 4)
+  uint64_t* acc_full = bars + 28;   // [4]  all MMAs of tile t complete (count 4: one commit per warp)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
+  float* vec_s = reinterpret_cast<float*>(bars + 34);  // [64]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int bh = blockIdx.y;
@@ -345,29 +401,30 @@ apply_kernel(const __grid_constant__ CUtensorMap tmS, const ApplyParams P) {
   const int s_end = P.use65 ? 66 : 65;
   const int nslab = s_end - s_begin;
 
-  if (warp == 2) {
+  if (warp == 16) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
   if (tid == 0) {
-    for (int i = 0; i < A_STAGES; ++i) mbar_init(&full[i], 1), mbar_init(&empty[i], 1);
-    for (int i = 0; i < 8; ++i) mbar_init(&a_full[i], 128), mbar_init(&a_empty[i], 1);
-    mbar_init(acc_full, 1);
+    for (int i = 0; i < A_STAGES; ++i) mbar_init(&full[i], 1), mbar_init(&empty[i], 4);
+    for (int i = 0; i < 8; ++i) mbar_init(&a_empty[i], 1), mbar_init(&a_ready[i], 4);
+    for (int i = 0; i < 4; ++i) mbar_init(&acc_full[i], 4);
     fence_barrier_init();
     tma_prefetch_desc(&tmS);
   }
-  if (tid >= 64 && tid < 128) {
+  if (tid < 64) {
     float v = 0.f;
     if (has_state && P.vec_sel >= 0)
-      v = reinterpret_cast<const float*>(P.state + (size_t)rec_idx * REC_BYTES + VEC_OFF)[P.vec_sel * 64 + tid - 64];
-    vec_s[tid - 64] = v;
+      v = reinterpret_cast<const float*>(P.state + (size_t)rec_idx * REC_BYTES + VEC_OFF)[P.vec_sel * 64 + tid];
+    vec_s[tid] = v;
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == 16) {
+    // ---------------------------------------------------------------- TMA producer (state slabs)
     if (lane == 0 && has_state) {
       for (int n = 0; n < nslab; ++n) {
         const int st = n % A_STAGES, ph = (n / A_STAGES) & 1;
@@ -376,86 +433,50 @@ apply_kernel(const __grid_constant__ CUtensorMap tmS, const ApplyParams P) {
         tma_load_3d(smem + st * 8192, &tmS, &full[st], 0, (s_begin + n) * 64, rec_idx);
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0 && has_state) {
-      const uint32_t idesc = make_idesc_bf16(128, 64, false, !P.b_kmajor);
-      for (int n = 0; n < nslab; ++n) {
-        const int st = n % A_STAGES, ph = (n / A_STAGES) & 1;
-        mbar_wait(&full[st], ph);
-        tc_fence_after();
-        const uint32_t sb = smem_u32(smem + st * 8192);
-        const uint64_t bd = P.b_kmajor ? desc_kmajor_sw128(sb) : desc_mnmajor_sw128(sb, 8192);
-        const uint32_t kstep = P.b_kmajor ? 2 : 128;
-        const int buf = n & 1, use = n >> 1;
-#pragma unroll 1
-        for (int t = 0; t < 4; ++t) {
-          mbar_wait(&a_full[t * 2 + buf], use & 1);
-          tc_fence_after();
-          const uint32_t a_t = tmem + 256 + (t * 2 + buf) * 32;
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) umma_ts(tmem + 64 * t, a_t + kk * 8, bd + kk * kstep, idesc, (n | kk) != 0);
-          umma_commit(&a_empty[t * 2 + buf]);
-        }
-        umma_commit(&empty[st]);
-      }
-      umma_commit(acc_full);
-    }
-  } else if (warp >= 4) {
-    // ---------------------------------------------------------------- generators + epilogue
-    const int t = (warp - 4) >> 2, q = warp & 3;
+  } else {
+    // ---------------------------------------------------------------- tile warpgroups (warps 0..15)
+    // Warpgroup t owns token tile t: its 128 threads generate the A operand rows of every slab into
+    // tensor memory (double buffered); the MMAs of slab n are issued by warp n%4 of the warpgroup.
+    const int t = warp >> 2, q = warp & 3;
     const int i = t0 + 128 * t + 32 * q + lane;   // token row of this thread
     const bool valid = i < P.N;
     const size_t grow = (size_t)bh * P.N + i;
     const uint32_t lane_addr = tmem + ((uint32_t)(32 * q) << 16);
     if (has_state) {
-      // Y row lives in registers; X is re-read two features at a time through L1 (a runtime-indexed
-      // register array would be demoted to local memory)
+      ApplyCtx c;
+      c.full = full, c.empty = empty, c.a_empty = a_empty, c.a_ready = a_ready, c.smem = smem;
+      c.tmem = tmem, c.lane_addr = lane_addr, c.idesc = make_idesc_bf16(128, 64, false, !P.b_kmajor);
+      c.kstep = P.b_kmajor ? 2 : 128, c.t = t, c.q = q, c.lane = lane, c.b_kmajor = P.b_kmajor;
       uint32_t yr[32];
       load_row64(P.Y, grow, valid, yr);
-      const uint32_t* xrow = reinterpret_cast<const uint32_t*>(P.X + (valid ? grow : 0) * 64);
+      const uint4* xrow4 = reinterpret_cast<const uint4*>(P.X + (valid ? grow : 0) * 64);
       const uint32_t creg = pack_bf16x2(P.coef_reg, P.coef_reg);
-      const uint32_t c64 = pack_bf16x2(P.coef64, P.coef64);
+      int n = 0;
+      if (P.p == 2) {
 #pragma unroll 1
-      for (int n = 0; n < nslab; ++n) {
-        const int s = s_begin + n, buf = n & 1, use = n >> 1;
-        // scalar of this slab (bf16x2, both halves equal); slab 65 multiplies the X row itself
-        uint32_t xs;
-        if (s < 64) {
-          const uint32_t xw = valid ? __ldg(xrow + (s >> 1)) : 0u;
-          xs = (s & 1) ? __byte_perm(xw, 0, 0x3232) : __byte_perm(xw, 0, 0x1010);
-          xs = mul_bf16x2(xs, creg);
-        } else {
-          xs = s == 64 ? c64 : pack_bf16x2(P.coef65, P.coef65);
-        }
-        mbar_wait(&a_empty[t * 2 + buf], (use & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t a_dst = lane_addr + 256 + (t * 2 + buf) * 32;
-        if (s != 65) {
+        for (int sg = 0; sg < 8; ++sg) {
+          // eight features of the X row per 16-byte load (a per-slab 4-byte load costs one L1 tag
+          // lookup per lane); the inner loop is unrolled so the feature select is static
+          const uint4 xv = valid ? __ldg(xrow4 + sg) : make_uint4(0, 0, 0, 0);
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            uint32_t a[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) a[j] = mul_bf16x2(xs, yr[16 * h + j]);
-            tmem_st16(a_dst + 16 * h, a);
-          }
-        } else {
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            uint32_t a[16];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint4 xv = valid ? __ldg(reinterpret_cast<const uint4*>(xrow) + 4 * h + j) : make_uint4(0, 0, 0, 0);
-              a[4 * j] = mul_bf16x2(xs, xv.x), a[4 * j + 1] = mul_bf16x2(xs, xv.y);
-              a[4 * j + 2] = mul_bf16x2(xs, xv.z), a[4 * j + 3] = mul_bf16x2(xs, xv.w);
-            }
-            tmem_st16(a_dst + 16 * h, a);
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t xw = j < 2 ? xv.x : (j < 4 ? xv.y : (j < 6 ? xv.z : xv.w));
+            uint32_t xs = (j & 1) ? __byte_perm(xw, 0, 0x3232) : __byte_perm(xw, 0, 0x1010);
+            xs = mul_bf16x2(xs, creg);
+            apply_slab_step(c, n, xs, yr);
+            ++n;
           }
         }
-        tmem_wait_st();
-        tc_fence_before();
-        mbar_arrive(&a_full[t * 2 + buf]);
       }
-      mbar_wait(acc_full, 0);
+      apply_slab_step(c, n, pack_bf16x2(P.coef64, P.coef64), yr);   // slab 64 (first-order moments)
+      ++n;
+      if (P.use65) {                                                // slab 65: A = coef65 * X row
+        load_row64(P.X, grow, valid, yr);
+        apply_slab_step(c, n, pack_bf16x2(P.coef65, P.coef65), yr);
+        ++n;
+      }
+      if (lane == 0) umma_commit(&acc_full[t]);   // covers every MMA this warp issued (none: arrives at once)
+      mbar_wait(&acc_full[t], 0);
       tc_fence_after();
     }
     float scale = P.out_scale;
@@ -495,7 +516,7 @@ apply_kernel(const __grid_constant__ CUtensorMap tmS, const ApplyParams P) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem, 512);
+  if (warp == 16) tmem_dealloc(tmem, 512);
 }
 
 // =============================================================================================
@@ -643,20 +664,21 @@ static int launch_build(const Problem& pb, const MomLayout& m, const void* xt, c
                         uint8_t* state, int reverse) {
   CUtensorMap tmXT, tmW, tmW2;
   int rc;
-  if ((rc = make_tmap_bf16_3d(&tmXT, xt, m.Npad, 64, m.BH, (uint64_t)m.Npad * 2, (uint64_t)m.Npad * 128, 64, 64))) return rc;
+  if ((rc = make_tmap_bf16_3d(&tmXT, xt, 64, m.Npad, m.BH, 128, (uint64_t)m.Npad * 128, 64, 64))) return rc;
   if ((rc = make_tmap_bf16_3d(&tmW, w, 64, m.N, m.BH, 128, (uint64_t)m.N * 128, 64, 64))) return rc;
   if ((rc = make_tmap_bf16_3d(&tmW2, w2, 64, m.N, m.BH, 128, (uint64_t)m.N * 128, 64, 64))) return rc;
   BuildParams P{};
   P.N = m.N, P.nblk = (m.N + 63) / 64, P.Lb = m.L / 64, P.nseg = m.nseg, P.reverse = reverse, P.causal = pb.causal;
   P.p = pb.p, P.state = state;
+  P.special_cx = pb.p == 2 ? B_CTAS_P2 - 1 : 0;
   if (!pb.causal) P.nproc = P.nblk;
   else if (reverse) P.nproc = P.nblk - P.Lb;
   else P.nproc = (m.nseg - 1) * P.Lb;
   if (P.nproc <= 0) return FASTMAX_OK;   // single segment: no boundary state needed
   FM_CUDA(cudaFuncSetAttribute(build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
-  dim3 grid(pb.p == 2 ? 5 : 1, m.BH);
+  dim3 grid(pb.p == 2 ? B_CTAS_P2 : 1, m.BH);
   FM_LAUNCH(reverse ? "mom_build_rev" : "mom_build", pb.stream,
-            build_kernel<<<grid, 512, B_SMEM, pb.stream>>>(tmXT, tmW, tmW2, P));
+            build_kernel<<<grid, B_THREADS, B_SMEM, pb.stream>>>(tmXT, tmW, tmW2, P));
   return FASTMAX_OK;
 }
 
@@ -667,7 +689,7 @@ static int launch_apply(const Problem& pb, const MomLayout& m, const char* name,
   P.N = m.N, P.L = m.L, P.nseg = m.nseg, P.causal = pb.causal, P.p = pb.p;
   FM_CUDA(cudaFuncSetAttribute(apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A_SMEM));
   dim3 grid((m.N + APPLY_TOK - 1) / APPLY_TOK, m.BH);
-  FM_LAUNCH(name, pb.stream, apply_kernel<<<grid, 640, A_SMEM, pb.stream>>>(tmS, P));
+  FM_LAUNCH(name, pb.stream, apply_kernel<<<grid, 544, A_SMEM, pb.stream>>>(tmS, P));
   return FASTMAX_OK;
 }
 
@@ -690,11 +712,13 @@ int moments_fwd(const Problem& pb, const void* q, const void* k, const void* v, 
   if ((rc = launch_build(pb, m, w8 + m.off_xt, v, k, state, 0))) return rc;
   // 2. intra-segment part (causal only) and the normaliser
   if (pb.causal) {
-    if ((rc = intra_fwd(pb, m.L, m.Npad, q, k, v, part, g))) return rc;
+    // intra-segment scores + the normaliser (its moment part rides along as one more score MMA)
+    if ((rc = intra_fwd(pb, m.L, m.Npad, q, k, v, part, g, state))) return rc;
+  } else {
+    NormParams np{};
+    np.mode = 0, np.accumulate = 0, np.Q = (const bf16*)q, np.g = g, np.state = state;
+    if ((rc = launch_norm(pb, m, np))) return rc;
   }
-  NormParams np{};
-  np.mode = 0, np.accumulate = pb.causal, np.Q = (const bf16*)q, np.g = g, np.state = state;
-  if ((rc = launch_norm(pb, m, np))) return rc;
   // 3. inter-segment part + normalisation
   ApplyParams ap{};
   ap.mode = APPLY_FWD, ap.state_reverse = 0, ap.b_kmajor = 0, ap.use65 = 0;
@@ -731,12 +755,13 @@ int moments_bwd(const Problem& pb, const void* q, const void* k, const void* v, 
   if ((rc = launch_build(pb, m, w8 + m.off_xt2, u, qd, R, 1))) return rc;
   // 3. intra-segment partials
   if (pb.causal) {
-    if ((rc = intra_dq(pb, m.L, m.Npad, q, u, k, v, dlt, dq_part))) return rc;
+    if ((rc = intra_dq(pb, m.L, m.Npad, q, u, k, v, dlt, dq_part, S))) return rc;
     if ((rc = intra_dkdv(pb, m.L, m.Npad, k, v, q, u, dlt, dk_part, dv_part))) return rc;
+  } else {
+    NormParams np{};
+    np.mode = 1, np.accumulate = 0, np.Q = (const bf16*)q, np.dlt = dlt, np.part = dq_part, np.state = S;
+    if ((rc = launch_norm(pb, m, np))) return rc;
   }
-  NormParams np{};
-  np.mode = 1, np.accumulate = pb.causal, np.Q = (const bf16*)q, np.dlt = dlt, np.part = dq_part, np.state = S;
-  if ((rc = launch_norm(pb, m, np))) return rc;
   // 4. inter-segment parts
   ApplyParams ap{};
   ap.mode = APPLY_DQ, ap.state_reverse = 0, ap.b_kmajor = 1, ap.use65 = 0;

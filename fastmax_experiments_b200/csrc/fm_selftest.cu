@@ -110,3 +110,161 @@ extern "C" int fastmax_selftest_umma(const void* A, const void* Bk, const void* 
             selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(tmA, tmBk, tmBn, (const __nv_bfloat16*)A, D));
   return FASTMAX_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Tensor-pipe rate probe (developer tool): cycles per tcgen05.mma for a few operand configurations.
+// variant bit0: B MN-major, bit1: A from TMEM, bits 2-3: N = 64 << x, bit4: rotate over 4 accumulators
+// ---------------------------------------------------------------------------------------------
+namespace fm {
+namespace {
+using namespace sm100;
+__global__ void __launch_bounds__(128, 1) mmarate_kernel(int variant, int reps, unsigned long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 65536);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 65536 + 64);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 65536 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3C003C00u;  // small bf16 values
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    fence_barrier_init();
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const bool b_mn = variant & 1, a_tmem = variant & 2, rotate = variant & 16;
+  const int N = 64 << ((variant >> 2) & 3);
+  if (variant & 64) {
+    // "clean" warp-uniform issue: the whole warp runs the loop, every operand is derived from
+    // provably warp-uniform values (TMEM base asserted to be 0), one elected lane issues.
+    const int nissuers = (variant & 128) ? 4 : 1;   // concurrent issuing warps (different accumulators)
+    if (warp < nissuers) {
+      const uint32_t tmu = __shfl_sync(0xffffffffu, tmem, 0);   // warp-uniform for the compiler
+      const uint32_t idesc = make_idesc_bf16(128, N, false, b_mn);
+      const uint32_t sb = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+      const uint64_t dA = desc_kmajor_sw128(sb);
+      const uint64_t dB = b_mn ? desc_mnmajor_sw128(sb + 16384, 8192) : desc_kmajor_sw128(sb + 16384);
+      const uint32_t kstep = b_mn ? 128 : 2;
+      long long t0 = clock64();
+      for (int r = 0; r < reps; r += 4) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint32_t d = tmu + (rotate ? kk * 64 : 0) + (nissuers > 1 ? __shfl_sync(0xffffffffu, warp, 0) * 64 : 0);
+          if (elect_one()) {
+            if (a_tmem) umma_ts(d, tmu + 448 + kk * 8, dB + kk * kstep, idesc, 1);
+            else umma_ss(d, dA + kk * 2, dB + kk * kstep, idesc, 1);
+          }
+        }
+      }
+      long long t1 = clock64();
+      if (tid == 0) {
+        umma_commit(&bars[0]);
+        mbar_wait(&bars[0], 0);
+        long long t2 = clock64();
+        out[0] = (unsigned long long)(t1 - t0);
+        out[1] = (unsigned long long)(t2 - t0);
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+    return;
+  }
+  const bool uniform_issue = variant & 32;   // whole warp runs the loop, one elected lane issues
+  if (uniform_issue ? warp == 0 : tid == 0) {
+    const uint32_t idesc = make_idesc_bf16(128, N, false, b_mn);
+    const uint64_t dA = desc_kmajor_sw128(smem_u32(smem));
+    const uint64_t dB = b_mn ? desc_mnmajor_sw128(smem_u32(smem + 16384), 8192) : desc_kmajor_sw128(smem_u32(smem + 16384));
+    const int nacc = rotate ? 4 : 1;
+    const uint32_t tm = uniform_issue ? __shfl_sync(0xffffffffu, tmem, 0) : tmem;
+    long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+      const uint32_t d = tm + (nacc > 1 ? (r & 3) * 64 : 0);
+      const int kk = r & 3;
+      if (!uniform_issue || elect_one()) {
+        if (a_tmem) umma_ts(d, tm + 448 + kk * 8, dB + (b_mn ? kk * 128 : kk * 2), idesc, 1);
+        else umma_ss(d, dA + kk * 2, dB + (b_mn ? kk * 128 : kk * 2), idesc, 1);
+      }
+      if (uniform_issue) __syncwarp();
+    }
+    long long t1 = clock64();
+    if (tid == 0) {
+      umma_commit(&bars[0]);
+      mbar_wait(&bars[0], 0);
+      long long t2 = clock64();
+      out[0] = (unsigned long long)(t1 - t0);
+      out[1] = (unsigned long long)(t2 - t0);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+}  // namespace
+}  // namespace fm
+
+extern "C" int fastmax_selftest_mmarate(int variant, int reps, unsigned long long* out_dev, void* stream) {
+  using namespace fm;
+  const int smem = 65536 + 1024 + 1024;
+  FM_CUDA(cudaFuncSetAttribute(mmarate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  FM_LAUNCH("selftest_mmarate", (cudaStream_t)stream,
+            mmarate_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(variant, reps, out_dev));
+  return FASTMAX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ALU rate probe (developer tool): cycles per warp-instruction of a few candidate element-wise ops,
+// 8 independent chains per thread.  kind: 0 mul.bf16x2, 1 fma.bf16x2, 2 mul.f16x2, 3 mul.f32, 4 mul.f32x2
+// ---------------------------------------------------------------------------------------------
+namespace fm {
+namespace {
+template <int KIND>
+__global__ void alurate_kernel(int iters, unsigned long long* out, uint32_t seed) {
+  uint32_t r[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r[i] = seed + i * 0x00010001u + threadIdx.x;
+  const uint32_t m = 0x3F803F80u ^ (seed & 1);
+  unsigned long long m2 = ((unsigned long long)0x3F800000u << 32) | 0x3F800000u;
+  unsigned long long v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = ((unsigned long long)r[i] << 32) | r[i];
+  long long t0 = clock64();
+#pragma unroll 1
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (KIND == 0) asm volatile("mul.rn.bf16x2 %0, %0, %1;" : "+r"(r[i]) : "r"(m));
+      else if (KIND == 1) asm volatile("fma.rn.bf16x2 %0, %0, %1, %1;" : "+r"(r[i]) : "r"(m));
+      else if (KIND == 2) asm volatile("mul.rn.f16x2 %0, %0, %1;" : "+r"(r[i]) : "r"(m));
+      else if (KIND == 3) asm volatile("mul.rn.f32 %0, %0, %1;" : "+f"(*reinterpret_cast<float*>(&r[i])) : "f"(1.0001f));
+      else if (KIND == 4) asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(v[i]) : "l"(m2));
+    }
+  }
+  long long t1 = clock64();
+  uint32_t acc = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc ^= r[i] ^ (uint32_t)v[i];
+  if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = (unsigned long long)(t1 - t0);
+  if (acc == 0x12345678u) out[1] = acc;
+}
+}  // namespace
+}  // namespace fm
+
+extern "C" int fastmax_selftest_alurate(int kind, int iters, int threads, unsigned long long* out_dev, void* stream) {
+  using namespace fm;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (kind) {
+    case 0: FM_LAUNCH("selftest_alurate", st, alurate_kernel<0><<<1, threads, 0, st>>>(iters, out_dev, 12345u)); break;
+    case 1: FM_LAUNCH("selftest_alurate", st, alurate_kernel<1><<<1, threads, 0, st>>>(iters, out_dev, 12345u)); break;
+    case 2: FM_LAUNCH("selftest_alurate", st, alurate_kernel<2><<<1, threads, 0, st>>>(iters, out_dev, 12345u)); break;
+    case 3: FM_LAUNCH("selftest_alurate", st, alurate_kernel<3><<<1, threads, 0, st>>>(iters, out_dev, 12345u)); break;
+    default: FM_LAUNCH("selftest_alurate", st, alurate_kernel<4><<<1, threads, 0, st>>>(iters, out_dev, 12345u)); break;
+  }
+  return FASTMAX_OK;
+}

@@ -68,6 +68,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Warp-collective wait: one lane polls, the warp reconverges.  Every polling thread costs an
+// operation on the SM's (serial) mbarrier unit, so hundreds of threads spinning on the same
+// barrier throttle every arrive/wait of the CTA; one poller per warp is enough.
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+  __syncwarp();
+}
+
 // ---------------------------------------------------------------- TMA ---------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
