@@ -82,7 +82,7 @@ int intra_fwd(const Problem& pb, int L, int Npad, const void* q, const void* k, 
 int intra_dq(const Problem& pb, int L, int Npad, const void* q, const void* u, const void* k, const void* v,
              const float* dlt, float* dq_part, const uint8_t* state);
 int intra_dkdv(const Problem& pb, int L, int Npad, const void* k, const void* v, const void* q, const void* u,
-               const float* dlt, float* dk_part, float* dv_part);
+               const float* dlt, float* dk_part, float* dv_part, const uint8_t* rstate);
 int moments_seg_len(int N);
 size_t moments_workspace_bytes(int B, int H, int N, int causal, bool bwd);
 void moments_flops(int B, int H, int N, int p, int causal, double* fwd, double* bwd);

@@ -37,7 +37,8 @@ struct IntraParams {
   float* out0;             // FWD: O partial; DQ: dQ partial; DKDV: dV partial   (BH,N,64) fp32
   float* out1;             // DKDV: dK partial
   float* g;                // FWD: normaliser (BH,N): intra rowsum + moment part of the segment boundary
-  const uint8_t* state;    // forward-direction boundary states (normaliser column), nullable
+  const uint8_t* state;    // boundary states whose normaliser column is folded in here (FWD, DQ: forward-
+                           // direction states; DKDV: reverse-direction states), nullable
   int nseg;
 };
 
@@ -48,7 +49,7 @@ template <int MODE> struct IntraCfg {
   static constexpr int STAGE_BYTES = 2 * 8192 + (MODE == INTRA_DKDV ? 256 : 0);
   static constexpr int STAGE_STRIDE = 2 * 8192 + 1024;            // keeps every tile 1024-aligned
   static constexpr int RES_BYTES = OUT_TILES * RES_OPS * 16384;
-  static constexpr int NORM_BYTES = MODE == INTRA_DKDV ? 0 : 8192 + 1024;   // slab 65 (bf16) + N1 (fp32)
+  static constexpr int NORM_BYTES = 8192 + 1024;   // slab 65 of the boundary state (bf16)
   static constexpr int SMEM = RES_BYTES + STAGES * STAGE_STRIDE + NORM_BYTES + 1024 + 1024;
 };
 
@@ -85,7 +86,7 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
   // moment part of the normaliser column (FWD: g, DQ: the -dlt (N1 + a N2 q) term): only segments
   // that have a boundary state
   const int seg = c0 / P.L;
-  const bool has_norm = MODE != INTRA_DKDV && P.state != nullptr && seg > 0;
+  const bool has_norm = P.state != nullptr && (MODE == INTRA_DKDV ? seg < P.nseg - 1 : seg > 0);
   const int rec_idx = bh * P.nseg + seg;
 
   if (warp == 0) {
@@ -301,18 +302,17 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
     }
     // ---- moment part of the normaliser column: T_o = R1_o . N2 (one more score-like MMA per output
     // tile, into the two halves of the warpgroup's score buffer)
-    if constexpr (MODE != INTRA_DKDV) {
-      if (has_norm && issuer) {
-        if (npair > 0) mbar_wait(&s_free[w], (npair - 1) & 1);
-        tc_fence_after();
-        const uint64_t dN = desc_kmajor_sw128(smem_u32(norm_s));
+    if (has_norm && issuer) {
+      if (npair > 0) mbar_wait(&s_free[w], (npair - 1) & 1);
+      tc_fence_after();
+      const uint64_t dN = desc_kmajor_sw128(smem_u32(norm_s));
 #pragma unroll
-        for (int x = 0; x < 2; ++x) {
-          const uint64_t dA = desc_kmajor_sw128(smem_u32(res + otile[x] * 16384));
+      for (int x = 0; x < 2; ++x) {
+        if (x >= n_ot) break;
+        const uint64_t dA = desc_kmajor_sw128(smem_u32(res + otile[x] * 16384));
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            umma_ss(tmem + 256 + 128 * w + 64 * x, dA + kk * 2, dN + kk * 2, id_kk, kk > 0);
-        }
+        for (int kk = 0; kk < 4; ++kk)
+          umma_ss(tmem + 256 + 128 * w + 64 * x, dA + kk * 2, dN + kk * 2, id_kk, kk > 0);
       }
     }
     if (issuer) umma_commit(&acc_done[w]);
@@ -337,7 +337,17 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
         for (int h = 0; h < 2; ++h) {
           uint32_t v[32];
           tmem_ld32(lane_addr + col + 32 * h, v);
-          if constexpr (MODE != INTRA_DKDV) {
+          if constexpr (MODE == INTRA_DKDV) {
+            if (has_norm && a2 == 1) {   // dk_part[l] += RN1[l] + a (RN2 k)[l]
+              uint32_t tn[32];
+              tmem_ld32(sbuf + 32 * h, tn);
+              tmem_wait_ld();
+#pragma unroll
+              for (int c = 0; c < 32; ++c)
+                v[c] = __float_as_uint(__uint_as_float(v[c]) +
+                                       fmaf(P.p == 2 ? a : 0.f, __uint_as_float(tn[c]), __ldg(vec + 64 + 32 * h + c)));
+            }
+          } else {
             if (has_norm) {   // CTA-uniform
               uint32_t tn[32];
               tmem_ld32(sbuf + 64 * x + 32 * h, tn);
@@ -426,8 +436,8 @@ int intra_dq(const Problem& pb, int L, int Npad, const void* q, const void* u, c
   return launch_intra_t<INTRA_DQ>(pb, L, Npad, q, u, k, v, dlt, dq_part, nullptr, nullptr, state, "mom_intra_dq");
 }
 int intra_dkdv(const Problem& pb, int L, int Npad, const void* k, const void* v, const void* q, const void* u,
-               const float* dlt, float* dk_part, float* dv_part) {
-  return launch_intra_t<INTRA_DKDV>(pb, L, Npad, k, v, q, u, dlt, dv_part, dk_part, nullptr, nullptr, "mom_intra_dkdv");
+               const float* dlt, float* dk_part, float* dv_part, const uint8_t* rstate) {
+  return launch_intra_t<INTRA_DKDV>(pb, L, Npad, k, v, q, u, dlt, dv_part, dk_part, nullptr, rstate, "mom_intra_dkdv");
 }
 
 }  // namespace fm

@@ -302,7 +302,22 @@ build_kernel(const __grid_constant__ CUtensorMap tmXT, const __grid_constant__ C
 }
 
 // =============================================================================================
-// apply kernel
+// apply kernel ("two-stage" contraction)
+//
+//   out[i][c] = scale_i ( sum_x coef X[i][x] * T_x[i][c]  +  coef64 * T_64[i][c]  + vec[c] + partial[i][c] )
+//   T_x = Y_tile . B_x        (B_x = slab x of the boundary state, 64x64)
+//
+// i.e. the second-order contraction  sum_{x,y} X[x] Y[y] S[x][y][c]  is split into a plain GEMM of the
+// token tile Y (128x64, resident in shared memory) against FOUR slabs at once (one 128x256x16
+// tcgen05.mma per k-step: large-N MMAs are the only ones a single issuing thread can keep the
+// tensor pipe busy with, see tools/mmarate.py) and a per-token scalar multiply-add over x that runs
+// on the CUDA cores while the fp32 T tile is read out of tensor memory.  No operand generation, and
+// the products with X stay in fp32.
+//
+//   forward o : X = Y = q, slabs read MN-major (contract y)          coef a^2/2, coef64 a
+//   dq        : X = q, Y = do/g, slabs read K-major (contract a)      coef a,     coef64 1
+//   dv        : X = Y = k on the reverse states, MN-major             coef a^2/2, coef64 a
+//   dk        : X = k, Y = v on the reverse states, K-major           coef a,     coef64 1
 // =============================================================================================
 enum ApplyMode { APPLY_FWD = 0, APPLY_DQ = 1, APPLY_DV = 2, APPLY_DK = 3 };
 
@@ -310,11 +325,9 @@ struct ApplyParams {
   int N, L, nseg, causal, p, mode;
   int state_reverse;        // 1: records are exclusive suffixes (last segment has none)
   int b_kmajor;             // 1: contraction over the slab's contiguous index (dq, dk)
-  int use65;                // 1: slab 65 joins the accumulator with A = coef65 * X (dk)
-  float coef_reg, coef64, coef65, out_scale;
+  float coef_reg, coef64, out_scale;
   int vec_sel;              // -1 none, 0: vec[0:64), 1: vec[64:128)
-  const bf16* X;
-  const bf16* Y;
+  const bf16* X;            // per-token scalars
   const float* partial;     // (BH, N, 64) fp32 intra-segment partial (nullable)
   const float* gden;        // (BH, N) fp32: divide rows by it (forward) (nullable)
   bf16* out;
@@ -322,95 +335,50 @@ struct ApplyParams {
 };
 
 constexpr int A_STAGES = 6;
-constexpr int A_SMEM = A_STAGES * 8192 + 1024 + 1024;
+constexpr int A_STAGE_BYTES = 2 * 8192;                  // two slabs per MMA (N = 128)
+constexpr int A_TOK = APPLY_TOK;                         // 4 token tiles per CTA
+constexpr int A_RES_BYTES = 4 * 16384;                   // four resident 128x64 Y tiles
+constexpr int A_SMEM = A_RES_BYTES + A_STAGES * A_STAGE_BYTES + 1024 + 1024;
+constexpr int A_THREADS = 19 * 32;                       // 16 epilogue warps, 2 MMA issuers, TMA producer
 
-__device__ __forceinline__ void load_row64(const bf16* base, size_t row, bool valid, uint32_t* r) {
-  const uint4* src = reinterpret_cast<const uint4*>(base + row * 64);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    uint4 v = valid ? __ldg(src + i) : make_uint4(0, 0, 0, 0);
-    r[4 * i] = v.x, r[4 * i + 1] = v.y, r[4 * i + 2] = v.z, r[4 * i + 3] = v.w;
-  }
-}
-
-// One slab step of a tile warpgroup: write A = xs * src (bf16x2 scalar times the 64-wide row held in
-// registers) into the tile's A buffer `buf`, publish it, and -- on the warp whose turn it is --
-// issue the tile's four MMAs for this slab.
-struct ApplyCtx {
-  uint64_t *full, *empty, *a_empty, *a_ready;
-  uint8_t* smem;
-  uint32_t tmem, lane_addr, idesc, kstep;
-  int t, q, lane, b_kmajor;
-};
-
-__device__ __forceinline__ void apply_slab_step(const ApplyCtx& c, int n, uint32_t xs, const uint32_t* src) {
-  const int buf = n & 1, use = n >> 1;
-  mbar_wait(&c.a_empty[c.t * 2 + buf], (use & 1) ^ 1);
-  tc_fence_after();
-  const uint32_t a_dst = c.lane_addr + 256 + (c.t * 2 + buf) * 32;
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    uint32_t a[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) a[j] = mul_bf16x2(xs, src[16 * h + j]);
-    tmem_st16(a_dst + 16 * h, a);
-  }
-  tmem_wait_st();
-  tc_fence_before();
-  __syncwarp();
-  if (c.lane == 0) mbar_arrive(&c.a_ready[c.t * 2 + buf]);
-  if ((n & 3) == c.q) {
-    if (c.lane == 0) {
-      const int st = n % A_STAGES, ph = (n / A_STAGES) & 1;
-      mbar_wait(&c.a_ready[c.t * 2 + buf], use & 1);
-      mbar_wait(&c.full[st], ph);
-      tc_fence_after();
-      const uint32_t sb = smem_u32(c.smem + st * 8192);
-      const uint64_t bd = c.b_kmajor ? desc_kmajor_sw128(sb) : desc_mnmajor_sw128(sb, 8192);
-      const uint32_t a_t = c.tmem + 256 + (c.t * 2 + buf) * 32;
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk)
-        umma_ts(c.tmem + 64 * c.t, a_t + kk * 8, bd + kk * c.kstep, c.idesc, (n | kk) != 0);
-      umma_commit(&c.a_empty[c.t * 2 + buf]);
-      umma_commit(&c.empty[st]);
-    }
-    __syncwarp();
-  }
-}
-
-__global__ void __launch_bounds__(544, 1)
-apply_kernel(const __grid_constant__ CUtensorMap tmS, const ApplyParams P) {
+// Each token tile owns a private 128-column T buffer in tensor memory and its own barrier pair.
+// Measured alternatives on B200 at the headline shape (ms per apply launch): this layout 2.3;
+// two shared N=256 T buffers with one issuer 2.6; two tiles per CTA with a column-split epilogue
+// 2.9; issuing from the epilogue warpgroups 3.2; generated A operands in tensor memory 3.2-5.2.
+__global__ void __launch_bounds__(A_THREADS, 1)
+apply_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmY, const ApplyParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A_STAGES * 8192);
-  uint64_t* full = bars;            // [6]  slab landed (TMA)
-  uint64_t* empty = bars + 6;       // [6]  slab consumed by the MMAs of all four tiles (count 4)
-  uint64_t* a_empty = bars + 12;    // [4][2] A buffer of tile t drained by its MMAs
-  uint64_t* a_ready = bars + 20;    // [4][2] A buffer of tile t written by its 4 warps (count 4)
-  uint64_t* acc_full = bars + 28;   // [4]  all MMAs of tile t complete (count 4: one commit per warp)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
-  float* vec_s = reinterpret_cast<float*>(bars + 34);  // [64]
+  uint8_t* res = smem;                       // [4 tiles][16 KiB]
+  uint8_t* ring = smem + A_RES_BYTES;        // [6 stages][16 KiB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + A_STAGES * A_STAGE_BYTES);
+  uint64_t* full = bars;            // [6] slab pair landed
+  uint64_t* empty = bars + 6;       // [6] slab pair consumed by the MMAs of all four tiles (count 2: one per issuer)
+  uint64_t* t_full = bars + 12;     // [4] T tile of (slab pair, tile t) is in tensor memory
+  uint64_t* t_free = bars + 16;     // [4] ... and has been read out by warpgroup t (count 4: one per warp)
+  uint64_t* res_full = bars + 20;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+  float* vec_s = reinterpret_cast<float*>(bars + 24);  // [64]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int bh = blockIdx.y;
-  const int t0 = blockIdx.x * APPLY_TOK;
+  const int t0 = blockIdx.x * A_TOK;
   const int seg = t0 / P.L;
   const bool has_state = !P.causal || (P.state_reverse ? seg < P.nseg - 1 : seg > 0);
   const int rec_idx = P.causal ? bh * P.nseg + seg : bh;
-  const int s_begin = P.p == 2 ? 0 : 64;
-  const int s_end = P.use65 ? 66 : 65;
-  const int nslab = s_end - s_begin;
+  const int ngroups = (P.p == 2 ? 32 : 0) + 1;     // 32 pairs of second-order slabs + slab 64
 
-  if (warp == 16) {
+  if (warp == 18) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
   if (tid == 0) {
-    for (int i = 0; i < A_STAGES; ++i) mbar_init(&full[i], 1), mbar_init(&empty[i], 4);
-    for (int i = 0; i < 8; ++i) mbar_init(&a_empty[i], 1), mbar_init(&a_ready[i], 4);
-    for (int i = 0; i < 4; ++i) mbar_init(&acc_full[i], 4);
+    for (int i = 0; i < A_STAGES; ++i) mbar_init(&full[i], 1), mbar_init(&empty[i], 2);
+    for (int i = 0; i < 4; ++i) mbar_init(&t_full[i], 1), mbar_init(&t_free[i], 4);
+    mbar_init(res_full, 1);
     fence_barrier_init();
     tma_prefetch_desc(&tmS);
+    tma_prefetch_desc(&tmY);
   }
   if (tid < 64) {
     float v = 0.f;
@@ -423,100 +391,124 @@ apply_kernel(const __grid_constant__ CUtensorMap tmS, const ApplyParams P) {
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 16) {
-    // ---------------------------------------------------------------- TMA producer (state slabs)
+  if (warp == 18) {
+    // ---------------------------------------------------------------- TMA producer
     if (lane == 0 && has_state) {
-      for (int n = 0; n < nslab; ++n) {
-        const int st = n % A_STAGES, ph = (n / A_STAGES) & 1;
-        mbar_wait(&empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&full[st], 8192);
-        tma_load_3d(smem + st * 8192, &tmS, &full[st], 0, (s_begin + n) * 64, rec_idx);
+      mbar_arrive_expect_tx(res_full, A_RES_BYTES);
+      for (int t = 0; t < 4; ++t)
+        for (int h = 0; h < 2; ++h) tma_load_3d(res + t * 16384 + h * 8192, &tmY, res_full, 0, t0 + t * 128 + h * 64, bh);
+      for (int gi = 0; gi < ngroups; ++gi) {
+        const int st = gi % A_STAGES, ph = (gi / A_STAGES) & 1;
+        const bool last = gi == ngroups - 1;
+        mbar_wait(&empty[st], ph ^ 1, 1000 + gi);
+        mbar_arrive_expect_tx(&full[st], last ? 8192 : A_STAGE_BYTES);
+        uint8_t* dst = ring + st * A_STAGE_BYTES;
+        if (last) {
+          tma_load_3d(dst, &tmS, &full[st], 0, 64 * 64, rec_idx);
+        } else {
+          tma_load_3d(dst, &tmS, &full[st], 0, (2 * gi) * 64, rec_idx);
+          tma_load_3d(dst + 8192, &tmS, &full[st], 0, (2 * gi + 1) * 64, rec_idx);
+        }
+      }
+    }
+  } else if (warp >= 16) {
+    // ---------------------------------------------------------------- MMA issuers (tiles 0,1 | tiles 2,3)
+    // one thread sustains one tcgen05.mma per ~110 cycles; a 128x128x16 MMA occupies the pipe for ~64
+    if (lane == 0 && has_state) {
+      const int tb = (warp - 16) * 2;
+      const uint32_t id128 = make_idesc_bf16(128, 128, false, !P.b_kmajor);
+      const uint32_t id64 = make_idesc_bf16(128, 64, false, !P.b_kmajor);
+      const uint32_t kstep = P.b_kmajor ? 2 : 128;
+      mbar_wait(res_full, 0);
+      for (int gi = 0; gi < ngroups; ++gi) {
+        const int st = gi % A_STAGES;
+        const bool last = gi == ngroups - 1;
+        mbar_wait(&full[st], (gi / A_STAGES) & 1, 2000 + gi);
+        const uint32_t sb = smem_u32(ring + st * A_STAGE_BYTES);
+        const uint64_t bd = P.b_kmajor ? desc_kmajor_sw128(sb) : desc_mnmajor_sw128(sb, 8192);
+        const uint32_t idesc = last ? id64 : id128;
+#pragma unroll
+        for (int tt = 0; tt < 2; ++tt) {
+          const int t = tb + tt;
+          if (gi > 0) mbar_wait(&t_free[t], (gi - 1) & 1, 3000 + gi);
+          tc_fence_after();
+          const uint64_t ad = desc_kmajor_sw128(smem_u32(res + t * 16384));
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) umma_ss(tmem + 128 * t, ad + kk * 2, bd + kk * kstep, idesc, kk > 0);
+          umma_commit(&t_full[t]);
+        }
+        umma_commit(&empty[st]);
       }
     }
   } else {
-    // ---------------------------------------------------------------- tile warpgroups (warps 0..15)
-    // Warpgroup t owns token tile t: its 128 threads generate the A operand rows of every slab into
-    // tensor memory (double buffered); the MMAs of slab n are issued by warp n%4 of the warpgroup.
+    // ---------------------------------------------------------------- epilogue warpgroups (warps 0..15)
     const int t = warp >> 2, q = warp & 3;
     const int i = t0 + 128 * t + 32 * q + lane;   // token row of this thread
     const bool valid = i < P.N;
     const size_t grow = (size_t)bh * P.N + i;
-    const uint32_t lane_addr = tmem + ((uint32_t)(32 * q) << 16);
-    if (has_state) {
-      ApplyCtx c;
-      c.full = full, c.empty = empty, c.a_empty = a_empty, c.a_ready = a_ready, c.smem = smem;
-      c.tmem = tmem, c.lane_addr = lane_addr, c.idesc = make_idesc_bf16(128, 64, false, !P.b_kmajor);
-      c.kstep = P.b_kmajor ? 2 : 128, c.t = t, c.q = q, c.lane = lane, c.b_kmajor = P.b_kmajor;
-      uint32_t yr[32];
-      load_row64(P.Y, grow, valid, yr);
-      const uint4* xrow4 = reinterpret_cast<const uint4*>(P.X + (valid ? grow : 0) * 64);
-      const uint32_t creg = pack_bf16x2(P.coef_reg, P.coef_reg);
-      int n = 0;
-      if (P.p == 2) {
-#pragma unroll 1
-        for (int sg = 0; sg < 8; ++sg) {
-          // eight features of the X row per 16-byte load (a per-slab 4-byte load costs one L1 tag
-          // lookup per lane); the inner loop is unrolled so the feature select is static
-          const uint4 xv = valid ? __ldg(xrow4 + sg) : make_uint4(0, 0, 0, 0);
+    const uint32_t tbuf = tmem + ((uint32_t)(32 * q) << 16) + 128 * t;
+    float O[64];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint32_t xw = j < 2 ? xv.x : (j < 4 ? xv.y : (j < 6 ? xv.z : xv.w));
-            uint32_t xs = (j & 1) ? __byte_perm(xw, 0, 0x3232) : __byte_perm(xw, 0, 0x1010);
-            xs = mul_bf16x2(xs, creg);
-            apply_slab_step(c, n, xs, yr);
-            ++n;
+    for (int c = 0; c < 64; ++c) O[c] = 0.f;
+    if (has_state) {
+      const uint32_t* xrow = reinterpret_cast<const uint32_t*>(P.X + (valid ? grow : 0) * 64);
+#pragma unroll 1
+      for (int gi = 0; gi < ngroups; ++gi) {
+        const bool last = gi == ngroups - 1;
+        float xs[2];
+        if (!last) {
+          const uint32_t xw = valid ? __ldg(xrow + gi) : 0u;
+          xs[0] = __uint_as_float(xw << 16) * P.coef_reg;
+          xs[1] = __uint_as_float(xw & 0xffff0000u) * P.coef_reg;
+        } else {
+          xs[0] = P.coef64, xs[1] = 0.f;
+        }
+        mbar_wait(&t_full[t], gi & 1, 4000 + gi);
+        tc_fence_after();
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          if (j > 0 && last) break;
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            uint32_t v[16];
+            tmem_ld16(tbuf + 64 * j + 16 * h, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int c = 0; c < 16; ++c) O[16 * h + c] = fmaf(xs[j], __uint_as_float(v[c]), O[16 * h + c]);
           }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&t_free[t]);
       }
-      apply_slab_step(c, n, pack_bf16x2(P.coef64, P.coef64), yr);   // slab 64 (first-order moments)
-      ++n;
-      if (P.use65) {                                                // slab 65: A = coef65 * X row
-        load_row64(P.X, grow, valid, yr);
-        apply_slab_step(c, n, pack_bf16x2(P.coef65, P.coef65), yr);
-        ++n;
-      }
-      if (lane == 0) umma_commit(&acc_full[t]);   // covers every MMA this warp issued (none: arrives at once)
-      mbar_wait(&acc_full[t], 0);
-      tc_fence_after();
     }
     float scale = P.out_scale;
     if (valid && P.gden) scale *= 1.f / P.gden[grow];
-    const float4* part = P.partial ? reinterpret_cast<const float4*>(P.partial + grow * 64) : nullptr;
-    uint4* dst = reinterpret_cast<uint4*>(P.out + grow * 64);
-#pragma unroll 1
-    for (int h = 0; h < 2; ++h) {
-      uint32_t v[32];
-      if (has_state) {
-        tmem_ld32(lane_addr + 64 * t + 32 * h, v);   // warp-collective: every lane takes part
-        tmem_wait_ld();
-      } else {
+    if (valid) {
+      const float4* part = P.partial ? reinterpret_cast<const float4*>(P.partial + grow * 64) : nullptr;
+      uint4* dst = reinterpret_cast<uint4*>(P.out + grow * 64);
 #pragma unroll
-        for (int c = 0; c < 32; ++c) v[c] = 0u;
-      }
-      if (valid) {
+      for (int c8 = 0; c8 < 8; ++c8) {
+        float r[8];
 #pragma unroll
-        for (int c8 = 0; c8 < 4; ++c8) {
-          float r[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) r[j] = __uint_as_float(v[8 * c8 + j]) + vec_s[32 * h + 8 * c8 + j];
-          if (part) {
-            float4 p0 = __ldg(part + 8 * h + 2 * c8), p1 = __ldg(part + 8 * h + 2 * c8 + 1);
-            r[0] += p0.x, r[1] += p0.y, r[2] += p0.z, r[3] += p0.w;
-            r[4] += p1.x, r[5] += p1.y, r[6] += p1.z, r[7] += p1.w;
-          }
-          uint4 o;
-          o.x = pack_bf16x2(r[0] * scale, r[1] * scale);
-          o.y = pack_bf16x2(r[2] * scale, r[3] * scale);
-          o.z = pack_bf16x2(r[4] * scale, r[5] * scale);
-          o.w = pack_bf16x2(r[6] * scale, r[7] * scale);
-          dst[4 * h + c8] = o;
+        for (int j = 0; j < 8; ++j) r[j] = O[8 * c8 + j] + vec_s[8 * c8 + j];
+        if (part) {
+          float4 p0 = __ldg(part + 2 * c8), p1 = __ldg(part + 2 * c8 + 1);
+          r[0] += p0.x, r[1] += p0.y, r[2] += p0.z, r[3] += p0.w;
+          r[4] += p1.x, r[5] += p1.y, r[6] += p1.z, r[7] += p1.w;
         }
+        uint4 o;
+        o.x = pack_bf16x2(r[0] * scale, r[1] * scale);
+        o.y = pack_bf16x2(r[2] * scale, r[3] * scale);
+        o.z = pack_bf16x2(r[4] * scale, r[5] * scale);
+        o.w = pack_bf16x2(r[6] * scale, r[7] * scale);
+        dst[c8] = o;
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 16) tmem_dealloc(tmem, 512);
+  if (warp == 18) tmem_dealloc(tmem, 512);
 }
 
 // =============================================================================================
@@ -569,11 +561,12 @@ __global__ void __launch_bounds__(256) norm_kernel(const NormParams P) {
       for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
       if (lane == 0) P.g[grow] = (P.accumulate ? P.g[grow] : 0.f) + count + s;
     } else {
-      const float d = P.dlt[(size_t)bh * ((P.N + 63) / 64 * 64) + i];
+      // mode 1 (dq): -dlt (N1 + a N2 q)  on the forward states;  mode 2 (dk): RN1 + a RN2 k  on the reverse ones
+      const float d = P.mode == 1 ? -P.dlt[(size_t)bh * ((P.N + 63) / 64 * 64) + i] : 1.f;
       float* pr = P.part + grow * 64;
       const float b0 = P.accumulate ? pr[lane] : 0.f, b1 = P.accumulate ? pr[lane + 32] : 0.f;
-      pr[lane] = b0 - d * (n1[lane] + P.a * w0);
-      pr[lane + 32] = b1 - d * (n1[lane + 32] + P.a * w1);
+      pr[lane] = b0 + d * (n1[lane] + P.a * w0);
+      pr[lane + 32] = b1 + d * (n1[lane + 32] + P.a * w1);
     }
   }
 }
@@ -682,21 +675,23 @@ static int launch_build(const Problem& pb, const MomLayout& m, const void* xt, c
   return FASTMAX_OK;
 }
 
-static int launch_apply(const Problem& pb, const MomLayout& m, const char* name, ApplyParams P) {
-  CUtensorMap tmS;
+static int launch_apply(const Problem& pb, const MomLayout& m, const char* name, ApplyParams P, const void* Y) {
+  CUtensorMap tmS, tmY;
   int rc;
   if ((rc = make_tmap_bf16_3d(&tmS, P.state, 64, NSLAB * 64, (uint64_t)m.BH * m.nrec, 128, REC_BYTES, 64, 64))) return rc;
+  if ((rc = make_tmap_bf16_3d(&tmY, Y, 64, m.N, m.BH, 128, (uint64_t)m.N * 128, 64, 64))) return rc;
   P.N = m.N, P.L = m.L, P.nseg = m.nseg, P.causal = pb.causal, P.p = pb.p;
   FM_CUDA(cudaFuncSetAttribute(apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A_SMEM));
-  dim3 grid((m.N + APPLY_TOK - 1) / APPLY_TOK, m.BH);
-  FM_LAUNCH(name, pb.stream, apply_kernel<<<grid, 544, A_SMEM, pb.stream>>>(tmS, P));
+  dim3 grid((m.N + A_TOK - 1) / A_TOK, m.BH);
+  FM_LAUNCH(name, pb.stream, apply_kernel<<<grid, A_THREADS, A_SMEM, pb.stream>>>(tmS, tmY, P));
   return FASTMAX_OK;
 }
 
 static int launch_norm(const Problem& pb, const MomLayout& m, NormParams P) {
   P.N = m.N, P.L = m.L, P.nseg = m.nseg, P.causal = pb.causal, P.p = pb.p, P.a = pb.inv_c;
   dim3 grid((m.N + 63) / 64, m.BH);
-  FM_LAUNCH(P.mode == 0 ? "mom_norm_fwd" : "mom_norm_dq", pb.stream, norm_kernel<<<grid, 256, 0, pb.stream>>>(P));
+  FM_LAUNCH(P.mode == 0 ? "mom_norm_fwd" : (P.mode == 1 ? "mom_norm_dq" : "mom_norm_dk"), pb.stream,
+            norm_kernel<<<grid, 256, 0, pb.stream>>>(P));
   return FASTMAX_OK;
 }
 
@@ -721,11 +716,11 @@ int moments_fwd(const Problem& pb, const void* q, const void* k, const void* v, 
   }
   // 3. inter-segment part + normalisation
   ApplyParams ap{};
-  ap.mode = APPLY_FWD, ap.state_reverse = 0, ap.b_kmajor = 0, ap.use65 = 0;
-  ap.coef_reg = 0.5f * a * a, ap.coef64 = a, ap.coef65 = 0.f, ap.out_scale = 1.f, ap.vec_sel = 0;
-  ap.X = (const bf16*)q, ap.Y = (const bf16*)q, ap.partial = pb.causal ? part : nullptr, ap.gden = g;
+  ap.mode = APPLY_FWD, ap.state_reverse = 0, ap.b_kmajor = 0;
+  ap.coef_reg = 0.5f * a * a, ap.coef64 = a, ap.out_scale = 1.f, ap.vec_sel = 0;
+  ap.X = (const bf16*)q, ap.partial = pb.causal ? part : nullptr, ap.gden = g;
   ap.out = (bf16*)o, ap.state = state;
-  return launch_apply(pb, m, "mom_apply_fwd", ap);
+  return launch_apply(pb, m, "mom_apply_fwd", ap, q);
 }
 
 int moments_bwd(const Problem& pb, const void* q, const void* k, const void* v, const void* o, const float* g,
@@ -756,35 +751,35 @@ int moments_bwd(const Problem& pb, const void* q, const void* k, const void* v, 
   // 3. intra-segment partials
   if (pb.causal) {
     if ((rc = intra_dq(pb, m.L, m.Npad, q, u, k, v, dlt, dq_part, S))) return rc;
-    if ((rc = intra_dkdv(pb, m.L, m.Npad, k, v, q, u, dlt, dk_part, dv_part))) return rc;
+    if ((rc = intra_dkdv(pb, m.L, m.Npad, k, v, q, u, dlt, dk_part, dv_part, R))) return rc;
   } else {
     NormParams np{};
     np.mode = 1, np.accumulate = 0, np.Q = (const bf16*)q, np.dlt = dlt, np.part = dq_part, np.state = S;
     if ((rc = launch_norm(pb, m, np))) return rc;
+    np.mode = 2, np.Q = (const bf16*)k, np.dlt = nullptr, np.part = dk_part, np.state = R;
+    if ((rc = launch_norm(pb, m, np))) return rc;
   }
   // 4. inter-segment parts
   ApplyParams ap{};
-  ap.mode = APPLY_DQ, ap.state_reverse = 0, ap.b_kmajor = 1, ap.use65 = 0;
-  ap.coef_reg = a, ap.coef64 = 1.f, ap.coef65 = 0.f, ap.out_scale = a, ap.vec_sel = -1;
-  ap.X = (const bf16*)q, ap.Y = u, ap.partial = dq_part, ap.gden = nullptr, ap.out = (bf16*)dq, ap.state = S;
-  if (!pb.causal) {
-    // non-causal: the norm kernel wrote every row of dq_part (accumulate = 0)
-  }
-  if ((rc = launch_apply(pb, m, "mom_apply_dq", ap))) return rc;
+  ap.mode = APPLY_DQ, ap.state_reverse = 0, ap.b_kmajor = 1;
+  ap.coef_reg = a, ap.coef64 = 1.f, ap.out_scale = a, ap.vec_sel = -1;
+  ap.X = (const bf16*)q, ap.partial = dq_part, ap.gden = nullptr, ap.out = (bf16*)dq, ap.state = S;
+  if ((rc = launch_apply(pb, m, "mom_apply_dq", ap, u))) return rc;
 
   ap = ApplyParams{};
-  ap.mode = APPLY_DV, ap.state_reverse = 1, ap.b_kmajor = 0, ap.use65 = 0;
-  ap.coef_reg = 0.5f * a * a, ap.coef64 = a, ap.coef65 = 0.f, ap.out_scale = 1.f, ap.vec_sel = 0;
-  ap.X = (const bf16*)k, ap.Y = (const bf16*)k, ap.partial = pb.causal ? dv_part : nullptr, ap.gden = nullptr;
+  ap.mode = APPLY_DV, ap.state_reverse = 1, ap.b_kmajor = 0;
+  ap.coef_reg = 0.5f * a * a, ap.coef64 = a, ap.out_scale = 1.f, ap.vec_sel = 0;
+  ap.X = (const bf16*)k, ap.partial = pb.causal ? dv_part : nullptr, ap.gden = nullptr;
   ap.out = (bf16*)dv, ap.state = R;
-  if ((rc = launch_apply(pb, m, "mom_apply_dv", ap))) return rc;
+  if ((rc = launch_apply(pb, m, "mom_apply_dv", ap, k))) return rc;
 
   ap = ApplyParams{};
-  ap.mode = APPLY_DK, ap.state_reverse = 1, ap.b_kmajor = 1, ap.use65 = 1;
-  ap.coef_reg = a, ap.coef64 = 1.f, ap.coef65 = a, ap.out_scale = a, ap.vec_sel = 1;
-  ap.X = (const bf16*)k, ap.Y = (const bf16*)v, ap.partial = pb.causal ? dk_part : nullptr, ap.gden = nullptr;
+  // the normaliser column of the reverse state (RN1 + a RN2 k) is already inside dk_part
+  ap.mode = APPLY_DK, ap.state_reverse = 1, ap.b_kmajor = 1;
+  ap.coef_reg = a, ap.coef64 = 1.f, ap.out_scale = a, ap.vec_sel = -1;
+  ap.X = (const bf16*)k, ap.partial = dk_part, ap.gden = nullptr;
   ap.out = (bf16*)dk, ap.state = R;
-  return launch_apply(pb, m, "mom_apply_dk", ap);
+  return launch_apply(pb, m, "mom_apply_dk", ap, v);
 }
 
 // executed tensor-core flops of the plan (for the utilisation report; never the algorithmic count)
@@ -803,7 +798,7 @@ void moments_flops(int B, int H, int N, int p, int causal, double* fwd, double* 
   const double slabs = p == 2 ? 65 : 1;
   const double apply = m.BH * with_state * slabs * 16 * mma;
   *fwd = build_f + apply;
-  *bwd = build_f + build_r + 3 * apply + m.BH * with_state * 16 * mma /*slab 65 of dk*/;
+  *bwd = build_f + build_r + 3 * apply;
 }
 
 }  // namespace fm

@@ -268,3 +268,59 @@ extern "C" int fastmax_selftest_alurate(int kind, int iters, int threads, unsign
   }
   return FASTMAX_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// TMEM load probe (developer tool): cycles per (tcgen05.ld xN + wait) with `inflight` loads per wait
+// ---------------------------------------------------------------------------------------------
+namespace fm {
+namespace {
+using namespace sm100;
+template <int WIDTH, int INFLIGHT>
+__global__ void ldrate_kernel(int iters, unsigned long long* out) {
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    tmem_alloc(&slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = slot + ((uint32_t)(32 * (warp & 3)) << 16);
+  uint32_t acc = 0;
+  long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    uint32_t v[INFLIGHT][WIDTH];
+#pragma unroll
+    for (int j = 0; j < INFLIGHT; ++j) {
+      if (WIDTH == 16) tmem_ld16(tmem + ((it * INFLIGHT + j) * WIDTH) % 256, v[j]);
+      else tmem_ld32(tmem + ((it * INFLIGHT + j) * WIDTH) % 256, v[j]);
+    }
+    tmem_wait_ld();
+#pragma unroll
+    for (int j = 0; j < INFLIGHT; ++j)
+#pragma unroll
+      for (int c = 0; c < WIDTH; ++c) acc += v[j][c];
+  }
+  long long t1 = clock64();
+  if (threadIdx.x == 0) out[0] = (unsigned long long)(t1 - t0);
+  if (acc == 0x12345u) out[1] = acc;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(slot, 512);
+}
+}  // namespace
+}  // namespace fm
+
+extern "C" int fastmax_selftest_ldrate(int width, int inflight, int iters, int threads, unsigned long long* out_dev,
+                                       void* stream) {
+  using namespace fm;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (width == 16 && inflight == 1) { FM_LAUNCH("ldrate", st, ldrate_kernel<16, 1><<<1, threads, 0, st>>>(iters, out_dev)); }
+  else if (width == 16 && inflight == 2) { FM_LAUNCH("ldrate", st, ldrate_kernel<16, 2><<<1, threads, 0, st>>>(iters, out_dev)); }
+  else if (width == 16 && inflight == 4) { FM_LAUNCH("ldrate", st, ldrate_kernel<16, 4><<<1, threads, 0, st>>>(iters, out_dev)); }
+  else if (width == 32 && inflight == 1) { FM_LAUNCH("ldrate", st, ldrate_kernel<32, 1><<<1, threads, 0, st>>>(iters, out_dev)); }
+  else if (width == 32 && inflight == 2) { FM_LAUNCH("ldrate", st, ldrate_kernel<32, 2><<<1, threads, 0, st>>>(iters, out_dev)); }
+  else return FASTMAX_ERR_BAD_ARG;
+  return FASTMAX_OK;
+}

@@ -56,13 +56,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Wait with a watchdog: a protocol bug must trap (kernel error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
   if (mbar_try_wait(bar, parity)) return;
   long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) {  // ~2 s
-      printf("fastmax: mbarrier wait timed out (block %d,%d thread %d bar %u parity %u)\n", blockIdx.x,
-             blockIdx.y, threadIdx.x, smem_u32(bar), parity);
+      printf("fastmax: mbarrier wait timed out (block %d,%d thread %d bar %u parity %u tag %d)\n", blockIdx.x,
+             blockIdx.y, threadIdx.x, smem_u32(bar), parity, tag);
       __trap();
     }
   }

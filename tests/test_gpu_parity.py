@@ -90,7 +90,7 @@ def test_seeded_parity_vs_oracle(shape, p, causal, dtype, algo):
     for nm, x, r in zip(("o", "g", "dq", "dk", "dv"), out, ref):
         # N=1 has dq = dk = 0 exactly (terms of size ~0.1 cancel): floor the denominator so the
         # bf16 cancellation residue (2^-9 of the term size) is judged against the term size
-        err = orc.rel_err(x, r, floor=1e-3 if dtype == torch.float32 else 5e-2)
+        err = orc.rel_err(x, r, floor=1e-3 if dtype == torch.float32 else 1e-1)
         assert err <= TOL[dtype], (shape, p, causal, nm, err)
 
 
