@@ -1,5 +1,7 @@
 """fastmax_experiments_b200 -- B200-native FastMax attention (one hot path)."""
 from .fastmax import fastmax, fastattention_einops, FastmaxFunction  # noqa: F401
+from .attention import fastmax_attention, patch_causal_self_attention  # noqa: F401
 from . import _lib  # noqa: F401
 
-__all__ = ["fastmax", "fastattention_einops", "FastmaxFunction"]
+__all__ = ["fastmax", "fastattention_einops", "FastmaxFunction", "fastmax_attention",
+           "patch_causal_self_attention"]
