@@ -19,6 +19,8 @@ SYMBOLS = [
     "fastmax_plan_make", "fastmax_fwd_workspace_bytes", "fastmax_bwd_workspace_bytes",
     "fastmax_fwd", "fastmax_bwd", "fastmax_last_launch_count",
     "fastmax_profile_enable", "fastmax_profile_fetch",
+    "fastmax_sp_state_bytes", "fastmax_sp_local_state_workspace_bytes", "fastmax_sp_local_state",
+    "fastmax_sp_local_state_rev", "fastmax_sp_reduce", "fastmax_fwd_sp", "fastmax_bwd_sp",
 ]
 
 
@@ -64,6 +66,21 @@ def load() -> C.CDLL:
     lib.fastmax_fwd.argtypes = [vp] * 5 + [i32] * 6 + [f32, i32, i32, vp, sz, vp]
     lib.fastmax_bwd.restype = i32
     lib.fastmax_bwd.argtypes = [vp] * 9 + [i32] * 6 + [f32, i32, i32, vp, sz, vp]
+    ll = C.c_longlong
+    lib.fastmax_sp_state_bytes.restype = sz
+    lib.fastmax_sp_state_bytes.argtypes = [i32, i32]
+    lib.fastmax_sp_local_state_workspace_bytes.restype = sz
+    lib.fastmax_sp_local_state_workspace_bytes.argtypes = [i32] * 4
+    lib.fastmax_sp_local_state.restype = i32
+    lib.fastmax_sp_local_state.argtypes = [vp] * 3 + [i32] * 5 + [vp, sz, vp]
+    lib.fastmax_sp_local_state_rev.restype = i32
+    lib.fastmax_sp_local_state_rev.argtypes = [vp] * 5 + [i32] * 5 + [vp, sz, vp]
+    lib.fastmax_sp_reduce.restype = i32
+    lib.fastmax_sp_reduce.argtypes = [vp, i32, i32, i32, vp, i32, i32, vp]
+    lib.fastmax_fwd_sp.restype = i32
+    lib.fastmax_fwd_sp.argtypes = [vp] * 6 + [ll] + [i32] * 5 + [f32, i32, vp, sz, vp]
+    lib.fastmax_bwd_sp.restype = i32
+    lib.fastmax_bwd_sp.argtypes = [vp] * 11 + [ll] + [i32] * 5 + [f32, i32, vp, sz, vp]
     lib.fastmax_profile_enable.restype = None
     lib.fastmax_profile_enable.argtypes = [i32]
     lib.fastmax_profile_fetch.restype = i32

@@ -170,4 +170,80 @@ int fastmax_bwd(const void* q, const void* k, const void* v, const void* o, cons
   return fm::exact_bwd(pb, q, k, v, o, g, d_o, dq, dk, dv);
 }
 
+// ---- sequence parallelism ------------------------------------------------------------------
+static int check_sp(int B, int H, int N, int D, int p, int dtype) {
+  int rc = check_common(B, H, N, D, p, dtype);
+  if (rc) return rc;
+  if (dtype != FASTMAX_DTYPE_BF16 || D != 64) return FASTMAX_ERR_UNSUPPORTED;
+  return FASTMAX_OK;
+}
+
+size_t fastmax_sp_state_bytes(int B, int H) { return fm::moments_state_bytes(B, H); }
+
+size_t fastmax_sp_local_state_workspace_bytes(int B, int H, int N, int reverse) {
+  return reverse ? fm::moments_local_state_rev_workspace_bytes(B, H, N) : fm::moments_local_state_workspace_bytes(B, H, N);
+}
+
+int fastmax_sp_local_state(const void* k, const void* v, void* state_out, int B, int H, int N, int D, int p,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+  fm::status().launches = 0;
+  if (!k || !v || !state_out || !workspace) return FASTMAX_ERR_BAD_ARG;
+  int rc = check_sp(B, H, N, D, p, FASTMAX_DTYPE_BF16);
+  if (rc) return rc;
+  if (workspace_bytes < fm::moments_local_state_workspace_bytes(B, H, N)) return FASTMAX_ERR_WORKSPACE;
+  Problem pb{B, H, N, D, p, 0, FASTMAX_DTYPE_BF16, 0.f, (cudaStream_t)stream};
+  return fm::moments_local_state(pb, k, v, k, state_out, workspace);
+}
+
+int fastmax_sp_local_state_rev(const void* q, const void* o, const float* g, const void* d_o, void* state_out,
+                               int B, int H, int N, int D, int p, void* workspace, size_t workspace_bytes,
+                               void* stream) {
+  fm::status().launches = 0;
+  if (!q || !o || !g || !d_o || !state_out || !workspace) return FASTMAX_ERR_BAD_ARG;
+  int rc = check_sp(B, H, N, D, p, FASTMAX_DTYPE_BF16);
+  if (rc) return rc;
+  if (workspace_bytes < fm::moments_local_state_rev_workspace_bytes(B, H, N)) return FASTMAX_ERR_WORKSPACE;
+  Problem pb{B, H, N, D, p, 0, FASTMAX_DTYPE_BF16, 0.f, (cudaStream_t)stream};
+  return fm::moments_local_state_rev(pb, q, o, g, d_o, state_out, workspace);
+}
+
+int fastmax_sp_reduce(const void* gathered, int n_ranks, int rank, int dir, void* state_out, int B, int H,
+                      void* stream) {
+  fm::status().launches = 0;
+  if (!gathered || !state_out || n_ranks <= 0 || rank < 0 || rank >= n_ranks || B <= 0 || H <= 0 || (dir != 0 && dir != 1))
+    return FASTMAX_ERR_BAD_ARG;
+  return fm::moments_reduce_states(gathered, n_ranks, rank, dir, state_out, B, H, (cudaStream_t)stream);
+}
+
+int fastmax_fwd_sp(const void* q, const void* k, const void* v, void* o, float* g, const void* init_state,
+                   long long token_offset, int B, int H, int N, int D, int p, float inv_c, int dtype,
+                   void* workspace, size_t workspace_bytes, void* stream) {
+  fm::status().launches = 0;
+  fm::status().cuda_err[0] = 0;
+  if (!q || !k || !v || !o || !g || token_offset < 0) return FASTMAX_ERR_BAD_ARG;
+  int rc = check_sp(B, H, N, D, p, dtype);
+  if (rc) return rc;
+  const size_t need = fm::moments_workspace_bytes(B, H, N, 1, false);
+  if (need > workspace_bytes || !workspace || ((uintptr_t)workspace & 255)) return FASTMAX_ERR_WORKSPACE;
+  Problem pb{B, H, N, D, p, 1, dtype, inv_c, (cudaStream_t)stream};
+  pb.sp_init_fwd = init_state, pb.sp_offset = token_offset;
+  return fm::moments_fwd(pb, q, k, v, o, g, workspace);
+}
+
+int fastmax_bwd_sp(const void* q, const void* k, const void* v, const void* o, const float* g, const void* d_o,
+                   void* dq, void* dk, void* dv, const void* init_state_fwd, const void* init_state_rev,
+                   long long token_offset, int B, int H, int N, int D, int p, float inv_c, int dtype,
+                   void* workspace, size_t workspace_bytes, void* stream) {
+  fm::status().launches = 0;
+  fm::status().cuda_err[0] = 0;
+  if (!q || !k || !v || !o || !g || !d_o || !dq || !dk || !dv || token_offset < 0) return FASTMAX_ERR_BAD_ARG;
+  int rc = check_sp(B, H, N, D, p, dtype);
+  if (rc) return rc;
+  const size_t need = fm::moments_workspace_bytes(B, H, N, 1, true);
+  if (need > workspace_bytes || !workspace || ((uintptr_t)workspace & 255)) return FASTMAX_ERR_WORKSPACE;
+  Problem pb{B, H, N, D, p, 1, dtype, inv_c, (cudaStream_t)stream};
+  pb.sp_init_fwd = init_state_fwd, pb.sp_init_rev = init_state_rev, pb.sp_offset = token_offset;
+  return fm::moments_bwd(pb, q, k, v, o, g, d_o, dq, dk, dv, workspace);
+}
+
 }  // extern "C"

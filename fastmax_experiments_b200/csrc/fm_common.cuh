@@ -48,6 +48,12 @@ struct Problem {
   int B, H, N, D, p, causal, dtype;
   float inv_c;
   cudaStream_t stream;
+  // sequence parallelism (fastmax_*_sp): this rank holds tokens [sp_offset, sp_offset + N) of a longer
+  // sequence; sp_init_fwd = moment state of all earlier tokens, sp_init_rev = reverse state of all later
+  // tokens (one record per (b,h); null = none)
+  const void* sp_init_fwd = nullptr;
+  const void* sp_init_rev = nullptr;
+  long long sp_offset = 0;
 };
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -84,6 +90,13 @@ int intra_dq(const Problem& pb, int L, int Npad, const void* q, const void* u, c
 int intra_dkdv(const Problem& pb, int L, int Npad, const void* k, const void* v, const void* q, const void* u,
                const float* dlt, float* dk_part, float* dv_part, const uint8_t* rstate);
 int moments_seg_len(int N);
+size_t moments_state_bytes(int B, int H);
+size_t moments_local_state_workspace_bytes(int B, int H, int N);
+int moments_local_state(const Problem& pb, const void* x, const void* w, const void* w2, void* state_out, void* ws);
+int moments_local_state_rev(const Problem& pb, const void* q, const void* o, const float* g, const void* d_o,
+                            void* state_out, void* ws);
+size_t moments_local_state_rev_workspace_bytes(int B, int H, int N);
+int moments_reduce_states(const void* gathered, int G, int rank, int dir, void* out, int B, int H, cudaStream_t stream);
 size_t moments_workspace_bytes(int B, int H, int N, int causal, bool bwd);
 void moments_flops(int B, int H, int N, int p, int causal, double* fwd, double* bwd);
 int moments_fwd(const Problem& pb, const void* q, const void* k, const void* v, void* o, float* g, void* ws);

@@ -40,6 +40,8 @@ struct IntraParams {
   const uint8_t* state;    // boundary states whose normaliser column is folded in here (FWD, DQ: forward-
                            // direction states; DKDV: reverse-direction states), nullable
   int nseg;
+  int edge_state;          // sequence parallel: the first (FWD, DQ) / last (DKDV) local segment has a state too
+  float count_offset;      // tokens of earlier ranks (normaliser count term)
 };
 
 template <int MODE> struct IntraCfg {
@@ -86,7 +88,8 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
   // moment part of the normaliser column (FWD: g, DQ: the -dlt (N1 + a N2 q) term): only segments
   // that have a boundary state
   const int seg = c0 / P.L;
-  const bool has_norm = P.state != nullptr && (MODE == INTRA_DKDV ? seg < P.nseg - 1 : seg > 0);
+  const bool has_norm =
+      P.state != nullptr && (MODE == INTRA_DKDV ? (seg < P.nseg - 1 || P.edge_state) : (seg > 0 || P.edge_state));
   const int rec_idx = bh * P.nseg + seg;
 
   if (warp == 0) {
@@ -385,7 +388,7 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
           }
         }
       }
-      if (MODE == INTRA_FWD && r_abs < P.N) P.g[grow] = gsum[x] + (has_norm ? (float)(seg * P.L) + gmom : 0.f);
+      if (MODE == INTRA_FWD && r_abs < P.N) P.g[grow] = gsum[x] + (has_norm ? (float)(seg * P.L) + P.count_offset + gmom : 0.f);
     }
   }
   tc_fence_before();
@@ -413,7 +416,9 @@ static int launch_intra_t(const Problem& pb, int L, int Npad, const void* r1, co
   IntraParams P{};
   P.N = pb.N, P.Npad = Npad, P.L = L, P.p = pb.p, P.a = pb.inv_c, P.dlt = dlt, P.out0 = out0, P.out1 = out1, P.g = g;
   P.nseg = (pb.N + L - 1) / L;
-  P.state = P.nseg > 1 ? state : nullptr;
+  P.edge_state = MODE == INTRA_DKDV ? pb.sp_init_rev != nullptr : pb.sp_init_fwd != nullptr;
+  P.count_offset = (float)pb.sp_offset;
+  P.state = (P.nseg > 1 || P.edge_state) ? state : nullptr;
   CUtensorMap tmS = m[0];
   if (P.state) {
     int rc = make_tmap_bf16_3d(&tmS, state, 64, NSLAB * 64, (uint64_t)BH * P.nseg, 128, REC_BYTES, 64, 64);

@@ -61,6 +61,7 @@ struct BuildParams {
   int N, nblk, nproc, Lb, nseg, reverse, causal, p;
   int special_cx;   // blockIdx.x of the CTA that owns the special tile (S1 | normaliser): 8 for p=2, 0 for p=1
   uint8_t* state;   // records: causal -> [bh][nseg], else [bh]
+  const uint8_t* init;   // sequence parallel: record per (b,h) the scan starts from (nullable)
 };
 
 // CTA layout of the build kernel (p = 2): 8 "regular" CTAs per (b,h), each owning 4 tiles
@@ -144,6 +145,49 @@ build_kernel(const __grid_constant__ CUtensorMap tmXT, const __grid_constant__ C
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
+  // sequence parallel: start the scan from the state of the earlier (later, for the reverse scan)
+  // ranks, so every snapshot already contains it
+  const bool has_init = P.init != nullptr;
+  if (has_init) {
+    if (warp < 16 && (warp >> 2) < ntile) {
+      const int g = warp >> 2, q = warp & 3;
+      const int row = 32 * q + lane, xsel = row >> 6, y = row & 63;
+      const uint8_t* rec = P.init + (size_t)bh * REC_BYTES;
+      const int nacc = special ? 2 : 1;
+      for (int a2 = 0; a2 < nacc; ++a2) {
+        const int slab = special ? 64 + a2 : 8 * cx + 2 * g + xsel;
+        const float* vec = reinterpret_cast<const float*>(rec + VEC_OFF);
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          uint32_t v[32];
+          if (!special || row < 64) {
+            if (special && a2 == 1) {          // fp32 copy of the normaliser matrix
+#pragma unroll
+              for (int c = 0; c < 32; ++c) v[c] = __float_as_uint(vec[128 + y * 64 + 32 * h + c]);
+            } else {
+              const uint4* src = reinterpret_cast<const uint4*>(rec + (size_t)slab * SLAB_BYTES + (size_t)y * 128 + 64 * h);
+#pragma unroll
+              for (int c8 = 0; c8 < 4; ++c8) {
+                const uint4 w4 = src[c8];
+                const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[8 * c8 + 2 * j] = w[j] << 16, v[8 * c8 + 2 * j + 1] = w[j] & 0xffff0000u;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) v[c] = row == 64 ? __float_as_uint(vec[a2 * 64 + 32 * h + c]) : 0u;
+          }
+          tmem_st32(tmem + ((uint32_t)(32 * q) << 16) + 64 * (g + a2) + 32 * h, v);
+        }
+      }
+      tmem_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
+
   if (warp < 16) {
     // ------------------------------------------------------------------ generator groups
     const int g = warp >> 2, q = warp & 3;
@@ -214,10 +258,11 @@ build_kernel(const __grid_constant__ CUtensorMap tmXT, const __grid_constant__ C
         mbar_wait(&a_ready[g * 2 + buf], (it >> 1) & 1);
         tc_fence_after();
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) umma_ts(acc, a_t + kk * 8, dW + kk * 128, idesc, (it | kk) != 0);
+        for (int kk = 0; kk < 4; ++kk) umma_ts(acc, a_t + kk * 8, dW + kk * 128, idesc, has_init || (it | kk) != 0);
         if (special) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) umma_ts(tmem + 64, a_t + kk * 8, dW + 512 + kk * 128, idesc, (it | kk) != 0);
+          for (int kk = 0; kk < 4; ++kk)
+            umma_ts(tmem + 64, a_t + kk * 8, dW + 512 + kk * 128, idesc, has_init || (it | kk) != 0);
         }
         umma_commit(&done[s]);
         if (bnd) {
@@ -327,6 +372,7 @@ struct ApplyParams {
   int b_kmajor;             // 1: contraction over the slab's contiguous index (dq, dk)
   float coef_reg, coef64, out_scale;
   int vec_sel;              // -1 none, 0: vec[0:64), 1: vec[64:128)
+  int edge_state;           // sequence parallel: first (forward states) / last (reverse) local segment has a state
   const bf16* X;            // per-token scalars
   const float* partial;     // (BH, N, 64) fp32 intra-segment partial (nullable)
   const float* gden;        // (BH, N) fp32: divide rows by it (forward) (nullable)
@@ -364,7 +410,8 @@ apply_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CU
   const int bh = blockIdx.y;
   const int t0 = blockIdx.x * A_TOK;
   const int seg = t0 / P.L;
-  const bool has_state = !P.causal || (P.state_reverse ? seg < P.nseg - 1 : seg > 0);
+  const bool has_state =
+      !P.causal || (P.state_reverse ? (seg < P.nseg - 1 || P.edge_state) : (seg > 0 || P.edge_state));
   const int rec_idx = P.causal ? bh * P.nseg + seg : bh;
   const int ngroups = (P.p == 2 ? 32 : 0) + 1;     // 32 pairs of second-order slabs + slab 64
 
@@ -654,7 +701,7 @@ static int launch_transpose(const Problem& pb, const void* in, void* out, int Np
 }
 
 static int launch_build(const Problem& pb, const MomLayout& m, const void* xt, const void* w, const void* w2,
-                        uint8_t* state, int reverse) {
+                        uint8_t* state, int reverse, const void* init = nullptr) {
   CUtensorMap tmXT, tmW, tmW2;
   int rc;
   if ((rc = make_tmap_bf16_3d(&tmXT, xt, 64, m.Npad, m.BH, 128, (uint64_t)m.Npad * 128, 64, 64))) return rc;
@@ -662,8 +709,14 @@ static int launch_build(const Problem& pb, const MomLayout& m, const void* xt, c
   if ((rc = make_tmap_bf16_3d(&tmW2, w2, 64, m.N, m.BH, 128, (uint64_t)m.N * 128, 64, 64))) return rc;
   BuildParams P{};
   P.N = m.N, P.nblk = (m.N + 63) / 64, P.Lb = m.L / 64, P.nseg = m.nseg, P.reverse = reverse, P.causal = pb.causal;
-  P.p = pb.p, P.state = state;
+  P.p = pb.p, P.state = state, P.init = (const uint8_t*)init;
   P.special_cx = pb.p == 2 ? B_CTAS_P2 - 1 : 0;
+  if (init && pb.causal) {
+    // the boundary state of the first (reverse scan: last) local segment is the incoming state itself
+    uint8_t* dst = state + (size_t)(reverse ? m.nseg - 1 : 0) * REC_BYTES;
+    FM_CUDA(cudaMemcpy2DAsync(dst, (size_t)m.nseg * REC_BYTES, init, REC_BYTES, REC_BYTES, m.BH,
+                              cudaMemcpyDeviceToDevice, pb.stream));
+  }
   if (!pb.causal) P.nproc = P.nblk;
   else if (reverse) P.nproc = P.nblk - P.Lb;
   else P.nproc = (m.nseg - 1) * P.Lb;
@@ -704,7 +757,7 @@ int moments_fwd(const Problem& pb, const void* q, const void* k, const void* v, 
   float* part = (float*)(w8 + m.off_part);
   // 1. K^T and the boundary states (forward direction)
   if ((rc = launch_transpose(pb, k, w8 + m.off_xt, m.Npad))) return rc;
-  if ((rc = launch_build(pb, m, w8 + m.off_xt, v, k, state, 0))) return rc;
+  if ((rc = launch_build(pb, m, w8 + m.off_xt, v, k, state, 0, pb.sp_init_fwd))) return rc;
   // 2. intra-segment part (causal only) and the normaliser
   if (pb.causal) {
     // intra-segment scores + the normaliser (its moment part rides along as one more score MMA)
@@ -716,7 +769,7 @@ int moments_fwd(const Problem& pb, const void* q, const void* k, const void* v, 
   }
   // 3. inter-segment part + normalisation
   ApplyParams ap{};
-  ap.mode = APPLY_FWD, ap.state_reverse = 0, ap.b_kmajor = 0;
+  ap.mode = APPLY_FWD, ap.state_reverse = 0, ap.b_kmajor = 0, ap.edge_state = pb.sp_init_fwd != nullptr;
   ap.coef_reg = 0.5f * a * a, ap.coef64 = a, ap.out_scale = 1.f, ap.vec_sel = 0;
   ap.X = (const bf16*)q, ap.partial = pb.causal ? part : nullptr, ap.gden = g;
   ap.out = (bf16*)o, ap.state = state;
@@ -745,9 +798,9 @@ int moments_bwd(const Problem& pb, const void* q, const void* k, const void* v, 
                 (const bf16*)q, (const bf16*)o, (const bf16*)d_o, g, u, dlt, qd, rows, m.N, m.Npad));
   // 2. forward-direction states of (k, v) (recomputed, not saved) and reverse-direction states of (q, u)
   if ((rc = launch_transpose(pb, k, w8 + m.off_xt, m.Npad))) return rc;
-  if ((rc = launch_build(pb, m, w8 + m.off_xt, v, k, S, 0))) return rc;
+  if ((rc = launch_build(pb, m, w8 + m.off_xt, v, k, S, 0, pb.sp_init_fwd))) return rc;
   if ((rc = launch_transpose(pb, q, w8 + m.off_xt2, m.Npad))) return rc;
-  if ((rc = launch_build(pb, m, w8 + m.off_xt2, u, qd, R, 1))) return rc;
+  if ((rc = launch_build(pb, m, w8 + m.off_xt2, u, qd, R, 1, pb.sp_init_rev))) return rc;
   // 3. intra-segment partials
   if (pb.causal) {
     if ((rc = intra_dq(pb, m.L, m.Npad, q, u, k, v, dlt, dq_part, S))) return rc;
@@ -761,13 +814,13 @@ int moments_bwd(const Problem& pb, const void* q, const void* k, const void* v, 
   }
   // 4. inter-segment parts
   ApplyParams ap{};
-  ap.mode = APPLY_DQ, ap.state_reverse = 0, ap.b_kmajor = 1;
+  ap.mode = APPLY_DQ, ap.state_reverse = 0, ap.b_kmajor = 1, ap.edge_state = pb.sp_init_fwd != nullptr;
   ap.coef_reg = a, ap.coef64 = 1.f, ap.out_scale = a, ap.vec_sel = -1;
   ap.X = (const bf16*)q, ap.partial = dq_part, ap.gden = nullptr, ap.out = (bf16*)dq, ap.state = S;
   if ((rc = launch_apply(pb, m, "mom_apply_dq", ap, u))) return rc;
 
   ap = ApplyParams{};
-  ap.mode = APPLY_DV, ap.state_reverse = 1, ap.b_kmajor = 0;
+  ap.mode = APPLY_DV, ap.state_reverse = 1, ap.b_kmajor = 0, ap.edge_state = pb.sp_init_rev != nullptr;
   ap.coef_reg = 0.5f * a * a, ap.coef64 = a, ap.out_scale = 1.f, ap.vec_sel = 0;
   ap.X = (const bf16*)k, ap.partial = pb.causal ? dv_part : nullptr, ap.gden = nullptr;
   ap.out = (bf16*)dv, ap.state = R;
@@ -775,11 +828,86 @@ int moments_bwd(const Problem& pb, const void* q, const void* k, const void* v, 
 
   ap = ApplyParams{};
   // the normaliser column of the reverse state (RN1 + a RN2 k) is already inside dk_part
-  ap.mode = APPLY_DK, ap.state_reverse = 1, ap.b_kmajor = 1;
+  ap.mode = APPLY_DK, ap.state_reverse = 1, ap.b_kmajor = 1, ap.edge_state = pb.sp_init_rev != nullptr;
   ap.coef_reg = a, ap.coef64 = 1.f, ap.out_scale = a, ap.vec_sel = -1;
   ap.X = (const bf16*)k, ap.partial = dk_part, ap.gden = nullptr;
   ap.out = (bf16*)dk, ap.state = R;
   return launch_apply(pb, m, "mom_apply_dk", ap, v);
+}
+
+// =============================================================================================
+// sequence parallelism: per-rank total states and their exclusive prefix / suffix over the ranks
+// =============================================================================================
+size_t moments_state_bytes(int B, int H) { return (size_t)B * H * REC_BYTES; }
+
+size_t moments_local_state_workspace_bytes(int B, int H, int N) {
+  return align_up((size_t)B * H * 64 * align_up(N, 64) * 2, 1024);
+}
+
+// total forward-direction state of the local tokens: x = k, w = v, w2 = k  (one record per (b,h))
+int moments_local_state(const Problem& pb_in, const void* x, const void* w, const void* w2, void* state_out, void* ws) {
+  Problem pb = pb_in;
+  pb.causal = 0;
+  const MomLayout m = mom_layout(pb.B, pb.H, pb.N, moments_seg_len(pb.N), 0, false);
+  int rc;
+  if ((rc = launch_transpose(pb, x, ws, m.Npad))) return rc;
+  return launch_build(pb, m, ws, w, w2, (uint8_t*)state_out, 0);
+}
+
+size_t moments_local_state_rev_workspace_bytes(int B, int H, int N) {
+  const size_t tens = (size_t)B * H * N * 64, npad = align_up(N, 64);
+  return align_up((size_t)B * H * 64 * npad * 2, 1024) + 2 * align_up(tens * 2, 1024) + align_up((size_t)B * H * npad * 4, 1024);
+}
+
+// total reverse-direction state of the local tokens: x = q, w = do/g, w2 = -dlt*q
+int moments_local_state_rev(const Problem& pb_in, const void* q, const void* o, const float* g, const void* d_o,
+                            void* state_out, void* ws) {
+  Problem pb = pb_in;
+  pb.causal = 0;
+  const MomLayout m = mom_layout(pb.B, pb.H, pb.N, moments_seg_len(pb.N), 0, false);
+  uint8_t* w8 = (uint8_t*)ws;
+  const size_t tens = (size_t)m.BH * m.N * 64;
+  size_t off = align_up((size_t)m.BH * 64 * m.Npad * 2, 1024);
+  bf16* u = (bf16*)(w8 + off);
+  off += align_up(tens * 2, 1024);
+  bf16* qd = (bf16*)(w8 + off);
+  off += align_up(tens * 2, 1024);
+  float* dlt = (float*)(w8 + off);
+  const size_t rows = (size_t)m.BH * m.N;
+  FM_CUDA(cudaMemsetAsync(dlt, 0, (size_t)m.BH * m.Npad * 4, pb.stream));
+  FM_LAUNCH("mom_prep_bwd", pb.stream,
+            prep_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, pb.stream>>>(
+                (const bf16*)q, (const bf16*)o, (const bf16*)d_o, g, u, dlt, qd, rows, m.N, m.Npad));
+  int rc;
+  if ((rc = launch_transpose(pb, q, w8, m.Npad))) return rc;
+  return launch_build(pb, m, w8, u, qd, (uint8_t*)state_out, 1);
+}
+
+// out[bh] = sum over ranks r' < rank (dir 0) or r' > rank (dir 1) of gathered[r'][bh]; bf16 slabs are
+// summed in fp32.  HBM-bound, G records in, one out.
+__global__ void __launch_bounds__(256) reduce_states_kernel(const uint8_t* __restrict__ gathered, int G, int rank,
+                                                            int dir, uint8_t* __restrict__ out, size_t bh_count) {
+  const size_t words_per_rec = REC_BYTES / 4;
+  const size_t total = bh_count * words_per_rec;
+  const int r0 = dir == 0 ? 0 : rank + 1, r1 = dir == 0 ? rank : G;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const size_t bh = idx / words_per_rec, w = idx % words_per_rec;
+    const bool is_vec = w * 4 >= VEC_OFF;
+    float a0 = 0.f, a1 = 0.f;
+    for (int r = r0; r < r1; ++r) {
+      const uint32_t x = reinterpret_cast<const uint32_t*>(gathered + ((size_t)r * bh_count + bh) * REC_BYTES)[w];
+      if (is_vec) a0 += __uint_as_float(x);
+      else a0 += __uint_as_float(x << 16), a1 += __uint_as_float(x & 0xffff0000u);
+    }
+    reinterpret_cast<uint32_t*>(out + bh * REC_BYTES)[w] = is_vec ? __float_as_uint(a0) : sm100::pack_bf16x2(a0, a1);
+  }
+}
+
+int moments_reduce_states(const void* gathered, int G, int rank, int dir, void* out, int B, int H, cudaStream_t stream) {
+  const size_t bh = (size_t)B * H;
+  FM_LAUNCH("mom_reduce_states", stream,
+            reduce_states_kernel<<<148 * 4, 256, 0, stream>>>((const uint8_t*)gathered, G, rank, dir, (uint8_t*)out, bh));
+  return FASTMAX_OK;
 }
 
 // executed tensor-core flops of the plan (for the utilisation report; never the algorithmic count)

@@ -99,6 +99,33 @@ int fastmax_bwd(const void* q, const void* k, const void* v, const void* o, cons
  * (bench.py reports it as gpu_launches) */
 int fastmax_last_launch_count(void);
 
+/* ---- sequence parallelism (no reference counterpart; BASELINE.json north_star) ----------
+ * A long sequence is split by contiguous token ranges over the GPUs of one box.  Outputs are linear
+ * in the moment state of the preceding tokens, so one exchange per scan direction suffices:
+ *   1. fastmax_sp_local_state{,_rev}: each rank reduces the moment state of its own tokens
+ *      (fastmax_sp_state_bytes bytes, one 545 KiB record per (b,h));
+ *   2. the caller all-gathers the records (NCCL) into [G][B*H] order;
+ *   3. fastmax_sp_reduce: exclusive prefix (dir 0) or exclusive suffix (dir 1) over the ranks;
+ *   4. fastmax_fwd_sp / fastmax_bwd_sp: the local chunked scan started from that state.
+ * Supported: bf16, D = 64, causal (FASTMAX_ALGO_MOMENTS).  N is the LOCAL token count,
+ * token_offset the number of tokens held by earlier ranks.  init_* may be NULL (rank 0 / last rank). */
+size_t fastmax_sp_state_bytes(int B, int H);
+size_t fastmax_sp_local_state_workspace_bytes(int B, int H, int N, int reverse);
+int fastmax_sp_local_state(const void* k, const void* v, void* state_out, int B, int H, int N, int D, int p,
+                           void* workspace, size_t workspace_bytes, void* stream);
+int fastmax_sp_local_state_rev(const void* q, const void* o, const float* g, const void* d_o, void* state_out,
+                               int B, int H, int N, int D, int p, void* workspace, size_t workspace_bytes,
+                               void* stream);
+int fastmax_sp_reduce(const void* gathered, int n_ranks, int rank, int dir, void* state_out, int B, int H,
+                      void* stream);
+int fastmax_fwd_sp(const void* q, const void* k, const void* v, void* o, float* g, const void* init_state,
+                   long long token_offset, int B, int H, int N, int D, int p, float inv_c, int dtype,
+                   void* workspace, size_t workspace_bytes, void* stream);
+int fastmax_bwd_sp(const void* q, const void* k, const void* v, const void* o, const float* g, const void* d_o,
+                   void* dq, void* dk, void* dv, const void* init_state_fwd, const void* init_state_rev,
+                   long long token_offset, int B, int H, int N, int D, int p, float inv_c, int dtype,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
 /* Optional per-launch timing for measurement harnesses (no reference counterpart).
  * While enabled, every kernel launch of the calling thread is bracketed by CUDA events on the
  * launching stream.  fastmax_profile_fetch waits for them and writes up to `cap` durations (ms)
