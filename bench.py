@@ -138,6 +138,85 @@ def run_reference(args, rank: int) -> None:
 
 
 # ----------------------------------------------------------------------------------------------
+def run_sequence_parallel(args, rank: int, world: int, local: int) -> None:
+    """BASELINE.json config 5: p=2 causal fwd+bwd of ONE long sequence set (B=1, H=32, D=64, N=--seq)
+    split by token ranges over the ranks; one state all-gather per scan direction over NCCL."""
+    import torch.distributed as dist
+    from fastmax_experiments_b200 import _lib
+    from fastmax_experiments_b200.sequence_parallel import fastmax_sp, partition
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29511")
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    lib = _lib.load()
+    B, H, D, p = 1, HL["H"], HL["D"], HL["p"]
+    N = args.seq if args.seq != HL["N"] else 131072
+    a0, a1 = partition(N, world, rank)
+    gen = torch.Generator(device=dev).manual_seed(4321 + rank)
+    q, k, v = (torch.randn(B, H, a1 - a0, D, device=dev, generator=gen).to(torch.bfloat16).requires_grad_(True)
+               for _ in range(3))
+    do = torch.randn(B, H, a1 - a0, D, device=dev, generator=gen).to(torch.bfloat16)
+
+    def step():
+        for t in (q, k, v):
+            t.grad = None
+        o = fastmax_sp(q, k, v, p=p)
+        o.backward(do)
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    clocks = sampler.finish()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    _lib.profile_enable(True)
+    step()
+    torch.cuda.synchronize()
+    recs = _lib.profile_fetch()
+    _lib.profile_enable(False)
+    kern = {}
+    for name, ms in recs:
+        a = kern.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += ms
+    f_fwd, f_bwd = flops_alg(D, p)
+    peaks = load_peaks()
+    ach = B * H * N * (f_fwd + f_bwd) / (ms_step * 1e-3) / 1e12
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": B * N / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"sequence-parallel fastmax p=2 causal fwd+bwd B={B} H={H} N={N} D={D} bf16, "
+                                   f"tokens split over {world} rank(s), state all-gather over NCCL",
+                       "B": B, "H": H, "N": N, "D": D, "p": p, "causal": True, "local_tokens": a1 - a0,
+                       "l2": "inputs larger than L2"},
+            "clocks": clocks, "gpu_launches": len(recs) * args.steps,
+            "roofline": {"bound": "tensor", "achieved": round(ach, 3), "peak": peaks["tflops"] * world,
+                         "unit": "TFLOP/s", "frac": round(ach / (peaks["tflops"] * world), 5), "traffic": None,
+                         "scope": "whole fwd+bwd step over all ranks (algorithmic flops; the per-rank state "
+                                  "reduce passes are redundant work and not counted)"},
+            "kernels": {n: {"launches": a[0], "ms": round(a[1], 4)} for n, a in sorted(kern.items(), key=lambda kv: -kv[1][1])},
+        }))
+    dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -147,6 +226,9 @@ def main() -> None:
     ap.add_argument("--algo", default="auto", choices=["auto", "exact", "moments"])
     ap.add_argument("--seq", type=int, default=HL["N"], help="override N (diagnostics only)")
     ap.add_argument("--batch", type=int, default=HL["B"], help="override B (diagnostics only)")
+    ap.add_argument("--workload", default="headline", choices=["headline", "sp"],
+                    help="headline: (b,h)-sharded op at B=8,H=32,N=16k (default); sp: sequence-parallel "
+                         "long-context scan, B=1,H=32, --seq tokens split over the ranks (BASELINE config 5)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -159,6 +241,9 @@ def main() -> None:
 
     if args.impl == "reference":
         run_reference(args, rank)
+        return
+    if args.workload == "sp":
+        run_sequence_parallel(args, rank, world, local)
         return
 
     import torch.distributed as dist
