@@ -62,6 +62,8 @@ struct BuildParams {
   int special_cx;   // blockIdx.x of the CTA that owns the special tile (S1 | normaliser): 8 for p=2, 0 for p=1
   uint8_t* state;   // records: causal -> [bh][nseg], else [bh]
   const uint8_t* init;   // sequence parallel: record per (b,h) the scan starts from (nullable)
+  unsigned long long dW[4][4];    // B-operand descriptors [ring stage][k-step] of the W tile (host-built)
+  unsigned long long dW2[4][4];   // ... and of the W2 tile (special CTA)
 };
 
 // CTA layout of the build kernel (p = 2): 8 "regular" CTAs per (b,h), each owning 4 tiles
@@ -69,13 +71,10 @@ struct BuildParams {
 // accumulators of the special tile.  Tensor memory: accumulators in columns [0,256), A operand
 // buffers (4 tiles x 2 stages x 32 columns) in [256,512).
 //
-// Roles (25 warps): generator group g = warps 4g..4g+3 owns tile g for the whole kernel and turns
-// each 64-token block into the tile's bf16 Khatri-Rao rows in tensor memory; issuer warp 16+g issues
-// that tile's four MMAs per block (measured with tools/mmarate.py: one thread sustains only one
-// tcgen05.mma per ~110 cycles while a 128x64x16 MMA occupies the tensor pipe for ~32, so four
-// threads issue concurrently; each issues every MMA of "its" accumulator, so its tcgen05.commit
-// covers that accumulator exactly); warp 20 is the TMA producer; warps 21..24 write the bf16
-// snapshots at segment boundaries.
+// Roles (25 warps): generator group k = warps 4k..4k+3 produces MMA k-step k (16 of the 64 tokens of a
+// block) of all four tiles; issuer warp 16+k issues that k-step's four MMAs (converged warp, operands
+// from the constant bank / immediates, see fm_sm100.cuh), so every issuer waits on one barrier per
+// block; warp 20 is the TMA producer; warps 21..24 write the bf16 snapshots at segment boundaries.
 constexpr int B_STAGES = 4;
 constexpr int B_STAGE_BYTES = 3 * 8192;
 constexpr int B_SMEM = B_STAGES * B_STAGE_BYTES + 1024 /*barriers*/ + 1024 /*align slack*/;
@@ -132,9 +131,9 @@ build_kernel(const __grid_constant__ CUtensorMap tmXT, const __grid_constant__ C
     tmem_relinquish();
   }
   if (tid == 0) {
-    for (int i = 0; i < B_STAGES; ++i) mbar_init(&full[i], 1), mbar_init(&done[i], ntile);
+    for (int i = 0; i < B_STAGES; ++i) mbar_init(&full[i], 1), mbar_init(&done[i], 4);
     for (int i = 0; i < 8; ++i) mbar_init(&a_ready[i], 4);
-    for (int i = 0; i < 4; ++i) mbar_init(&acc_full[i], 1), mbar_init(&acc_free[i], 128);
+    for (int i = 0; i < 4; ++i) mbar_init(&acc_full[i], 4), mbar_init(&acc_free[i], 128);
     fence_barrier_init();
     tma_prefetch_desc(&tmXT);
     tma_prefetch_desc(&tmW);
@@ -145,21 +144,25 @@ build_kernel(const __grid_constant__ CUtensorMap tmXT, const __grid_constant__ C
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  // sequence parallel: start the scan from the state of the earlier (later, for the reverse scan)
-  // ranks, so every snapshot already contains it
+  assert_bases(tmem, smem);
+  // Accumulators start from the incoming state of the sequence-parallel exchange (the state of the
+  // earlier -- reverse scan: later -- ranks, so every snapshot already contains it) or from zero;
+  // every MMA then accumulates.
   const bool has_init = P.init != nullptr;
-  if (has_init) {
-    if (warp < 16 && (warp >> 2) < ntile) {
-      const int g = warp >> 2, q = warp & 3;
-      const int row = 32 * q + lane, xsel = row >> 6, y = row & 63;
-      const uint8_t* rec = P.init + (size_t)bh * REC_BYTES;
-      const int nacc = special ? 2 : 1;
-      for (int a2 = 0; a2 < nacc; ++a2) {
-        const int slab = special ? 64 + a2 : 8 * cx + 2 * g + xsel;
-        const float* vec = reinterpret_cast<const float*>(rec + VEC_OFF);
+  if (warp < 16 && (warp >> 2) < ntile) {
+    const int g = warp >> 2, q = warp & 3;
+    const int row = 32 * q + lane, xsel = row >> 6, y = row & 63;
+    const uint8_t* rec = has_init ? P.init + (size_t)bh * REC_BYTES : nullptr;
+    const int nacc = special ? 2 : 1;
+    for (int a2 = 0; a2 < nacc; ++a2) {
+      const int slab = special ? 64 + a2 : 8 * cx + 2 * g + xsel;
 #pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
-          uint32_t v[32];
+      for (int h = 0; h < 2; ++h) {
+        uint32_t v[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) v[c] = 0u;
+        if (has_init) {
+          const float* vec = reinterpret_cast<const float*>(rec + VEC_OFF);
           if (!special || row < 64) {
             if (special && a2 == 1) {          // fp32 copy of the normaliser matrix
 #pragma unroll
@@ -174,102 +177,120 @@ build_kernel(const __grid_constant__ CUtensorMap tmXT, const __grid_constant__ C
                 for (int j = 0; j < 4; ++j) v[8 * c8 + 2 * j] = w[j] << 16, v[8 * c8 + 2 * j + 1] = w[j] & 0xffff0000u;
               }
             }
-          } else {
+          } else if (row == 64) {
 #pragma unroll
-            for (int c = 0; c < 32; ++c) v[c] = row == 64 ? __float_as_uint(vec[a2 * 64 + 32 * h + c]) : 0u;
+            for (int c = 0; c < 32; ++c) v[c] = __float_as_uint(vec[a2 * 64 + 32 * h + c]);
           }
-          tmem_st32(tmem + ((uint32_t)(32 * q) << 16) + 64 * (g + a2) + 32 * h, v);
         }
+        tmem_st32(((uint32_t)(32 * q) << 16) + 64 * (g + a2) + 32 * h, v);
       }
-      tmem_wait_st();
     }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
+    tmem_wait_st();
   }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
 
   if (warp < 16) {
-    // ------------------------------------------------------------------ generator groups
-    const int g = warp >> 2, q = warp & 3;
-    if (g < ntile) {
-      const int row = 32 * q + lane;          // TMEM lane == feature row (xsel, y) of the tile
-      const int xsel = row >> 6, y = row & 63;
-      const int x = (8 * cx + 2 * g + xsel) & 63;
-      const uint32_t a_dst = tmem + ((uint32_t)(32 * q) << 16) + B_ACOL + 64 * g;
-      // byte offsets of the 16-byte chunks of rows y and x inside the 128B-swizzled XT tile
-      uint32_t yo[8], xo[8];
+    // ------------------------------------------------------------------ generator groups ("k-split")
+    // The 64 tokens of a block are four MMA k-steps of 16 tokens.  Group k (4 warps = the 4 TMEM lane
+    // quadrants) produces k-step k of ALL tiles of the CTA: it reads its 16-token run of feature row y
+    // once and multiplies it with the runs of the tiles' x rows.  (One group per tile would re-read
+    // the y rows four times: 640 shared-memory wavefronts per block against 512 cycles of MMA.)
+    const int k = warp >> 2, q = warp & 3;
+    const int row = 32 * q + lane;                // TMEM lane == feature row (xsel, y) of every tile
+    const int xsel = row >> 6, y = row & 63;
+    // byte offsets inside the 128B-swizzled XT tile of the two 16-byte chunks holding tokens
+    // [16k, 16k+16) of row y and of the x rows of the four tiles
+    uint32_t yo[2], xo[4][2];
 #pragma unroll
-      for (int c8 = 0; c8 < 8; ++c8) {
-        yo[c8] = (uint32_t)y * 128 + ((uint32_t)(c8 ^ (y & 7)) << 4);
-        xo[c8] = (uint32_t)x * 128 + ((uint32_t)(c8 ^ (x & 7)) << 4);
-      }
-      const uint32_t fill = row == 64 ? 0x3F803F80u : 0u;
-      const uint32_t smem0 = smem_u32(smem);
-#pragma unroll 1
-      for (int it = 0; it < P.nproc; ++it) {
-        const int s = it & 3, ph = (it >> 2) & 1, buf = it & 1;
-        mbar_wait(&full[s], ph);
-        const uint32_t xt = smem0 + s * B_STAGE_BYTES;
-        uint32_t a[32];
+    for (int c = 0; c < 2; ++c) {
+      yo[c] = (uint32_t)y * 128 + ((uint32_t)((2 * k + c) ^ (y & 7)) << 4);
 #pragma unroll
-        for (int c8 = 0; c8 < 8; ++c8) lds128(xt + yo[c8], a + 4 * c8);
-        if (!special) {
-#pragma unroll
-          for (int c8 = 0; c8 < 8; ++c8) {
-            uint32_t v[4];
-            lds128(xt + xo[c8], v);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) a[4 * c8 + i] = mul_bf16x2(v[i], a[4 * c8 + i]);
-          }
-        } else if (row >= 64) {
-          // special tile: rows 0..63 = Y (S1 / normaliser matrix), row 64 = ones (S0 / normaliser vector)
-#pragma unroll
-          for (int i = 0; i < 32; ++i) a[i] = fill;
-        }
-        // A buffer `buf` was last read by the MMAs of block it-2
-        if (it >= 2) mbar_wait(&done[(it - 2) & 3], ((it - 2) >> 2) & 1);
-        tc_fence_after();
-        tmem_st32(a_dst + 32 * buf, a);
-        tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&a_ready[g * 2 + buf]);
+      for (int t = 0; t < 4; ++t) {
+        const int x = (8 * cx + 2 * t + xsel) & 63;
+        xo[t][c] = (uint32_t)x * 128 + ((uint32_t)((2 * k + c) ^ (x & 7)) << 4);
       }
     }
-  } else if (warp < 20) {
-    // ------------------------------------------------------------------ MMA issuers
-    const int g = warp - 16;
-    if (lane == 0 && g < ntile) {
-      const uint32_t idesc = make_idesc_bf16(128, 64, false, true);
-      const uint64_t dW0 = desc_mnmajor_sw128(smem_u32(smem) + 8192, 8192);
-      const uint32_t acc = tmem + 64 * g;
-      const uint32_t a0 = tmem + B_ACOL + 64 * g;
-      BoundaryIter bi(P);
-      int snaps = 0;
-      bool pending = false;
+    const uint32_t fill = row == 64 ? 0x3F803F80u : 0u;
+    const uint32_t a_col0 = ((uint32_t)(32 * q) << 16) + B_ACOL + 8 * k;
 #pragma unroll 1
-      for (int it = 0; it < P.nproc; ++it) {
-        const int s = it & 3, ph = (it >> 2) & 1, buf = it & 1;
-        const bool bnd = bi.step(it);
-        const uint64_t dW = dW0 + (uint64_t)(s * (B_STAGE_BYTES >> 4));
-        const uint32_t a_t = a0 + 32 * buf;
-        mbar_wait(&full[s], ph);
-        if (pending) mbar_wait(&acc_free[g], (snaps - 1) & 1);
-        mbar_wait(&a_ready[g * 2 + buf], (it >> 1) & 1);
-        tc_fence_after();
+    for (int it = 0; it < P.nproc; ++it) {
+      const int s = it & 3, ph = (it >> 2) & 1, buf = it & 1;
+      mbar_wait(&full[s], ph);
+      const uint32_t xt = FM_SMEM_BASE + s * B_STAGE_BYTES;
+      uint32_t yr[8], a[4][8];
+      lds128(xt + yo[0], yr);
+      lds128(xt + yo[1], yr + 4);
+      if (!special) {
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) umma_ts(acc, a_t + kk * 8, dW + kk * 128, idesc, has_init || (it | kk) != 0);
-        if (special) {
+        for (int t = 0; t < 4; ++t) {
+          uint32_t v[8];
+          lds128(xt + xo[t][0], v);
+          lds128(xt + xo[t][1], v + 4);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            umma_ts(tmem + 64, a_t + kk * 8, dW + 512 + kk * 128, idesc, has_init || (it | kk) != 0);
+          for (int i = 0; i < 8; ++i) a[t][i] = mul_bf16x2(v[i], yr[i]);
         }
-        umma_commit(&done[s]);
-        if (bnd) {
-          umma_commit(&acc_full[g]);
-          ++snaps;
+      } else {
+        // special tile: rows 0..63 = Y (S1 / normaliser matrix), row 64 = ones (S0 / normaliser vector)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[0][i] = row < 64 ? yr[i] : fill;
+      }
+      // A buffer `buf` was last read by the MMAs of block it-2
+      if (it >= 2) mbar_wait(&done[(it - 2) & 3], ((it - 2) >> 2) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        if (t < ntile) tmem_st8(a_col0 + 64 * t + 32 * buf, a[t]);
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a_ready[k * 2 + buf]);
+    }
+  } else if (warp < 20) {
+    // ------------------------------------------------------------------ MMA issuers (converged warps)
+    // issuer kk: k-step kk of every tile, as soon as generator group kk has written it
+    const int kk = warp - 16;
+    constexpr uint32_t IDESC = make_idesc_bf16(128, 64, false, true);
+    constexpr uint32_t BAR0 = FM_SMEM_BASE + B_STAGES * B_STAGE_BYTES;   // shared address of bars[0]
+    BoundaryIter bi(P);
+    int snaps = 0;
+    bool pending = false;
+#pragma unroll 1
+    for (int it0 = 0; it0 < P.nproc; it0 += 4) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {          // j = ring stage (compile-time), j & 1 = A buffer
+        const int it = it0 + j;
+        if (it < P.nproc) {
+          const bool bnd = bi.step(it);
+          if (lane == 0) {
+            if (pending)
+              for (int t = 0; t < ntile; ++t) mbar_wait(&acc_free[t], (snaps - 1) & 1);
+            // group kk read the block's tiles itself, so their TMA has landed
+            mbar_wait(&a_ready[kk * 2 + (j & 1)], (it >> 1) & 1);
+          }
+          __syncwarp();
+          tc_fence_after();
+          if (elect_one()) {
+            // (the k-step offsets of the A columns and of the descriptors are selected per warp)
+#define FM_BUILD_ISSUE(KK)                                                                              \
+  if (!special) {                                                                                       \
+    _Pragma("unroll") for (int t = 0; t < 4; ++t)                                                       \
+        umma_ts(64 * t, B_ACOL + 64 * t + 32 * (j & 1) + 8 * KK, P.dW[j][KK], IDESC, 1);                 \
+  } else {                                                                                              \
+    umma_ts(0, B_ACOL + 32 * (j & 1) + 8 * KK, P.dW[j][KK], IDESC, 1);                                   \
+    umma_ts(64, B_ACOL + 32 * (j & 1) + 8 * KK, P.dW2[j][KK], IDESC, 1);                                 \
+  }
+            if (kk == 0) { FM_BUILD_ISSUE(0) } else if (kk == 1) { FM_BUILD_ISSUE(1) }
+            else if (kk == 2) { FM_BUILD_ISSUE(2) } else { FM_BUILD_ISSUE(3) }
+            umma_commit_addr(BAR0 + 8 * (4 + j));   // done[j]
+            if (bnd)
+              for (int t = 0; t < ntile; ++t) umma_commit(&acc_full[t]);
+          }
+          __syncwarp();
+          if (bnd) ++snaps;
+          pending = bnd;
         }
-        pending = bnd;
       }
     }
   } else if (warp == 20) {
@@ -711,6 +732,12 @@ static int launch_build(const Problem& pb, const MomLayout& m, const void* xt, c
   P.N = m.N, P.nblk = (m.N + 63) / 64, P.Lb = m.L / 64, P.nseg = m.nseg, P.reverse = reverse, P.causal = pb.causal;
   P.p = pb.p, P.state = state, P.init = (const uint8_t*)init;
   P.special_cx = pb.p == 2 ? B_CTAS_P2 - 1 : 0;
+  for (int st = 0; st < B_STAGES; ++st)
+    for (int kk = 0; kk < 4; ++kk) {
+      const uint32_t base = sm100::FM_SMEM_BASE + st * B_STAGE_BYTES;
+      P.dW[st][kk] = sm100::desc_mnmajor_sw128_const(base + 8192, 8192) + kk * 128;
+      P.dW2[st][kk] = sm100::desc_mnmajor_sw128_const(base + 16384, 8192) + kk * 128;
+    }
   if (init && pb.causal) {
     // the boundary state of the first (reverse scan: last) local segment is the incoming state itself
     uint8_t* dst = state + (size_t)(reverse ? m.nseg - 1 : 0) * REC_BYTES;

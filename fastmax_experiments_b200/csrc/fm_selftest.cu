@@ -209,6 +209,83 @@ __global__ void __launch_bounds__(128, 1) mmarate_kernel(int variant, int reps, 
 }  // namespace
 }  // namespace fm
 
+// variant "const": every MMA operand comes from kernel parameters (constant bank) or immediates, so the
+// compiler can keep them in uniform registers without R2UR moves
+namespace fm {
+namespace {
+struct ConstDescs {
+  unsigned long long b[4];
+  unsigned int idesc, smem_base_expected;
+};
+__global__ void __launch_bounds__(128, 1) mmarate_const_kernel(const __grid_constant__ ConstDescs cd, int reps,
+                                                               unsigned long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 65536 / 4; i += 128) reinterpret_cast<uint32_t*>(smem_raw)[i] = 0x3C003C00u;
+  if (warp == 0) {
+    tmem_alloc(&slot, 512);
+    tmem_relinquish();
+  }
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_barrier_init();
+    out[2] = smem_u32(smem_raw);
+    out[3] = slot;
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 0) {
+    long long t0 = clock64();
+#pragma unroll 1
+    for (int r = 0; r < reps; r += 4) {
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) umma_ts(kk * 64, 448 + kk * 8, cd.b[kk], cd.idesc, 1);
+      }
+      __syncwarp();
+    }
+    long long t1 = clock64();
+    if (tid == 0) {
+      umma_commit(&bar);
+      mbar_wait(&bar, 0);
+      long long t2 = clock64();
+      out[0] = (unsigned long long)(t1 - t0);
+      out[1] = (unsigned long long)(t2 - t0);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(slot, 512);
+}
+}  // namespace
+}  // namespace fm
+
+extern "C" int fastmax_selftest_mmarate_const(int reps, unsigned int smem_base, unsigned long long* out_dev, void* stream) {
+  using namespace fm;
+  ConstDescs cd;
+  for (int kk = 0; kk < 4; ++kk) {
+    unsigned long long d = 0;
+    const unsigned int saddr = smem_base + 16384;
+    d |= (unsigned long long)((saddr & 0x3FFFFu) >> 4);
+    d |= (unsigned long long)((8192u >> 4) & 0x3FFFu) << 16;
+    d |= (unsigned long long)((1024u >> 4) & 0x3FFFu) << 32;
+    d |= 1ull << 46;
+    d |= 2ull << 61;
+    cd.b[kk] = d + kk * 128;
+  }
+  cd.idesc = sm100::make_idesc_bf16(128, 64, false, true);
+  cd.smem_base_expected = smem_base;
+  const int smem = 65536 + 1024;
+  FM_CUDA(cudaFuncSetAttribute(mmarate_const_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  FM_LAUNCH("selftest_mmarate_const", (cudaStream_t)stream,
+            mmarate_const_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(cd, reps, out_dev));
+  return FASTMAX_OK;
+}
+
 extern "C" int fastmax_selftest_mmarate(int variant, int reps, unsigned long long* out_dev, void* stream) {
   using namespace fm;
   const int smem = 65536 + 1024 + 1024;

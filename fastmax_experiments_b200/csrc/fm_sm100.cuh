@@ -220,6 +220,42 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64
       : "memory");
 }
 
+// ---- host-side descriptor construction ----------------------------------------------------
+// tcgen05.mma operands are uniform-datapath registers.  When a descriptor is computed in ordinary
+// registers nvcc 12.9 wraps every MMA in an ELECT / R2UR x4-7 / UTCHMMA sequence that costs ~110
+// cycles per instruction (tools/mmarate.py); when it comes from the constant bank (kernel parameters)
+// or is an immediate, and the MMAs sit together inside one elect.sync region of a converged warp,
+// they issue back to back at the tensor pipe's rate (32 cycles for 128x64x16, tools/mmarate_const.py).
+// So the kernels take their shared-memory descriptors as kernel parameters, built on the host for the
+// known dynamic-shared-memory base (FM_SMEM_BASE, asserted on the device), and address tensor memory
+// with immediates (allocation base asserted to be 0).
+constexpr uint32_t FM_SMEM_BASE = 1024;   // dynamic smem of a kernel without static __shared__ (1 KiB reserved)
+__host__ __device__ constexpr uint64_t make_smem_desc_const(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                            uint32_t swizzle) {
+  return static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4) | (static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         (static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (static_cast<uint64_t>(swizzle) << 61);
+}
+__host__ __device__ constexpr uint64_t desc_kmajor_sw128_const(uint32_t saddr) {
+  return make_smem_desc_const(saddr, 16, 1024, 2);
+}
+__host__ __device__ constexpr uint64_t desc_mnmajor_sw128_const(uint32_t saddr, uint32_t mn_block_bytes) {
+  return make_smem_desc_const(saddr, mn_block_bytes, 1024, 2);
+}
+// tcgen05.commit to an mbarrier given by its shared-memory address (an immediate in the callers)
+__device__ __forceinline__ void umma_commit_addr(uint32_t bar_saddr) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_saddr)
+               : "memory");
+}
+// kernels that rely on the immediates above check them once
+__device__ __forceinline__ void assert_bases(uint32_t tmem_base, const void* smem_aligned) {
+  if (tmem_base != 0 || smem_u32(smem_aligned) != FM_SMEM_BASE) {
+    if (threadIdx.x == 0)
+      printf("fastmax: unexpected TMEM base %u or dynamic smem base %u (expected 0 / %u)\n", tmem_base,
+             smem_u32(smem_aligned), FM_SMEM_BASE);
+    __trap();
+  }
+}
+
 // pack two floats to bf16x2: lo -> bits [15:0], hi -> bits [31:16]
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t r;
