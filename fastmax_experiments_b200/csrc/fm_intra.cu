@@ -55,11 +55,85 @@ template <int MODE> struct IntraCfg {
   static constexpr int SMEM = RES_BYTES + STAGES * STAGE_STRIDE + NORM_BYTES + 1024 + 1024;
 };
 
+// Shared-memory descriptors of every MMA operand, built on the host (fm_sm100.cuh: operands that come
+// from the constant bank let one thread issue at the tensor pipe's rate).
+struct IntraDescs {
+  unsigned long long resK[8][4];        // resident tile (R1 tiles, then R2 tiles) x k-step, K-major
+  unsigned long long strK[6][2][4];     // ring stage x operand (T1, T2) x k-step, K-major
+  unsigned long long strMN[6][2][4];    // same tiles read MN-major (B of the accumulating MMAs)
+  unsigned long long normK[4];          // normaliser slab, K-major
+};
+
+template <int MODE> __host__ __device__ constexpr int intra_otile(int w, int x) {
+  return MODE == INTRA_DKDV ? w : (w == 0 ? (x == 0 ? 0 : 3) : (x == 0 ? 1 : 2));
+}
+template <int MODE> __host__ __device__ constexpr uint32_t intra_bar0() {
+  return FM_SMEM_BASE + IntraCfg<MODE>::RES_BYTES + IntraCfg<MODE>::STAGES * IntraCfg<MODE>::STAGE_STRIDE +
+         IntraCfg<MODE>::NORM_BYTES;
+}
+
+// score MMAs of one (output tile, stream tile) pair: S = R1_o . T1^T  (and dP = R2_o . T2^T)
+template <int MODE, int W, int X>
+__device__ __forceinline__ void intra_issue_scores(const IntraDescs& D, int st) {
+  constexpr int O = intra_otile<MODE>(W, X);
+  constexpr uint32_t IDK = make_idesc_bf16(128, 64, false, false);
+  constexpr uint32_t SB = 256 + 128 * W;
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) umma_ss(SB, D.resK[O][kk], D.strK[st][0][kk], IDK, kk > 0);
+  if constexpr (MODE != INTRA_FWD) {
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk)
+      umma_ss(SB + 64, D.resK[IntraCfg<MODE>::OUT_TILES + O][kk], D.strK[st][1][kk], IDK, kk > 0);
+  }
+  umma_commit_addr(intra_bar0<MODE>() + 8 * (17 + W));   // s_full[W]
+}
+
+// accumulating MMAs of the pair (A = bf16 scores in tensor memory)
+template <int MODE, int W, int X>
+__device__ __forceinline__ void intra_issue_acc(const IntraDescs& D, int st) {
+  constexpr int O = intra_otile<MODE>(W, X);
+  constexpr uint32_t IDN = make_idesc_bf16(128, 64, false, true);
+  constexpr uint32_t SB = 256 + 128 * W;
+  if constexpr (MODE == INTRA_FWD) {
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) umma_ts(64 * O, SB + 8 * kk, D.strMN[st][1][kk], IDN, 1);
+  } else if constexpr (MODE == INTRA_DQ) {
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) umma_ts(64 * O, SB + 8 * kk, D.strMN[st][0][kk], IDN, 1);
+  } else {
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) umma_ts(128 * O, SB + 8 * kk, D.strMN[st][1][kk], IDN, 1);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) umma_ts(128 * O + 64, SB + 32 + 8 * kk, D.strMN[st][0][kk], IDN, 1);
+  }
+  umma_commit_addr(intra_bar0<MODE>() + 8 * (19 + W));   // s_free[W]
+}
+
+// normaliser column: T_o = R1_o . N2 into the two halves of the warpgroup's score buffer
+template <int MODE, int W, int X>
+__device__ __forceinline__ void intra_issue_norm(const IntraDescs& D) {
+  constexpr int O = intra_otile<MODE>(W, X);
+  constexpr uint32_t IDK = make_idesc_bf16(128, 64, false, false);
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) umma_ss(256 + 128 * W + 64 * X, D.resK[O][kk], D.normK[kk], IDK, kk > 0);
+}
+
+#define FM_INTRA_CALL_WX(FN, ...)                          \
+  do {                                                     \
+    if (w == 0) {                                          \
+      if (x == 0) FN<MODE, 0, 0>(__VA_ARGS__);             \
+      else FN<MODE, 0, 1>(__VA_ARGS__);                    \
+    } else {                                               \
+      if (x == 0) FN<MODE, 1, 0>(__VA_ARGS__);             \
+      else FN<MODE, 1, 1>(__VA_ARGS__);                    \
+    }                                                      \
+  } while (0)
+
 template <int MODE>
 __global__ void __launch_bounds__(384, 1)
 intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ CUtensorMap tmR2,
              const __grid_constant__ CUtensorMap tmT1, const __grid_constant__ CUtensorMap tmT2,
-             const __grid_constant__ CUtensorMap tmS, const IntraParams P) {
+             const __grid_constant__ CUtensorMap tmS, const __grid_constant__ IntraDescs DS, const IntraParams P) {
   using C = IntraCfg<MODE>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -109,6 +183,20 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  assert_bases(tmem, smem);
+  // the output accumulators start at zero; every accumulating MMA then has accumulate = 1
+  if (warp >= 4) {
+    uint32_t z[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) z[i] = 0u;
+    const uint32_t la = ((uint32_t)(32 * (warp & 3)) << 16) + 128 * ((warp - 4) >> 2);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) tmem_st32(la + 32 * i, z);
+    tmem_wait_st();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
 
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer
@@ -186,22 +274,13 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
           mbar_wait(&full[st], ph);
           used = true;
         }
-        // ---- score MMAs: S = R1_o . T1^T  (and dP = R2_o . T2^T)
-        if (issuer) {
-          if (npair > 0) mbar_wait(&s_free[w], (npair - 1) & 1);
+        // ---- score MMAs (issued by the warpgroup's first warp, converged, one elected lane)
+        if (q == 0) {
+          if (lane == 0 && npair > 0) mbar_wait(&s_free[w], (npair - 1) & 1);
+          __syncwarp();
           tc_fence_after();
-          const uint64_t dA1 = desc_kmajor_sw128(smem_u32(res + o * 16384));
-          const uint64_t dB1 = desc_kmajor_sw128(smem_u32(sp));
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) umma_ss(tmem + 256 + 128 * w, dA1 + kk * 2, dB1 + kk * 2, id_kk, kk > 0);
-          if constexpr (MODE != INTRA_FWD) {
-            const uint64_t dA2 = desc_kmajor_sw128(smem_u32(res + (C::OUT_TILES + o) * 16384));
-            const uint64_t dB2 = desc_kmajor_sw128(smem_u32(sp + 8192));
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              umma_ss(tmem + 256 + 128 * w + 64, dA2 + kk * 2, dB2 + kk * 2, id_kk, kk > 0);
-          }
-          umma_commit(&s_full[w]);
+          if (elect_one()) FM_INTRA_CALL_WX(intra_issue_scores, DS, st);
+          __syncwarp();
         }
         mbar_wait(&s_full[w], npair & 1);
         tc_fence_after();
@@ -265,30 +344,10 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
         tmem_wait_st();
         tc_fence_before();
         asm volatile("bar.sync %0, 128;" ::"r"(1 + w) : "memory");
-        if (issuer) {
+        if (q == 0) {
           tc_fence_after();
-          const uint32_t a_t = tmem + 256 + 128 * w;
-          if constexpr (MODE == INTRA_FWD) {
-            const uint64_t dV = desc_mnmajor_sw128(smem_u32(sp + 8192), 8192);
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) umma_ts(tmem + 64 * o, a_t + kk * 8, dV + kk * 128, id_kn, (jt | kk) != 0);
-          } else if constexpr (MODE == INTRA_DQ) {
-            const uint64_t dK = desc_mnmajor_sw128(smem_u32(sp), 8192);
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) umma_ts(tmem + 64 * o, a_t + kk * 8, dK + kk * 128, id_kn, (jt | kk) != 0);
-          } else {
-            // first stream tile of output tile o is jt == 2*o
-            const bool first = jt == 2 * o;
-            const uint64_t dU = desc_mnmajor_sw128(smem_u32(sp + 8192), 8192);
-            const uint64_t dQ = desc_mnmajor_sw128(smem_u32(sp), 8192);
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              umma_ts(tmem + 128 * o, a_t + kk * 8, dU + kk * 128, id_kn, !(first && kk == 0));
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              umma_ts(tmem + 128 * o + 64, a_t + 32 + kk * 8, dQ + kk * 128, id_kn, !(first && kk == 0));
-          }
-          umma_commit(&s_free[w]);
+          if (elect_one()) FM_INTRA_CALL_WX(intra_issue_acc, DS, st);
+          __syncwarp();
         }
         ++npair;
       }
@@ -305,18 +364,18 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
     }
     // ---- moment part of the normaliser column: T_o = R1_o . N2 (one more score-like MMA per output
     // tile, into the two halves of the warpgroup's score buffer)
-    if (has_norm && issuer) {
-      if (npair > 0) mbar_wait(&s_free[w], (npair - 1) & 1);
+    if (has_norm && q == 0) {
+      if (lane == 0 && npair > 0) mbar_wait(&s_free[w], (npair - 1) & 1);
+      __syncwarp();
       tc_fence_after();
-      const uint64_t dN = desc_kmajor_sw128(smem_u32(norm_s));
+      if (elect_one()) {
 #pragma unroll
-      for (int x = 0; x < 2; ++x) {
-        if (x >= n_ot) break;
-        const uint64_t dA = desc_kmajor_sw128(smem_u32(res + otile[x] * 16384));
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-          umma_ss(tmem + 256 + 128 * w + 64 * x, dA + kk * 2, dN + kk * 2, id_kk, kk > 0);
+        for (int x = 0; x < 2; ++x) {
+          if (x >= n_ot) break;
+          FM_INTRA_CALL_WX(intra_issue_norm, DS);
+        }
       }
+      __syncwarp();
     }
     if (issuer) umma_commit(&acc_done[w]);
     mbar_wait(&acc_done[w], 0);
@@ -428,7 +487,22 @@ static int launch_intra_t(const Problem& pb, int L, int Npad, const void* r1, co
   FM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
   constexpr int CT = C::OUT_TILES * 128;
   dim3 grid((pb.N + CT - 1) / CT, BH);
-  FM_LAUNCH(name, pb.stream, kern<<<grid, 384, C::SMEM, pb.stream>>>(m[0], m[1], m[2], m[3], tmS, P));
+  IntraDescs DS{};
+  {
+    const uint32_t base = sm100::FM_SMEM_BASE;
+    for (int i = 0; i < C::OUT_TILES * C::RES_OPS; ++i)
+      for (int kk = 0; kk < 4; ++kk) DS.resK[i][kk] = sm100::desc_kmajor_sw128_const(base + i * 16384) + kk * 2;
+    for (int st = 0; st < C::STAGES; ++st)
+      for (int op = 0; op < 2; ++op)
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint32_t a = base + C::RES_BYTES + st * C::STAGE_STRIDE + op * 8192;
+          DS.strK[st][op][kk] = sm100::desc_kmajor_sw128_const(a) + kk * 2;
+          DS.strMN[st][op][kk] = sm100::desc_mnmajor_sw128_const(a, 8192) + kk * 128;
+        }
+    for (int kk = 0; kk < 4; ++kk)
+      DS.normK[kk] = sm100::desc_kmajor_sw128_const(base + C::RES_BYTES + C::STAGES * C::STAGE_STRIDE) + kk * 2;
+  }
+  FM_LAUNCH(name, pb.stream, kern<<<grid, 384, C::SMEM, pb.stream>>>(m[0], m[1], m[2], m[3], tmS, DS, P));
   return FASTMAX_OK;
 }
 
