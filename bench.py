@@ -248,7 +248,8 @@ def main() -> None:
 
     import torch.distributed as dist
     from fastmax_experiments_b200 import _lib
-    from fastmax_experiments_b200.fastmax import fastmax_fwd_raw, fastmax_bwd_raw
+    from fastmax_experiments_b200.fastmax import (SAVE_STATES_MAX_BYTES, fastmax_bwd_raw, fastmax_fwd_raw,
+                                                  saved_state_bytes)
     from fastmax_experiments_b200.host import fastmax_fwd_bwd_host
 
     if not torch.cuda.is_available():
@@ -267,12 +268,17 @@ def main() -> None:
     pl = _lib.plan(B, H, N, D, p, True, _lib.DTYPE_BF16, algo)
 
     launches = 0
+    # same policy as the autograd op (fastmax.py): keep the forward moment states for backward when
+    # they fit the budget, else rebuild them in backward
+    keep_bytes = saved_state_bytes(q, True, p, algo)
+    keep = 0 < keep_bytes <= SAVE_STATES_MAX_BYTES
 
     def step():
         nonlocal launches
-        o, g = fastmax_fwd_raw(q, k, v, True, inv_c, p, algo)
+        saved = torch.empty(keep_bytes, dtype=torch.uint8, device=dev) if keep else None
+        o, g = fastmax_fwd_raw(q, k, v, True, inv_c, p, algo, saved=saved)
         launches += lib.fastmax_last_launch_count()
-        out = fastmax_bwd_raw(q, k, v, o, g, do, True, inv_c, p, algo)
+        out = fastmax_bwd_raw(q, k, v, o, g, do, True, inv_c, p, algo, saved=saved)
         launches += lib.fastmax_last_launch_count()
         return out
 
@@ -322,7 +328,7 @@ def main() -> None:
     peaks = load_peaks()
     U = B * H * N
     f_fwd, f_bwd = flops_alg(D, p)
-    exec_flops = (pl.fwd_tensor_flops + pl.bwd_tensor_flops) or None
+    exec_flops = (pl.fwd_tensor_flops + pl.bwd_tensor_flops - (pl.rebuild_tensor_flops if keep else 0.0)) or None
     counted = U * (f_fwd + f_bwd)
     if exec_flops:
         counted = min(counted, exec_flops)       # never overstate utilisation
@@ -348,6 +354,7 @@ def main() -> None:
         "config": {"workload": f"fastmax p=2 causal fwd+bwd B={B} H={H} N={N} D={D} bf16 (per GPU)",
                    "B": B, "H": H, "N": N, "D": D, "p": p, "causal": True,
                    "algo": {1: "exact", 2: "moments"}[pl.algo], "seg_len": pl.seg_len,
+                   "kept_forward_states_bytes": keep_bytes if keep else 0,
                    "l2": "inputs larger than L2 (q,k,v,do 512 MiB each)",
                    "sharding": "(b,h) units per rank, no collective"},
         "clocks": clocks, "gpu_launches": launches, "roofline": roofline, "kernels": kernels,

@@ -19,6 +19,7 @@ SYMBOLS = [
     "fastmax_plan_make", "fastmax_fwd_workspace_bytes", "fastmax_bwd_workspace_bytes",
     "fastmax_fwd", "fastmax_bwd", "fastmax_last_launch_count",
     "fastmax_profile_enable", "fastmax_profile_fetch",
+    "fastmax_saved_state_bytes", "fastmax_fwd_ex", "fastmax_bwd_ex",
     "fastmax_sp_state_bytes", "fastmax_sp_local_state_workspace_bytes", "fastmax_sp_local_state",
     "fastmax_sp_local_state_rev", "fastmax_sp_reduce", "fastmax_fwd_sp", "fastmax_bwd_sp",
 ]
@@ -29,6 +30,7 @@ class Plan(C.Structure):
         ("algo", C.c_int32), ("seg_len", C.c_int32), ("n_seg", C.c_int32), ("reserved", C.c_int32),
         ("fwd_workspace_bytes", C.c_uint64), ("bwd_workspace_bytes", C.c_uint64),
         ("fwd_tensor_flops", C.c_double), ("bwd_tensor_flops", C.c_double),
+        ("rebuild_tensor_flops", C.c_double),
     ]
 
 
@@ -66,6 +68,12 @@ def load() -> C.CDLL:
     lib.fastmax_fwd.argtypes = [vp] * 5 + [i32] * 6 + [f32, i32, i32, vp, sz, vp]
     lib.fastmax_bwd.restype = i32
     lib.fastmax_bwd.argtypes = [vp] * 9 + [i32] * 6 + [f32, i32, i32, vp, sz, vp]
+    lib.fastmax_saved_state_bytes.restype = sz
+    lib.fastmax_saved_state_bytes.argtypes = [i32] * 8
+    lib.fastmax_fwd_ex.restype = i32
+    lib.fastmax_fwd_ex.argtypes = [vp] * 6 + [i32] * 6 + [f32, i32, i32, vp, sz, vp]
+    lib.fastmax_bwd_ex.restype = i32
+    lib.fastmax_bwd_ex.argtypes = [vp] * 10 + [i32] * 6 + [f32, i32, i32, vp, sz, vp]
     ll = C.c_longlong
     lib.fastmax_sp_state_bytes.restype = sz
     lib.fastmax_sp_state_bytes.argtypes = [i32, i32]

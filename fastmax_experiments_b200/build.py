@@ -17,6 +17,8 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--use_fast_math", "-Xcompiler", "-fPIC", "-Xcompiler", "-O3",
 ]
+# developer switch, e.g. FASTMAX_NVCC_EXTRA="-DFM_TIMING" (in-kernel cycle counters, tools/timing.py)
+NVCC_FLAGS += os.environ.get("FASTMAX_NVCC_EXTRA", "").split()
 
 
 def sources() -> list[str]:

@@ -109,7 +109,8 @@ int fastmax_plan_make(fastmax_plan* plan, int B, int H, int N, int D, int p, int
     plan->n_seg = (N + plan->seg_len - 1) / plan->seg_len;
     plan->fwd_workspace_bytes = fm::moments_workspace_bytes(B, H, N, causal, false);
     plan->bwd_workspace_bytes = fm::moments_workspace_bytes(B, H, N, causal, true);
-    fm::moments_flops(B, H, N, p, causal, &plan->fwd_tensor_flops, &plan->bwd_tensor_flops);
+    fm::moments_flops(B, H, N, p, causal, &plan->fwd_tensor_flops, &plan->bwd_tensor_flops,
+                      &plan->rebuild_tensor_flops);
     return FASTMAX_OK;
   }
   plan->algo = FASTMAX_ALGO_EXACT;
@@ -168,6 +169,52 @@ int fastmax_bwd(const void* q, const void* k, const void* v, const void* o, cons
     return fm::moments_bwd(pb, q, k, v, o, g, d_o, dq, dk, dv, workspace);
   }
   return fm::exact_bwd(pb, q, k, v, o, g, d_o, dq, dk, dv);
+}
+
+// ---- forward states kept for backward ---------------------------------------------------------
+size_t fastmax_saved_state_bytes(int B, int H, int N, int D, int p, int causal, int dtype, int algo) {
+  fastmax_plan pl;
+  if (fastmax_plan_make(&pl, B, H, N, D, p, causal, dtype, algo)) return 0;
+  if (pl.algo != FASTMAX_ALGO_MOMENTS) return 0;
+  return fm::moments_saved_state_bytes(B, H, N, causal);
+}
+
+int fastmax_fwd_ex(const void* q, const void* k, const void* v, void* o, float* g, void* saved_states, int B, int H,
+                   int N, int D, int p, int causal, float inv_c, int dtype, int algo, void* workspace,
+                   size_t workspace_bytes, void* stream) {
+  if (!saved_states)
+    return fastmax_fwd(q, k, v, o, g, B, H, N, D, p, causal, inv_c, dtype, algo, workspace, workspace_bytes, stream);
+  fm::status().launches = 0;
+  fm::status().cuda_err[0] = 0;
+  if (!q || !k || !v || !o || !g) return FASTMAX_ERR_BAD_ARG;
+  fastmax_plan pl;
+  int rc = fastmax_plan_make(&pl, B, H, N, D, p, causal, dtype, algo);
+  if (rc) return rc;
+  if (pl.algo != FASTMAX_ALGO_MOMENTS) return FASTMAX_ERR_UNSUPPORTED;
+  if (pl.fwd_workspace_bytes > workspace_bytes || !workspace || ((uintptr_t)workspace & 255)) return FASTMAX_ERR_WORKSPACE;
+  Problem pb{B, H, N, D, p, causal ? 1 : 0, dtype, inv_c, (cudaStream_t)stream};
+  pb.saved_states = saved_states;
+  return fm::moments_fwd(pb, q, k, v, o, g, workspace);
+}
+
+int fastmax_bwd_ex(const void* q, const void* k, const void* v, const void* o, const float* g, const void* d_o,
+                   void* dq, void* dk, void* dv, const void* saved_states, int B, int H, int N, int D, int p,
+                   int causal, float inv_c, int dtype, int algo, void* workspace, size_t workspace_bytes,
+                   void* stream) {
+  if (!saved_states)
+    return fastmax_bwd(q, k, v, o, g, d_o, dq, dk, dv, B, H, N, D, p, causal, inv_c, dtype, algo, workspace,
+                       workspace_bytes, stream);
+  fm::status().launches = 0;
+  fm::status().cuda_err[0] = 0;
+  if (!q || !k || !v || !o || !g || !d_o || !dq || !dk || !dv) return FASTMAX_ERR_BAD_ARG;
+  fastmax_plan pl;
+  int rc = fastmax_plan_make(&pl, B, H, N, D, p, causal, dtype, algo);
+  if (rc) return rc;
+  if (pl.algo != FASTMAX_ALGO_MOMENTS) return FASTMAX_ERR_UNSUPPORTED;
+  if (pl.bwd_workspace_bytes > workspace_bytes || !workspace || ((uintptr_t)workspace & 255)) return FASTMAX_ERR_WORKSPACE;
+  Problem pb{B, H, N, D, p, causal ? 1 : 0, dtype, inv_c, (cudaStream_t)stream};
+  pb.saved_states = const_cast<void*>(saved_states);
+  return fm::moments_bwd(pb, q, k, v, o, g, d_o, dq, dk, dv, workspace);
 }
 
 // ---- sequence parallelism ------------------------------------------------------------------

@@ -54,6 +54,9 @@ struct Problem {
   const void* sp_init_fwd = nullptr;
   const void* sp_init_rev = nullptr;
   long long sp_offset = 0;
+  // forward states kept for backward (fastmax_fwd_ex / fastmax_bwd_ex): forward writes its boundary
+  // states here instead of into the workspace; backward reads them instead of rebuilding them
+  void* saved_states = nullptr;
 };
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -91,6 +94,7 @@ int intra_dkdv(const Problem& pb, int L, int Npad, const void* k, const void* v,
                const float* dlt, float* dk_part, float* dv_part, const uint8_t* rstate);
 int moments_seg_len(int N);
 size_t moments_state_bytes(int B, int H);
+size_t moments_saved_state_bytes(int B, int H, int N, int causal);
 size_t moments_local_state_workspace_bytes(int B, int H, int N);
 int moments_local_state(const Problem& pb, const void* x, const void* w, const void* w2, void* state_out, void* ws);
 int moments_local_state_rev(const Problem& pb, const void* q, const void* o, const float* g, const void* d_o,
@@ -98,7 +102,7 @@ int moments_local_state_rev(const Problem& pb, const void* q, const void* o, con
 size_t moments_local_state_rev_workspace_bytes(int B, int H, int N);
 int moments_reduce_states(const void* gathered, int G, int rank, int dir, void* out, int B, int H, cudaStream_t stream);
 size_t moments_workspace_bytes(int B, int H, int N, int causal, bool bwd);
-void moments_flops(int B, int H, int N, int p, int causal, double* fwd, double* bwd);
+void moments_flops(int B, int H, int N, int p, int causal, double* fwd, double* bwd, double* rebuild);
 int moments_fwd(const Problem& pb, const void* q, const void* k, const void* v, void* o, float* g, void* ws);
 int moments_bwd(const Problem& pb, const void* q, const void* k, const void* v, const void* o, const float* g,
                 const void* d_o, void* dq, void* dk, void* dv, void* ws);

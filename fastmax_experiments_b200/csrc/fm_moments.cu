@@ -20,6 +20,8 @@
 #include "fm_moments.cuh"
 #include <stdlib.h>
 
+FM_TIMING_DEFINE(moments)
+
 namespace fm {
 namespace mom {
 using namespace sm100;
@@ -409,9 +411,17 @@ constexpr int A_SMEM = A_RES_BYTES + A_STAGES * A_STAGE_BYTES + 1024 + 1024;
 constexpr int A_THREADS = 19 * 32;                       // 16 epilogue warps, 2 MMA issuers, TMA producer
 
 // Each token tile owns a private 128-column T buffer in tensor memory and its own barrier pair.
-// Measured alternatives on B200 at the headline shape (ms per apply launch): this layout 2.3;
-// two shared N=256 T buffers with one issuer 2.6; two tiles per CTA with a column-split epilogue
-// 2.9; issuing from the epilogue warpgroups 3.2; generated A operands in tensor memory 3.2-5.2.
+// In-kernel cycle counters (-DFM_TIMING, tools/timing.py) at the headline shape, per CTA: 528 MMAs of
+// 128x128x16 take ~75-95 cycles each while the warpgroups read T out (64 in isolation), and the
+// read-out runs at ~2.6 cycles per 32-lane column per quadrant (1.3 in isolation): MMA accumulation
+// and tcgen05.ld share tensor-memory bandwidth, so the floor of this two-stage scheme is about the sum
+// of the two (~56k cycles per 512 tokens), not their maximum.
+// Measured alternatives (ms per apply launch): this layout 2.3 (additive terms read in the tail) -> see
+// bench; one converged constant-bank issuer that also feeds the TMA ring (17 warps) 2.9; two tiles per
+// CTA, eight warps per tile, two N=128 buffers per tile 3.5; two 64-column buffers per tile (N=64 MMAs
+// from shared memory cost 48 cycles instead of 32) 3.7; two shared N=256 T buffers with one issuer 2.6;
+// two tiles per CTA with a column-split epilogue 2.9; issuing from the epilogue warpgroups 3.2;
+// generated A operands in tensor memory 3.2-5.2.
 __global__ void __launch_bounds__(A_THREADS, 1)
 apply_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmY, const ApplyParams P) {
   extern __shared__ uint8_t smem_raw[];
@@ -515,9 +525,20 @@ apply_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CU
     const bool valid = i < P.N;
     const size_t grow = (size_t)bh * P.N + i;
     const uint32_t tbuf = tmem + ((uint32_t)(32 * q) << 16) + 128 * t;
+    // O starts from the additive terms (state vector + intra-segment partial): their loads overlap the
+    // wait for the first T tile and the tail is stores only (the tail read cost 15 % of the CTA time)
     float O[64];
+    {
+      const float4* part = (valid && P.partial) ? reinterpret_cast<const float4*>(P.partial + grow * 64) : nullptr;
 #pragma unroll
-    for (int c = 0; c < 64; ++c) O[c] = 0.f;
+      for (int c4 = 0; c4 < 16; ++c4) {
+        float4 pv = part ? __ldg(part + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        O[4 * c4 + 0] = pv.x + vec_s[4 * c4 + 0];
+        O[4 * c4 + 1] = pv.y + vec_s[4 * c4 + 1];
+        O[4 * c4 + 2] = pv.z + vec_s[4 * c4 + 2];
+        O[4 * c4 + 3] = pv.w + vec_s[4 * c4 + 3];
+      }
+    }
     if (has_state) {
       const uint32_t* xrow = reinterpret_cast<const uint32_t*>(P.X + (valid ? grow : 0) * 64);
 #pragma unroll 1
@@ -553,23 +574,14 @@ apply_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CU
     float scale = P.out_scale;
     if (valid && P.gden) scale *= 1.f / P.gden[grow];
     if (valid) {
-      const float4* part = P.partial ? reinterpret_cast<const float4*>(P.partial + grow * 64) : nullptr;
       uint4* dst = reinterpret_cast<uint4*>(P.out + grow * 64);
 #pragma unroll
       for (int c8 = 0; c8 < 8; ++c8) {
-        float r[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = O[8 * c8 + j] + vec_s[8 * c8 + j];
-        if (part) {
-          float4 p0 = __ldg(part + 2 * c8), p1 = __ldg(part + 2 * c8 + 1);
-          r[0] += p0.x, r[1] += p0.y, r[2] += p0.z, r[3] += p0.w;
-          r[4] += p1.x, r[5] += p1.y, r[6] += p1.z, r[7] += p1.w;
-        }
         uint4 o;
-        o.x = pack_bf16x2(r[0] * scale, r[1] * scale);
-        o.y = pack_bf16x2(r[2] * scale, r[3] * scale);
-        o.z = pack_bf16x2(r[4] * scale, r[5] * scale);
-        o.w = pack_bf16x2(r[6] * scale, r[7] * scale);
+        o.x = pack_bf16x2(O[8 * c8 + 0] * scale, O[8 * c8 + 1] * scale);
+        o.y = pack_bf16x2(O[8 * c8 + 2] * scale, O[8 * c8 + 3] * scale);
+        o.z = pack_bf16x2(O[8 * c8 + 4] * scale, O[8 * c8 + 5] * scale);
+        o.w = pack_bf16x2(O[8 * c8 + 6] * scale, O[8 * c8 + 7] * scale);
         dst[c8] = o;
       }
     }
@@ -780,7 +792,7 @@ int moments_fwd(const Problem& pb, const void* q, const void* k, const void* v, 
   uint8_t* w8 = (uint8_t*)ws;
   int rc;
   const float a = pb.inv_c;
-  uint8_t* state = w8 + m.off_state;
+  uint8_t* state = pb.saved_states ? (uint8_t*)pb.saved_states : w8 + m.off_state;
   float* part = (float*)(w8 + m.off_part);
   // 1. K^T and the boundary states (forward direction)
   if ((rc = launch_transpose(pb, k, w8 + m.off_xt, m.Npad))) return rc;
@@ -809,7 +821,7 @@ int moments_bwd(const Problem& pb, const void* q, const void* k, const void* v, 
   uint8_t* w8 = (uint8_t*)ws;
   int rc;
   const float a = pb.inv_c;
-  uint8_t* S = w8 + m.off_state;
+  uint8_t* S = pb.saved_states ? (uint8_t*)pb.saved_states : w8 + m.off_state;
   uint8_t* R = w8 + m.off_state2;
   float* dq_part = (float*)(w8 + m.off_part);
   float* dk_part = (float*)(w8 + m.off_part2);
@@ -824,8 +836,10 @@ int moments_bwd(const Problem& pb, const void* q, const void* k, const void* v, 
             prep_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, pb.stream>>>(
                 (const bf16*)q, (const bf16*)o, (const bf16*)d_o, g, u, dlt, qd, rows, m.N, m.Npad));
   // 2. forward-direction states of (k, v) (recomputed, not saved) and reverse-direction states of (q, u)
-  if ((rc = launch_transpose(pb, k, w8 + m.off_xt, m.Npad))) return rc;
-  if ((rc = launch_build(pb, m, w8 + m.off_xt, v, k, S, 0, pb.sp_init_fwd))) return rc;
+  if (!pb.saved_states) {
+    if ((rc = launch_transpose(pb, k, w8 + m.off_xt, m.Npad))) return rc;
+    if ((rc = launch_build(pb, m, w8 + m.off_xt, v, k, S, 0, pb.sp_init_fwd))) return rc;
+  }
   if ((rc = launch_transpose(pb, q, w8 + m.off_xt2, m.Npad))) return rc;
   if ((rc = launch_build(pb, m, w8 + m.off_xt2, u, qd, R, 1, pb.sp_init_rev))) return rc;
   // 3. intra-segment partials
@@ -866,6 +880,11 @@ int moments_bwd(const Problem& pb, const void* q, const void* k, const void* v, 
 // sequence parallelism: per-rank total states and their exclusive prefix / suffix over the ranks
 // =============================================================================================
 size_t moments_state_bytes(int B, int H) { return (size_t)B * H * REC_BYTES; }
+
+size_t moments_saved_state_bytes(int B, int H, int N, int causal) {
+  const MomLayout m = mom_layout(B, H, N, moments_seg_len(N), causal, false);
+  return (size_t)m.BH * m.nrec * REC_BYTES;
+}
 
 size_t moments_local_state_workspace_bytes(int B, int H, int N) {
   return align_up((size_t)B * H * 64 * align_up(N, 64) * 2, 1024);
@@ -938,7 +957,7 @@ int moments_reduce_states(const void* gathered, int G, int rank, int dir, void* 
 }
 
 // executed tensor-core flops of the plan (for the utilisation report; never the algorithmic count)
-void moments_flops(int B, int H, int N, int p, int causal, double* fwd, double* bwd) {
+void moments_flops(int B, int H, int N, int p, int causal, double* fwd, double* bwd, double* rebuild) {
   const int L = moments_seg_len(N);
   const MomLayout m = mom_layout(B, H, N, L, causal, false);
   const double mma = 2.0 * 128 * 64 * 16;
@@ -951,9 +970,18 @@ void moments_flops(int B, int H, int N, int p, int causal, double* fwd, double* 
   const double ctas = (double)((N + APPLY_TOK - 1) / APPLY_TOK);
   const double with_state = causal ? (ctas - (double)L / APPLY_TOK > 0 ? ctas - (double)L / APPLY_TOK : 0) : ctas;
   const double slabs = p == 2 ? 65 : 1;
-  const double apply = m.BH * with_state * slabs * 16 * mma;
-  *fwd = build_f + apply;
-  *bwd = build_f + build_r + 3 * apply;
+  const double apply = m.BH * with_state * slabs * (APPLY_TOK / 128 * 4) * mma;
+  // intra-segment tiles (causal only): 128x128x64 GEMMs on the lower-triangular tile pairs of each
+  // segment; forward 2 per pair (scores, P.V), dq 3, dkdv 4
+  double intra_pair = 0;
+  if (causal) {
+    const double t = (double)((N + 127) / 128), ts = (double)L / 128;
+    const double full_segs = (double)(N / L), rem = t - full_segs * ts;
+    intra_pair = m.BH * (full_segs * ts * (ts + 1) / 2 + rem * (rem + 1) / 2) * 2.0 * 128 * 128 * 64;
+  }
+  *fwd = build_f + apply + 2 * intra_pair;
+  *bwd = build_f + build_r + 3 * apply + 7 * intra_pair;
+  *rebuild = build_f;   // skipped by backward when the forward states were kept
 }
 
 }  // namespace fm

@@ -210,13 +210,17 @@ __global__ void __launch_bounds__(128, 1) mmarate_kernel(int variant, int reps, 
 }  // namespace fm
 
 // variant "const": every MMA operand comes from kernel parameters (constant bank) or immediates, so the
-// compiler can keep them in uniform registers without R2UR moves
+// compiler can keep them in uniform registers without R2UR moves.
+// MODE 0: A in tensor memory, N=64   1: A in shared memory, N=64   2: A in smem, N=128   3: A in tmem, N=128
+// Operands rotate over the four k-steps of a 128x64 A tile and of a B tile, like a real K=64 product.
 namespace fm {
 namespace {
 struct ConstDescs {
+  unsigned long long a[4];
   unsigned long long b[4];
   unsigned int idesc, smem_base_expected;
 };
+template <int MODE>
 __global__ void __launch_bounds__(128, 1) mmarate_const_kernel(const __grid_constant__ ConstDescs cd, int reps,
                                                                unsigned long long* out) {
   extern __shared__ uint8_t smem_raw[];
@@ -244,7 +248,12 @@ __global__ void __launch_bounds__(128, 1) mmarate_const_kernel(const __grid_cons
     for (int r = 0; r < reps; r += 4) {
       if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) umma_ts(kk * 64, 448 + kk * 8, cd.b[kk], cd.idesc, 1);
+        for (int kk = 0; kk < 4; ++kk) {
+          if (MODE == 0) umma_ts(kk * 64, 448 + kk * 8, cd.b[kk], cd.idesc, 1);
+          else if (MODE == 1) umma_ss(kk * 64, cd.a[kk], cd.b[kk], cd.idesc, 1);
+          else if (MODE == 2) umma_ss((kk & 1) * 128, cd.a[kk], cd.b[kk], cd.idesc, 1);
+          else umma_ts((kk & 1) * 128, 448 + kk * 8, cd.b[kk], cd.idesc, 1);
+        }
       }
       __syncwarp();
     }
@@ -264,25 +273,29 @@ __global__ void __launch_bounds__(128, 1) mmarate_const_kernel(const __grid_cons
 }  // namespace
 }  // namespace fm
 
-extern "C" int fastmax_selftest_mmarate_const(int reps, unsigned int smem_base, unsigned long long* out_dev, void* stream) {
+extern "C" int fastmax_selftest_mmarate_const(int reps, unsigned int smem_base, unsigned long long* out_dev, void* stream,
+                                              int mode) {
   using namespace fm;
   ConstDescs cd;
+  const int n = (mode == 2 || mode == 3) ? 128 : 64;
   for (int kk = 0; kk < 4; ++kk) {
-    unsigned long long d = 0;
-    const unsigned int saddr = smem_base + 16384;
-    d |= (unsigned long long)((saddr & 0x3FFFFu) >> 4);
-    d |= (unsigned long long)((8192u >> 4) & 0x3FFFu) << 16;
-    d |= (unsigned long long)((1024u >> 4) & 0x3FFFu) << 32;
-    d |= 1ull << 46;
-    d |= 2ull << 61;
-    cd.b[kk] = d + kk * 128;
+    cd.a[kk] = sm100::desc_kmajor_sw128_const(smem_base) + kk * 2;                      // 128x64 K-major tile
+    cd.b[kk] = sm100::desc_mnmajor_sw128_const(smem_base + 16384, 8192) + kk * 128;     // 64xN MN-major tile(s)
   }
-  cd.idesc = sm100::make_idesc_bf16(128, 64, false, true);
+  cd.idesc = sm100::make_idesc_bf16(128, n, false, true);
   cd.smem_base_expected = smem_base;
   const int smem = 65536 + 1024;
-  FM_CUDA(cudaFuncSetAttribute(mmarate_const_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  FM_LAUNCH("selftest_mmarate_const", (cudaStream_t)stream,
-            mmarate_const_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(cd, reps, out_dev));
+  cudaStream_t st = (cudaStream_t)stream;
+#define FM_MRC(M)                                                                                            \
+  case M:                                                                                                    \
+    FM_CUDA(cudaFuncSetAttribute(mmarate_const_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+    FM_LAUNCH("selftest_mmarate_const", st, mmarate_const_kernel<M><<<1, 128, smem, st>>>(cd, reps, out_dev));   \
+    break;
+  switch (mode) {
+    FM_MRC(0) FM_MRC(1) FM_MRC(2) FM_MRC(3)
+    default: return FASTMAX_ERR_BAD_ARG;
+  }
+#undef FM_MRC
   return FASTMAX_OK;
 }
 
@@ -401,3 +414,4 @@ extern "C" int fastmax_selftest_ldrate(int width, int inflight, int iters, int t
   else return FASTMAX_ERR_BAD_ARG;
   return FASTMAX_OK;
 }
+

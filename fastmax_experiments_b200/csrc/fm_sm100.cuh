@@ -55,6 +55,29 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Developer cycle counters (-DFM_TIMING): FM_T(slot, cycles) adds into a per-file global table that
+// fastmax_debug_timing_fetch_<file>() returns; compiled out otherwise.  Put FM_TIMING_DEFINE(<file>)
+// once at namespace scope of the .cu that uses FM_T.
+#ifdef FM_TIMING
+#define FM_TIMING_DEFINE(name)                                                                        \
+  static __device__ unsigned long long fm_timing_tab[64];                                             \
+  extern "C" int fastmax_debug_timing_fetch_##name(unsigned long long* out, int reset) {              \
+    cudaDeviceSynchronize();                                                                          \
+    if (cudaMemcpyFromSymbol(out, fm_timing_tab, sizeof(unsigned long long) * 64) != cudaSuccess) return -4; \
+    if (reset) {                                                                                      \
+      unsigned long long z[64] = {};                                                                  \
+      cudaMemcpyToSymbol(fm_timing_tab, z, sizeof(z));                                                \
+    }                                                                                                 \
+    return 0;                                                                                         \
+  }
+#define FM_T(slot, val) atomicAdd(&fm_timing_tab[slot], (unsigned long long)(val))
+#define FM_NOW() clock64()
+#else
+#define FM_TIMING_DEFINE(name)
+#define FM_T(slot, val) ((void)0)
+#define FM_NOW() 0LL
+#endif
+
 // Wait with a watchdog: a protocol bug must trap (kernel error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
   if (mbar_try_wait(bar, parity)) return;
@@ -109,6 +132,24 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// wait::ld that names the destination registers of the load it completes, so the compiler cannot
+// move their uses above the wait (needed when other loads are kept in flight around it)
+__device__ __forceinline__ void tmem_wait_ld_dep16(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld_dep32(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                 "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                 "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // tcgen05.commit: mbarrier arrives when all prior tcgen05.mma of this thread have completed

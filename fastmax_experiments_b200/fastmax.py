@@ -21,6 +21,7 @@ Behavioural notes:
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 
@@ -52,8 +53,19 @@ def _stream_ptr(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
-def fastmax_fwd_raw(q, k, v, causal: bool, inv_c: float, p: int, algo: int = _lib.ALGO_AUTO):
-    """One call of the C ABI ``fastmax_fwd`` on contiguous (B,H,N,D) CUDA tensors -> (o, g)."""
+# Forward moment states are kept for backward when they fit this budget (bytes per call); above it
+# backward rebuilds them from k, v.  0 disables keeping (the reference's contract: only q,k,v,o,g saved).
+SAVE_STATES_MAX_BYTES = int(os.environ.get("FASTMAX_SAVE_STATES_MAX_BYTES", str(6 << 30)))
+
+
+def saved_state_bytes(q, causal: bool, p: int, algo: int = _lib.ALGO_AUTO) -> int:
+    B, H, N, D = q.shape
+    return _lib.load().fastmax_saved_state_bytes(B, H, N, D, p, int(causal), _DTYPES[q.dtype], algo)
+
+
+def fastmax_fwd_raw(q, k, v, causal: bool, inv_c: float, p: int, algo: int = _lib.ALGO_AUTO, saved=None):
+    """One call of the C ABI ``fastmax_fwd`` (``fastmax_fwd_ex`` when ``saved`` is a state buffer) on
+    contiguous (B,H,N,D) CUDA tensors -> (o, g)."""
     lib = _lib.load()
     B, H, N, D = q.shape
     dt = _DTYPES[q.dtype]
@@ -62,15 +74,16 @@ def fastmax_fwd_raw(q, k, v, causal: bool, inv_c: float, p: int, algo: int = _li
     nbytes = lib.fastmax_fwd_workspace_bytes(B, H, N, D, p, int(causal), dt, algo)
     ws = _workspace(nbytes, q.device)
     with torch.cuda.device(q.device):
-        rc = lib.fastmax_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), g.data_ptr(),
-                             B, H, N, D, p, int(causal), inv_c, dt, algo,
-                             ws.data_ptr() if ws is not None else None, nbytes, _stream_ptr(q.device))
+        rc = lib.fastmax_fwd_ex(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), g.data_ptr(),
+                                saved.data_ptr() if saved is not None else None,
+                                B, H, N, D, p, int(causal), inv_c, dt, algo,
+                                ws.data_ptr() if ws is not None else None, nbytes, _stream_ptr(q.device))
     _lib.check(rc, "fastmax_fwd")
     return o, g
 
 
-def fastmax_bwd_raw(q, k, v, o, g, do, causal: bool, inv_c: float, p: int, algo: int = _lib.ALGO_AUTO):
-    """One call of the C ABI ``fastmax_bwd`` -> (dq, dk, dv)."""
+def fastmax_bwd_raw(q, k, v, o, g, do, causal: bool, inv_c: float, p: int, algo: int = _lib.ALGO_AUTO, saved=None):
+    """One call of the C ABI ``fastmax_bwd`` (``fastmax_bwd_ex`` with kept states) -> (dq, dk, dv)."""
     lib = _lib.load()
     B, H, N, D = q.shape
     dt = _DTYPES[q.dtype]
@@ -78,10 +91,11 @@ def fastmax_bwd_raw(q, k, v, o, g, do, causal: bool, inv_c: float, p: int, algo:
     nbytes = lib.fastmax_bwd_workspace_bytes(B, H, N, D, p, int(causal), dt, algo)
     ws = _workspace(nbytes, q.device)
     with torch.cuda.device(q.device):
-        rc = lib.fastmax_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), g.data_ptr(),
-                             do.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
-                             B, H, N, D, p, int(causal), inv_c, dt, algo,
-                             ws.data_ptr() if ws is not None else None, nbytes, _stream_ptr(q.device))
+        rc = lib.fastmax_bwd_ex(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), g.data_ptr(),
+                                do.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
+                                saved.data_ptr() if saved is not None else None,
+                                B, H, N, D, p, int(causal), inv_c, dt, algo,
+                                ws.data_ptr() if ws is not None else None, nbytes, _stream_ptr(q.device))
     _lib.check(rc, "fastmax_bwd")
     return dq, dk, dv
 
@@ -102,16 +116,22 @@ class FastmaxFunction(torch.autograd.Function):
         c = 1.0 if tensors_normalized is True else normalize_term * math.sqrt(D)   # fastmax.py:79-82
         causal = mask is not False                                                 # fastmax.py:85
         q_, k_, v_ = q.contiguous(), k.contiguous(), v.contiguous()
-        o, g = fastmax_fwd_raw(q_, k_, v_, causal, 1.0 / c, p)
+        saved = None
+        if any(t.requires_grad for t in (q, k, v)):
+            nb = saved_state_bytes(q_, causal, p)
+            if 0 < nb <= SAVE_STATES_MAX_BYTES:
+                saved = torch.empty(nb, dtype=torch.uint8, device=q.device)
+        o, g = fastmax_fwd_raw(q_, k_, v_, causal, 1.0 / c, p, saved=saved)
         ctx.save_for_backward(q_, k_, v_, o, g)                                    # fastmax.py:106
-        ctx.causal, ctx.inv_c, ctx.p = causal, 1.0 / c, p
+        ctx.causal, ctx.inv_c, ctx.p, ctx.saved = causal, 1.0 / c, p, saved
         return o
 
     @staticmethod
     def backward(ctx, o_grad):
         q, k, v, o, g = ctx.saved_tensors
         do = o_grad.to(q.dtype).contiguous()
-        dq, dk, dv = fastmax_bwd_raw(q, k, v, o, g, do, ctx.causal, ctx.inv_c, ctx.p)
+        dq, dk, dv = fastmax_bwd_raw(q, k, v, o, g, do, ctx.causal, ctx.inv_c, ctx.p, saved=ctx.saved)
+        ctx.saved = None
         return dq, dk, dv, None, None, None, None, None, None                      # fastmax.py:182
 
 

@@ -17,9 +17,20 @@ import math
 import torch
 
 from . import _lib
-from .fastmax import fastmax_fwd_raw, fastmax_bwd_raw
+from .fastmax import SAVE_STATES_MAX_BYTES, fastmax_bwd_raw, fastmax_fwd_raw, saved_state_bytes
 
 __all__ = ["fastmax_fwd_bwd_host"]
+
+# One (H2D, compute, D2H) stream triple per device, created once: torch's caching allocator keys its
+# free blocks by stream, so fresh streams per call would turn every device buffer into a cudaMalloc.
+_STREAMS: dict = {}
+
+
+def _streams(dev):
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    if key not in _STREAMS:
+        _STREAMS[key] = tuple(torch.cuda.Stream(dev) for _ in range(3))
+    return _STREAMS[key]
 
 
 def fastmax_fwd_bwd_host(q, k, v, do, out=None, mask=True, normalize_term=8, tensors_normalized=False,
@@ -41,7 +52,7 @@ def fastmax_fwd_bwd_host(q, k, v, do, out=None, mask=True, normalize_term=8, ten
         out = tuple(torch.empty_like(q).pin_memory() for _ in range(4))
     chunks = min(B, chunks or B)
     bounds = [(i * B // chunks, (i + 1) * B // chunks) for i in range(chunks)]
-    s_in, s_cmp, s_out = (torch.cuda.Stream(dev) for _ in range(3))
+    s_in, s_cmp, s_out = _streams(dev)
     ev_in = [torch.cuda.Event() for _ in bounds]
     ev_cmp = [torch.cuda.Event() for _ in bounds]
     keep = []
@@ -51,14 +62,16 @@ def fastmax_fwd_bwd_host(q, k, v, do, out=None, mask=True, normalize_term=8, ten
             ev_in[i].record(s_in)
         with torch.cuda.stream(s_cmp):
             s_cmp.wait_event(ev_in[i])
-            o, g = fastmax_fwd_raw(dq_, dk_, dv_, causal, 1.0 / c, p)
-            gq, gk, gv = fastmax_bwd_raw(dq_, dk_, dv_, o, g, ddo, causal, 1.0 / c, p)
+            nb = saved_state_bytes(dq_, causal, p) if dq_.dtype == torch.bfloat16 else 0
+            saved = torch.empty(nb, dtype=torch.uint8, device=dev) if 0 < nb <= SAVE_STATES_MAX_BYTES else None
+            o, g = fastmax_fwd_raw(dq_, dk_, dv_, causal, 1.0 / c, p, saved=saved)
+            gq, gk, gv = fastmax_bwd_raw(dq_, dk_, dv_, o, g, ddo, causal, 1.0 / c, p, saved=saved)
             ev_cmp[i].record(s_cmp)
         with torch.cuda.stream(s_out):
             s_out.wait_event(ev_cmp[i])
             for dst, src in zip(out, (o, gq, gk, gv)):
                 dst[b0:b1].copy_(src, non_blocking=True)
-        keep.append((dq_, dk_, dv_, ddo, o, g, gq, gk, gv))   # keep alive until the streams drain
+        keep.append((dq_, dk_, dv_, ddo, o, g, gq, gk, gv, saved))   # keep alive until the streams drain
     s_out.synchronize()
     s_cmp.synchronize()
     return out

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define FASTMAX_B200_ABI_VERSION 1
+#define FASTMAX_B200_ABI_VERSION 2
 
 /* error codes */
 #define FASTMAX_OK              0
@@ -69,6 +69,8 @@ typedef struct fastmax_plan {
   uint64_t bwd_workspace_bytes;
   double fwd_tensor_flops; /* MMA flops the plan executes (not the algorithmic count)  */
   double bwd_tensor_flops;
+  double rebuild_tensor_flops; /* part of bwd_tensor_flops that fastmax_bwd_ex skips when the
+                                  forward states were kept (fastmax_fwd_ex saved_states)       */
 } fastmax_plan;
 
 int         fastmax_abi_version(void);
@@ -98,6 +100,22 @@ int fastmax_bwd(const void* q, const void* k, const void* v, const void* o, cons
 /* number of kernel launches the last fastmax_fwd / fastmax_bwd call of this thread issued
  * (bench.py reports it as gpu_launches) */
 int fastmax_last_launch_count(void);
+
+/* ---- keeping the forward moment states for backward (speed / memory knob, no reference counterpart) ----
+ * By default fastmax_bwd rebuilds the forward-direction boundary states from k, v (nothing but
+ * q,k,v,o,g is saved, like the reference: fastmax.py:106).  A caller that can spare
+ * fastmax_saved_state_bytes() of memory per call (545 KiB per (b,h) per segment) passes the same buffer
+ * to fastmax_fwd_ex and fastmax_bwd_ex and saves one build pass (~14 % of a fwd+bwd step at the
+ * headline shape).  saved_states == NULL makes the _ex entry points identical to fastmax_fwd / _bwd.
+ * fastmax_saved_state_bytes returns 0 when the plan does not use moment states. */
+size_t fastmax_saved_state_bytes(int B, int H, int N, int D, int p, int causal, int dtype, int algo);
+int fastmax_fwd_ex(const void* q, const void* k, const void* v, void* o, float* g, void* saved_states,
+                   int B, int H, int N, int D, int p, int causal, float inv_c, int dtype, int algo,
+                   void* workspace, size_t workspace_bytes, void* stream);
+int fastmax_bwd_ex(const void* q, const void* k, const void* v, const void* o, const float* g,
+                   const void* d_o, void* dq, void* dk, void* dv, const void* saved_states,
+                   int B, int H, int N, int D, int p, int causal, float inv_c, int dtype, int algo,
+                   void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- sequence parallelism (no reference counterpart; BASELINE.json north_star) ----------
  * A long sequence is split by contiguous token ranges over the GPUs of one box.  Outputs are linear

@@ -1,16 +1,20 @@
+"""Developer probe (GPU box): cycles per tcgen05.mma issued by one thread with constant-bank operands.
+mode 0: A in tensor memory, N=64; 1: A in shared memory, N=64; 2: A in smem, N=128; 3: A in tmem, N=128."""
 import sys, os, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from fastmax_experiments_b200 import _lib
 lib = _lib.load()
 lib.fastmax_selftest_mmarate_const.restype = ctypes.c_int
-lib.fastmax_selftest_mmarate_const.argtypes = [ctypes.c_int, ctypes.c_uint, ctypes.c_void_p, ctypes.c_void_p]
+lib.fastmax_selftest_mmarate_const.argtypes = [ctypes.c_int, ctypes.c_uint, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
 out = torch.zeros(4, dtype=torch.int64, device="cuda")
 reps = 4096
-base = 0
-for trial in range(3):
-    _lib.check(lib.fastmax_selftest_mmarate_const(reps, base, out.data_ptr(), None), "mmarate_const")
-    torch.cuda.synchronize()
-    o = out.tolist()
-    print(f"smem_base passed {base}, actual {o[2]}, tmem base {o[3]}: issue {o[0]/reps:.1f} cyc/mma, total {o[1]/reps:.1f} cyc/mma")
-    base = o[2]
+base = 1024
+for mode in range(4):
+    for trial in range(2):
+        _lib.check(lib.fastmax_selftest_mmarate_const(reps, base, out.data_ptr(), None, mode), "mmarate_const")
+        torch.cuda.synchronize()
+        o = out.tolist()
+        print(f"mode {mode}: smem_base passed {base}, actual {o[2]}, tmem base {o[3]}: issue {o[0]/reps:.1f} cyc/mma, "
+              f"total {o[1]/reps:.1f} cyc/mma")
+        base = o[2]

@@ -1,0 +1,46 @@
+"""Developer helper (GPU box): in-kernel cycle counters of a -DFM_TIMING build.
+
+    FASTMAX_NVCC_EXTRA=-DFM_TIMING python -m fastmax_experiments_b200.build   # here
+    gpurun -- python tools/timing.py [B H N]
+"""
+import ctypes as C, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from fastmax_experiments_b200 import _lib
+from fastmax_experiments_b200.fastmax import fastmax_fwd_raw, fastmax_bwd_raw
+
+B, H, N = (int(x) for x in (sys.argv[1:4] if len(sys.argv) > 3 else (8, 32, 16384)))
+lib = _lib.load()
+gen = torch.Generator(device="cuda").manual_seed(0)
+q, k, v, do = (torch.randn(B, H, N, 64, device="cuda", generator=gen).to(torch.bfloat16) for _ in range(4))
+tab = (C.c_ulonglong * 64)()
+
+
+def fetch(name, reset=1):
+    f = getattr(lib, "fastmax_debug_timing_fetch_" + name, None)
+    if f is None:
+        return None
+    f.argtypes = [C.POINTER(C.c_ulonglong), C.c_int]
+    f(tab, reset)
+    return list(tab)
+
+
+for _ in range(2):
+    o, g = fastmax_fwd_raw(q, k, v, True, 1.0 / 64, 2, _lib.ALGO_MOMENTS)
+fetch("moments"); fetch("intra")
+o, g = fastmax_fwd_raw(q, k, v, True, 1.0 / 64, 2, _lib.ALGO_MOMENTS)
+for name in ("moments", "intra"):
+    t = fetch(name)
+    if t is None:
+        continue
+    n = max(t[0], 1)
+    print(name, "fwd: ctas", t[0], " per-CTA avg cycles by slot:")
+    print("  ", {i: round(x / n) for i, x in enumerate(t) if x and i})
+if "--bwd" in sys.argv:
+    fastmax_bwd_raw(q, k, v, o, g, do, True, 1.0 / 64, 2, _lib.ALGO_MOMENTS)
+    for name in ("moments", "intra"):
+        t = fetch(name)
+        if t is None:
+            continue
+        n = max(t[0], 1)
+        print(name, "bwd: ctas", t[0], {i: round(x / n) for i, x in enumerate(t) if x and i})
