@@ -79,7 +79,8 @@ struct BuildParams {
 // block; warp 20 is the TMA producer; warps 21..24 write the bf16 snapshots at segment boundaries.
 constexpr int B_STAGES = 4;
 constexpr int B_STAGE_BYTES = 3 * 8192;
-constexpr int B_SMEM = B_STAGES * B_STAGE_BYTES + 1024 /*barriers*/ + 1024 /*align slack*/;
+constexpr int B_SNAP_BYTES = 8 * SLAB_BYTES;             // bf16 staging of the CTA's eight slabs at a boundary
+constexpr int B_SMEM = B_STAGES * B_STAGE_BYTES + B_SNAP_BYTES + 1024 /*barriers*/ + 1024 /*align slack*/;
 constexpr int B_ACOL = 256;
 constexpr int B_CTAS_P2 = 9;
 constexpr int B_THREADS = 25 * 32;
@@ -111,15 +112,16 @@ __device__ __forceinline__ void lds128(uint32_t saddr, uint32_t* r) {
 
 __global__ void __launch_bounds__(B_THREADS, 1)
 build_kernel(const __grid_constant__ CUtensorMap tmXT, const __grid_constant__ CUtensorMap tmW,
-             const __grid_constant__ CUtensorMap tmW2, const BuildParams P) {
+             const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmS, const BuildParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B_STAGES * B_STAGE_BYTES);
+  uint8_t* snap = smem + B_STAGES * B_STAGE_BYTES;   // [8 slabs][8 KiB], 128B-swizzled rows (TMA store source)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(snap + B_SNAP_BYTES);
   uint64_t* full = bars;                 // [4] block operands landed (TMA)
   uint64_t* done = bars + 4;             // [4] every MMA of the block in this ring slot complete (count ntile)
   uint64_t* a_ready = bars + 8;          // [4 tiles][2] A buffer written by the 4 warps of the group (count 4)
-  uint64_t* acc_full = bars + 16;        // [4 tiles] accumulator final for this segment boundary
-  uint64_t* acc_free = bars + 20;        // [4 tiles] snapshot writers have read it (count 128)
+  uint64_t* acc_full = bars + 16;        // accumulators final for this segment boundary (count 4: one commit per issuer)
+  uint64_t* acc_free = bars + 20;        // ... and read out by the four snapshot warps (count 4)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -135,11 +137,12 @@ build_kernel(const __grid_constant__ CUtensorMap tmXT, const __grid_constant__ C
   if (tid == 0) {
     for (int i = 0; i < B_STAGES; ++i) mbar_init(&full[i], 1), mbar_init(&done[i], 4);
     for (int i = 0; i < 8; ++i) mbar_init(&a_ready[i], 4);
-    for (int i = 0; i < 4; ++i) mbar_init(&acc_full[i], 4), mbar_init(&acc_free[i], 128);
+    mbar_init(acc_full, 4), mbar_init(acc_free, 4);
     fence_barrier_init();
     tma_prefetch_desc(&tmXT);
     tma_prefetch_desc(&tmW);
     tma_prefetch_desc(&tmW2);
+    tma_prefetch_desc(&tmS);
   }
   tc_fence_before();
   __syncthreads();
@@ -254,7 +257,7 @@ build_kernel(const __grid_constant__ CUtensorMap tmXT, const __grid_constant__ C
     // issuer kk: k-step kk of every tile, as soon as generator group kk has written it
     const int kk = warp - 16;
     constexpr uint32_t IDESC = make_idesc_bf16(128, 64, false, true);
-    constexpr uint32_t BAR0 = FM_SMEM_BASE + B_STAGES * B_STAGE_BYTES;   // shared address of bars[0]
+    constexpr uint32_t BAR0 = FM_SMEM_BASE + B_STAGES * B_STAGE_BYTES + B_SNAP_BYTES;   // shared address of bars[0]
     BoundaryIter bi(P);
     int snaps = 0;
     bool pending = false;
@@ -266,8 +269,7 @@ build_kernel(const __grid_constant__ CUtensorMap tmXT, const __grid_constant__ C
         if (it < P.nproc) {
           const bool bnd = bi.step(it);
           if (lane == 0) {
-            if (pending)
-              for (int t = 0; t < ntile; ++t) mbar_wait(&acc_free[t], (snaps - 1) & 1);
+            if (pending) mbar_wait(acc_free, (snaps - 1) & 1);
             // group kk read the block's tiles itself, so their TMA has landed
             mbar_wait(&a_ready[kk * 2 + (j & 1)], (it >> 1) & 1);
           }
@@ -286,8 +288,7 @@ build_kernel(const __grid_constant__ CUtensorMap tmXT, const __grid_constant__ C
             if (kk == 0) { FM_BUILD_ISSUE(0) } else if (kk == 1) { FM_BUILD_ISSUE(1) }
             else if (kk == 2) { FM_BUILD_ISSUE(2) } else { FM_BUILD_ISSUE(3) }
             umma_commit_addr(BAR0 + 8 * (4 + j));   // done[j]
-            if (bnd)
-              for (int t = 0; t < ntile; ++t) umma_commit(&acc_full[t]);
+            if (bnd) umma_commit(acc_full);
           }
           __syncwarp();
           if (bnd) ++snaps;
@@ -311,33 +312,71 @@ build_kernel(const __grid_constant__ CUtensorMap tmXT, const __grid_constant__ C
     }
   } else {
     // ------------------------------------------------------------------ snapshot writers (warps 21..24)
+    // The scan stalls while the accumulators are read, so the read-out is kept short: tcgen05.ld ->
+    // bf16 -> shared memory (swizzled rows), release the accumulators, and only then let one thread
+    // send the eight slabs to the record with bulk tensor stores.  (Storing from registers, 16 bytes
+    // per lane at a 128-byte stride, held the accumulators for ~4.8k cycles per boundary.)
     const int q = warp & 3;
     const int row = 32 * q + lane;
     const int xsel = row >> 6, y = row & 63;
     const uint32_t lane_addr = tmem + ((uint32_t)(32 * q) << 16);
+    const bool storer = warp == 21 && lane == 0;
     BoundaryIter bi(P);
     int kq = 0;
     for (int it = 0; it < P.nproc; ++it) {
       if (!bi.step(it)) continue;
       const int b = P.reverse ? P.nblk - 1 - it : it;
       const int seg = !P.causal ? 0 : (P.reverse ? b / P.Lb - 1 : (b + 1) / P.Lb);
-      uint8_t* rec = P.state + (size_t)(P.causal ? bh * P.nseg + seg : bh) * REC_BYTES;
-      for (int g = 0; g < ntile; ++g) {
-        mbar_wait(&acc_full[g], kq & 1);
-        tc_fence_after();
-        const int nacc = special ? 2 : 1;
-        for (int a2 = 0; a2 < nacc; ++a2) {
-          const int slab = special ? 64 + a2 : 8 * cx + 2 * g + xsel;
+      const int rec_idx = P.causal ? bh * P.nseg + seg : bh;
+      uint8_t* rec = P.state + (size_t)rec_idx * REC_BYTES;
+      if (storer) bulk_wait_group_read0();          // previous boundary's stores have left the staging tiles
+      mbar_wait(acc_full, kq & 1);
+      tc_fence_after();
+      if (!special) {
+        named_barrier_sync(1, 128);
+#pragma unroll 1
+        for (int g = 0; g < 4; ++g) {
+          uint32_t v0[32], v1[32];
+          tmem_ld32(lane_addr + 64 * g, v0);
+          tmem_ld32(lane_addr + 64 * g + 32, v1);
+          tmem_wait_ld_dep32(v0);
+          tmem_wait_ld_dep32(v1);
+          const uint32_t dst = smem_u32(snap) + (uint32_t)(2 * g + xsel) * SLAB_BYTES + (uint32_t)y * 128;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint32_t* v = c < 4 ? v0 + 8 * c : v1 + 8 * (c - 4);
+            sts128(dst + ((uint32_t)(c ^ (y & 7)) << 4),
+                   pack_bf16x2(__uint_as_float(v[0]), __uint_as_float(v[1])),
+                   pack_bf16x2(__uint_as_float(v[2]), __uint_as_float(v[3])),
+                   pack_bf16x2(__uint_as_float(v[4]), __uint_as_float(v[5])),
+                   pack_bf16x2(__uint_as_float(v[6]), __uint_as_float(v[7])));
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_free);
+        fence_proxy_async();
+        named_barrier_sync(1, 128);
+        if (storer) {
+#pragma unroll 1
+          for (int sl = 0; sl < 8; ++sl) tma_store_3d(&tmS, snap + sl * SLAB_BYTES, 0, (8 * cx + sl) * 64, rec_idx);
+          bulk_commit_group();
+        }
+      } else {
+        // special tile (S1 | normaliser matrix, row 64: S0 | normaliser vector): 1/33 of the state, stored directly
+        for (int a2 = 0; a2 < 2; ++a2) {
+          const int slab = 64 + a2;
 #pragma unroll 1
           for (int h = 0; h < 2; ++h) {
             uint32_t v[32];
-            tmem_ld32(lane_addr + 64 * (g + a2) + 32 * h, v);
-            tmem_wait_ld();
-            if (a2 == nacc - 1 && h == 1) {
+            tmem_ld32(lane_addr + 64 * a2 + 32 * h, v);
+            tmem_wait_ld_dep32(v);
+            if (a2 == 1 && h == 1) {
               tc_fence_before();
-              mbar_arrive(&acc_free[g]);
+              __syncwarp();
+              if (lane == 0) mbar_arrive(acc_free);
             }
-            if (!special || row < 64) {
+            if (row < 64) {
               uint4* dst = reinterpret_cast<uint4*>(rec + (size_t)slab * SLAB_BYTES + (size_t)y * 128 + 64 * h);
 #pragma unroll
               for (int c8 = 0; c8 < 4; ++c8) {
@@ -363,6 +402,7 @@ build_kernel(const __grid_constant__ CUtensorMap tmXT, const __grid_constant__ C
       }
       ++kq;
     }
+    if (storer) bulk_wait_group0();                 // shared memory must outlive the bulk stores
   }
   tc_fence_before();
   __syncthreads();
@@ -735,8 +775,9 @@ static int launch_transpose(const Problem& pb, const void* in, void* out, int Np
 
 static int launch_build(const Problem& pb, const MomLayout& m, const void* xt, const void* w, const void* w2,
                         uint8_t* state, int reverse, const void* init = nullptr) {
-  CUtensorMap tmXT, tmW, tmW2;
+  CUtensorMap tmXT, tmW, tmW2, tmS;
   int rc;
+  if ((rc = make_tmap_bf16_3d(&tmS, state, 64, NSLAB * 64, (uint64_t)m.BH * m.nrec, 128, REC_BYTES, 64, 64))) return rc;
   if ((rc = make_tmap_bf16_3d(&tmXT, xt, 64, m.Npad, m.BH, 128, (uint64_t)m.Npad * 128, 64, 64))) return rc;
   if ((rc = make_tmap_bf16_3d(&tmW, w, 64, m.N, m.BH, 128, (uint64_t)m.N * 128, 64, 64))) return rc;
   if ((rc = make_tmap_bf16_3d(&tmW2, w2, 64, m.N, m.BH, 128, (uint64_t)m.N * 128, 64, 64))) return rc;
@@ -763,7 +804,7 @@ static int launch_build(const Problem& pb, const MomLayout& m, const void* xt, c
   FM_CUDA(cudaFuncSetAttribute(build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
   dim3 grid(pb.p == 2 ? B_CTAS_P2 : 1, m.BH);
   FM_LAUNCH(reverse ? "mom_build_rev" : "mom_build", pb.stream,
-            build_kernel<<<grid, B_THREADS, B_SMEM, pb.stream>>>(tmXT, tmW, tmW2, P));
+            build_kernel<<<grid, B_THREADS, B_SMEM, pb.stream>>>(tmXT, tmW, tmW2, tmS, P));
   return FASTMAX_OK;
 }
 

@@ -252,7 +252,11 @@ __global__ void __launch_bounds__(128, 1) mmarate_const_kernel(const __grid_cons
           if (MODE == 0) umma_ts(kk * 64, 448 + kk * 8, cd.b[kk], cd.idesc, 1);
           else if (MODE == 1) umma_ss(kk * 64, cd.a[kk], cd.b[kk], cd.idesc, 1);
           else if (MODE == 2) umma_ss((kk & 1) * 128, cd.a[kk], cd.b[kk], cd.idesc, 1);
-          else umma_ts((kk & 1) * 128, 448 + kk * 8, cd.b[kk], cd.idesc, 1);
+          else if (MODE == 3) umma_ts((kk & 1) * 128, 448 + kk * 8, cd.b[kk], cd.idesc, 1);
+          else if (MODE == 5) umma_ss(0, cd.a[kk], cd.b[kk], cd.idesc, 1);           // SS N=128, one accumulator
+          else if (MODE == 6) umma_ts(0, 448 + kk * 8, cd.b[kk], cd.idesc, 1);       // TS N=64, one accumulator
+          else if (MODE == 7) umma_ss(0, cd.a[kk], cd.b[kk], cd.idesc, 1);           // SS N=64, one accumulator
+          else if (MODE == 8) umma_ts(0, 448 + kk * 8, cd.b[kk], cd.idesc, 1);       // TS N=128, one accumulator
         }
       }
       __syncwarp();
@@ -277,7 +281,7 @@ extern "C" int fastmax_selftest_mmarate_const(int reps, unsigned int smem_base, 
                                               int mode) {
   using namespace fm;
   ConstDescs cd;
-  const int n = (mode == 2 || mode == 3) ? 128 : 64;
+  const int n = (mode == 2 || mode == 3 || mode == 5 || mode == 8) ? 128 : 64;
   for (int kk = 0; kk < 4; ++kk) {
     cd.a[kk] = sm100::desc_kmajor_sw128_const(smem_base) + kk * 2;                      // 128x64 K-major tile
     cd.b[kk] = sm100::desc_mnmajor_sw128_const(smem_base + 16384, 8192) + kk * 128;     // 64xN MN-major tile(s)
@@ -292,7 +296,7 @@ extern "C" int fastmax_selftest_mmarate_const(int reps, unsigned int smem_base, 
     FM_LAUNCH("selftest_mmarate_const", st, mmarate_const_kernel<M><<<1, 128, smem, st>>>(cd, reps, out_dev));   \
     break;
   switch (mode) {
-    FM_MRC(0) FM_MRC(1) FM_MRC(2) FM_MRC(3)
+    FM_MRC(0) FM_MRC(1) FM_MRC(2) FM_MRC(3) FM_MRC(5) FM_MRC(6) FM_MRC(7) FM_MRC(8)
     default: return FASTMAX_ERR_BAD_ARG;
   }
 #undef FM_MRC
@@ -415,3 +419,204 @@ extern "C" int fastmax_selftest_ldrate(int width, int inflight, int iters, int t
   return FASTMAX_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Contention probe (developer tool): one converged warp issues tcgen05.mma back to back while
+// `ldwarps` other warps stream tcgen05.ld (kind 0) or tcgen05.st (kind 1) from/to other columns of
+// tensor memory.  out[0] = cycles of the MMA loop, out[1] = MMAs, out[2+2w] = cycles of warp w's
+// loop, out[3+2w] = 16-column chunks it moved.
+// MODE as in mmarate_const: 0 TS N=64, 1 SS N=64, 2 SS N=128, 3 TS N=128, 4 = no MMAs (spin).
+// ---------------------------------------------------------------------------------------------
+namespace fm {
+namespace {
+template <int MODE>
+__global__ void __launch_bounds__(17 * 32, 1) contention_kernel(const __grid_constant__ ConstDescs cd, int reps,
+                                                                 int ldwarps, int kind, unsigned long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  __shared__ volatile int done;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 65536 / 4; i += 17 * 32) reinterpret_cast<uint32_t*>(smem_raw)[i] = 0x3C003C00u;
+  if (warp == 16) {
+    tmem_alloc(&slot, 512);
+    tmem_relinquish();
+  }
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_barrier_init();
+    done = 0;
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 16) {
+    long long t0 = clock64();
+    while (clock64() - t0 < 20000) {}
+    t0 = clock64();
+    if (MODE < 4) {
+#pragma unroll 1
+      for (int r = 0; r < reps; r += 4) {
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            if (MODE == 0) umma_ts(kk * 64, 448 + kk * 8, cd.b[kk], cd.idesc, 1);
+            else if (MODE == 1) umma_ss(kk * 64, cd.a[kk], cd.b[kk], cd.idesc, 1);
+            else if (MODE == 2) umma_ss((kk & 1) * 128, cd.a[kk], cd.b[kk], cd.idesc, 1);
+            else umma_ts((kk & 1) * 128, 448 + kk * 8, cd.b[kk], cd.idesc, 1);
+          }
+        }
+        __syncwarp();
+      }
+      if (lane == 0) {
+        umma_commit(&bar);
+        mbar_wait(&bar, 0);
+      }
+    } else {
+      while (clock64() - t0 < (long long)reps * 64) {}
+    }
+    __syncwarp();
+    if (lane == 0) {
+      out[0] = (unsigned long long)(clock64() - t0);
+      out[1] = (unsigned long long)reps;
+      done = 1;
+    }
+  } else if (warp < ldwarps) {
+    const uint32_t tmem = slot + ((uint32_t)(32 * (warp & 3)) << 16) + 256;
+    uint32_t acc = 0, chunks = 0;
+    uint32_t v[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) v[c] = tid + c;
+    const long long t0 = clock64();
+    while (!done) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (kind == 0) {
+          tmem_ld16(tmem + 16 * j + 128 * ((warp >> 2) & 1), v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int c = 0; c < 16; ++c) acc ^= v[c];
+        } else {
+          tmem_st16(tmem + 16 * j + 128 * ((warp >> 2) & 1), v);
+          tmem_wait_st();
+        }
+      }
+      chunks += 8;
+    }
+    const long long t1 = clock64();
+    if (lane == 0) {
+      out[2 + 2 * warp] = (unsigned long long)(t1 - t0);
+      out[3 + 2 * warp] = chunks + (acc == 0x12345u ? 1 : 0);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 16) tmem_dealloc(slot, 512);
+}
+}  // namespace
+}  // namespace fm
+
+extern "C" int fastmax_selftest_contention(int mode, int reps, int ldwarps, int kind, unsigned int smem_base,
+                                           unsigned long long* out_dev, void* stream) {
+  using namespace fm;
+  ConstDescs cd;
+  const int n = (mode == 2 || mode == 3) ? 128 : 64;
+  for (int kk = 0; kk < 4; ++kk) {
+    cd.a[kk] = sm100::desc_kmajor_sw128_const(smem_base) + kk * 2;
+    cd.b[kk] = sm100::desc_mnmajor_sw128_const(smem_base + 16384, 8192) + kk * 128;
+  }
+  cd.idesc = sm100::make_idesc_bf16(128, n, false, true);
+  cd.smem_base_expected = smem_base;
+  const int smem = 65536 + 1024;
+  cudaStream_t st = (cudaStream_t)stream;
+#define FM_CT(M)                                                                                          \
+  case M:                                                                                                 \
+    FM_CUDA(cudaFuncSetAttribute(contention_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+    FM_LAUNCH("selftest_contention", st,                                                                  \
+              contention_kernel<M><<<1, 17 * 32, smem, st>>>(cd, reps, ldwarps, kind, out_dev));           \
+    break;
+  switch (mode) {
+    FM_CT(0) FM_CT(1) FM_CT(2) FM_CT(3) FM_CT(4)
+    default: return FASTMAX_ERR_BAD_ARG;
+  }
+#undef FM_CT
+  return FASTMAX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Multi-issuer probe (developer tool): `nissue` converged warps each issue groups of four TS N=64
+// MMAs (issuer w: k-step w of four accumulators, like the build kernel) followed by one
+// tcgen05.commit, back to back, no waits.  out[w] = cycles of issuer w's loop; `blocks` groups each.
+// ---------------------------------------------------------------------------------------------
+namespace fm {
+namespace {
+__global__ void __launch_bounds__(20 * 32, 1) multi_issue_kernel(const __grid_constant__ ConstDescs cd, int blocks,
+                                                                  int nissue, int commits, unsigned long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bar[4];
+  __shared__ uint32_t slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 65536 / 4; i += 20 * 32) reinterpret_cast<uint32_t*>(smem_raw)[i] = 0x3C003C00u;
+  if (warp == 0) {
+    tmem_alloc(&slot, 512);
+    tmem_relinquish();
+  }
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(&bar[i], nissue);
+    fence_barrier_init();
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp >= 16 && warp < 16 + nissue) {
+    const int kk = warp - 16;
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int b = 0; b < blocks; b += 4) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (elect_one()) {
+#define FM_MI(KK)                                                                   \
+  _Pragma("unroll") for (int t = 0; t < 4; ++t)                                     \
+      umma_ts(64 * t, 256 + 64 * t + 32 * (j & 1) + 8 * KK, cd.b[KK], cd.idesc, 1);
+          if (kk == 0) { FM_MI(0) } else if (kk == 1) { FM_MI(1) } else if (kk == 2) { FM_MI(2) } else { FM_MI(3) }
+#undef FM_MI
+          for (int c = 0; c < commits; ++c) umma_commit(&bar[j]);
+        }
+        __syncwarp();
+      }
+    }
+    if (lane == 0) out[kk] = (unsigned long long)(clock64() - t0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    if (lane == 0) {   // drain before freeing tensor memory
+      umma_commit(&bar[0]);
+    }
+    long long t0 = clock64();
+    while (clock64() - t0 < 200000) {}
+    tmem_dealloc(slot, 512);
+  }
+}
+}  // namespace
+}  // namespace fm
+
+extern "C" int fastmax_selftest_multi_issue(int blocks, int nissue, int commits, unsigned int smem_base,
+                                            unsigned long long* out_dev, void* stream) {
+  using namespace fm;
+  ConstDescs cd;
+  for (int kk = 0; kk < 4; ++kk) {
+    cd.a[kk] = sm100::desc_kmajor_sw128_const(smem_base) + kk * 2;
+    cd.b[kk] = sm100::desc_mnmajor_sw128_const(smem_base + 16384, 8192) + kk * 128;
+  }
+  cd.idesc = sm100::make_idesc_bf16(128, 64, false, true);
+  cd.smem_base_expected = smem_base;
+  const int smem = 65536 + 1024;
+  cudaStream_t st = (cudaStream_t)stream;
+  FM_CUDA(cudaFuncSetAttribute(multi_issue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  FM_LAUNCH("selftest_multi_issue", st, multi_issue_kernel<<<1, 20 * 32, smem, st>>>(cd, blocks, nissue, commits, out_dev));
+  return FASTMAX_OK;
+}

@@ -35,7 +35,10 @@ for name in ("moments", "intra"):
         continue
     n = max(t[0], 1)
     print(name, "fwd: ctas", t[0], " per-CTA avg cycles by slot:")
-    print("  ", {i: round(x / n) for i, x in enumerate(t) if x and i})
+    print("  ", {i: round(x / n) for i, x in enumerate(t) if x and 0 < i < 16})
+    if t[16]:
+        nb = t[16]
+        print("   build (per snapshot of cx=0 CTAs):", nb, {i: round(x / nb) for i, x in enumerate(t) if x and i > 16})
 if "--bwd" in sys.argv:
     fastmax_bwd_raw(q, k, v, o, g, do, True, 1.0 / 64, 2, _lib.ALGO_MOMENTS)
     for name in ("moments", "intra"):
