@@ -133,7 +133,8 @@ template <int MODE>
 __global__ void __launch_bounds__(384, 1)
 intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ CUtensorMap tmR2,
              const __grid_constant__ CUtensorMap tmT1, const __grid_constant__ CUtensorMap tmT2,
-             const __grid_constant__ CUtensorMap tmS, const __grid_constant__ IntraDescs DS, const IntraParams P) {
+             const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmO0,
+             const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ IntraDescs DS, const IntraParams P) {
   using C = IntraCfg<MODE>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -178,6 +179,7 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
     tma_prefetch_desc(&tmR1);
     tma_prefetch_desc(&tmT1);
     tma_prefetch_desc(&tmT2);
+    tma_prefetch_desc(&tmO0);
   }
   tc_fence_before();
   __syncthreads();
@@ -381,20 +383,31 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
     mbar_wait(&acc_done[w], 0);
     tc_fence_after();
     // ---------------------------------------------------------------- epilogue: fp32 partials
+    // Written through shared memory with bulk tensor stores: a thread owns a 256-byte output row, so
+    // storing from registers means 16-byte pieces at a 256-byte stride (measured: a third of the CTA's
+    // time).  Once both warpgroups' MMAs are complete the stream ring is free; each warpgroup stages one
+    // 128x64 fp32 tile there (two 128-byte-swizzled halves of 32 columns) and one thread sends it.
+    asm volatile("bar.sync 3, 256;" ::: "memory");
+    uint8_t* stg = ring + w * 32768;
+    const bool storer = q == 0 && lane == 0;
+    int nstored = 0;
 #pragma unroll
     for (int x = 0; x < 2; ++x) {
       if (x >= n_ot) break;
       const int o = otile[x];
       const int r_abs = c0 + o * 128 + rloc;
-      const bool tile_live = c0 + o * 128 < P.N;          // warp-uniform
+      const bool tile_live = c0 + o * 128 < P.N;          // uniform over the warpgroup
       if (!tile_live) continue;
       const size_t grow = (size_t)bh * P.N + r_abs;
       const int nacc = MODE == INTRA_DKDV ? 2 : 1;
       const float* vec = has_norm ? reinterpret_cast<const float*>(P.state + (size_t)rec_idx * REC_BYTES + VEC_OFF) : nullptr;
       float gmom = 0.f;   // FWD: a q.N1 + (a^2/2) q.T
       for (int a2 = 0; a2 < nacc; ++a2) {
-        float* outp = a2 == 0 ? P.out0 : P.out1;
         const uint32_t col = MODE == INTRA_DKDV ? 128 * o + 64 * a2 : 64 * o;
+        if (nstored > 0) {       // the previous tile's stores have read the staging area
+          if (storer) bulk_wait_group_read0();
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + w) : "memory");
+        }
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
           uint32_t v[32];
@@ -440,15 +453,24 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
             }
           }
           tmem_wait_ld();
-          if (r_abs < P.N) {
-            uint4* dst = reinterpret_cast<uint4*>(outp + grow * 64 + 32 * h);
+          const uint32_t dst = smem_u32(stg) + h * 16384 + rloc * 128;
 #pragma unroll
-            for (int c4 = 0; c4 < 8; ++c4) dst[c4] = make_uint4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
-          }
+          for (int c4 = 0; c4 < 8; ++c4)
+            sts128(dst + ((uint32_t)(c4 ^ (rloc & 7)) << 4), v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
         }
+        fence_proxy_async();
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + w) : "memory");
+        if (storer) {
+          const CUtensorMap* tm = a2 == 0 ? &tmO0 : &tmO1;
+          tma_store_3d(tm, stg, 0, c0 + o * 128, bh);          // rows past N are clipped by the tensor map
+          tma_store_3d(tm, stg + 16384, 32, c0 + o * 128, bh);
+          bulk_commit_group();
+        }
+        ++nstored;
       }
       if (MODE == INTRA_FWD && r_abs < P.N) P.g[grow] = gsum[x] + (has_norm ? (float)(seg * P.L) + P.count_offset + gmom : 0.f);
     }
+    if (storer) bulk_wait_group0();      // shared memory must outlive the bulk stores
   }
   tc_fence_before();
   __syncthreads();
@@ -483,6 +505,14 @@ static int launch_intra_t(const Problem& pb, int L, int Npad, const void* r1, co
     int rc = make_tmap_bf16_3d(&tmS, state, 64, NSLAB * 64, (uint64_t)BH * P.nseg, 128, REC_BYTES, 64, 64);
     if (rc) return rc;
   }
+  CUtensorMap tmO0, tmO1;
+  {
+    int rc = make_tmap_f32_3d(&tmO0, out0, 64, pb.N, BH, 256, (uint64_t)pb.N * 256, 32, 128);
+    if (rc) return rc;
+    tmO1 = tmO0;
+    if (out1 && (rc = make_tmap_f32_3d(&tmO1, out1, 64, pb.N, BH, 256, (uint64_t)pb.N * 256, 32, 128))) return rc;
+  }
+  static_assert(C::STAGES * C::STAGE_STRIDE >= 2 * 32768, "the epilogue stages one fp32 tile per warpgroup in the ring");
   auto kern = intra_kernel<MODE>;
   FM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
   constexpr int CT = C::OUT_TILES * 128;
@@ -502,7 +532,7 @@ static int launch_intra_t(const Problem& pb, int L, int Npad, const void* r1, co
     for (int kk = 0; kk < 4; ++kk)
       DS.normK[kk] = sm100::desc_kmajor_sw128_const(base + C::RES_BYTES + C::STAGES * C::STAGE_STRIDE) + kk * 2;
   }
-  FM_LAUNCH(name, pb.stream, kern<<<grid, 384, C::SMEM, pb.stream>>>(m[0], m[1], m[2], m[3], tmS, DS, P));
+  FM_LAUNCH(name, pb.stream, kern<<<grid, 384, C::SMEM, pb.stream>>>(m[0], m[1], m[2], m[3], tmS, tmO0, tmO1, DS, P));
   return FASTMAX_OK;
 }
 

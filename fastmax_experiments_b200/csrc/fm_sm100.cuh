@@ -340,5 +340,9 @@ __device__ __forceinline__ uint32_t bcast_bf16(uint32_t x, int sel) {
 int make_tmap_bf16_3d(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint64_t batch,
                       uint64_t row_stride_bytes, uint64_t batch_stride_bytes, uint32_t box_cols,
                       uint32_t box_rows);
+// same for an fp32 tensor (box_cols * 4 bytes <= 128: one swizzle row)
+int make_tmap_f32_3d(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint64_t batch,
+                      uint64_t row_stride_bytes, uint64_t batch_stride_bytes, uint32_t box_cols,
+                      uint32_t box_rows);
 
 }  // namespace fm

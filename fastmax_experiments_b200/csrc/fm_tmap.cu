@@ -21,9 +21,27 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
+static int make_tmap_3d(CUtensorMap* map, CUtensorMapDataType dt, const void* base, uint64_t cols, uint64_t rows,
+                        uint64_t batch, uint64_t row_stride_bytes, uint64_t batch_stride_bytes, uint32_t box_cols,
+                        uint32_t box_rows);
+
 int make_tmap_bf16_3d(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint64_t batch,
                       uint64_t row_stride_bytes, uint64_t batch_stride_bytes, uint32_t box_cols,
                       uint32_t box_rows) {
+  return make_tmap_3d(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, cols, rows, batch, row_stride_bytes,
+                      batch_stride_bytes, box_cols, box_rows);
+}
+
+int make_tmap_f32_3d(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint64_t batch,
+                     uint64_t row_stride_bytes, uint64_t batch_stride_bytes, uint32_t box_cols,
+                     uint32_t box_rows) {
+  return make_tmap_3d(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, cols, rows, batch, row_stride_bytes,
+                      batch_stride_bytes, box_cols, box_rows);
+}
+
+static int make_tmap_3d(CUtensorMap* map, CUtensorMapDataType dt, const void* base, uint64_t cols, uint64_t rows,
+                        uint64_t batch, uint64_t row_stride_bytes, uint64_t batch_stride_bytes, uint32_t box_cols,
+                        uint32_t box_rows) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     snprintf(status().cuda_err, sizeof(status().cuda_err), "cuTensorMapEncodeTiled entry point not found");
@@ -33,7 +51,7 @@ int make_tmap_bf16_3d(CUtensorMap* map, const void* base, uint64_t cols, uint64_
   cuuint64_t strides[2] = {row_stride_bytes, batch_stride_bytes};
   cuuint32_t box[3] = {box_cols, box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = fn(map, dt, 3, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {

@@ -29,9 +29,23 @@ for _ in range(2):
     o, g = fastmax_fwd_raw(q, k, v, True, 1.0 / 64, 2, _lib.ALGO_MOMENTS)
 fetch("moments"); fetch("intra")
 o, g = fastmax_fwd_raw(q, k, v, True, 1.0 / 64, 2, _lib.ALGO_MOMENTS)
+def show_intra(t):
+    for mode, nm in enumerate(("fwd", "dq", "dkdv")):
+        c = t[8 * mode]
+        if not c:
+            continue
+        v = [round(t[8 * mode + i] / c) for i in range(1, 8)]
+        print(f"   intra {nm}: ctas {c}; WG0 warp: setup {v[0]}, operands landed {v[1]}, item loop end {v[2]} "
+              f"(wait scores {v[3]}, wait warpgroup barrier {v[4]}, items {v[6]}), accumulators final {v[5]}, "
+              f"CTA end {round(t[24 + mode] / c)}")
+
+
 for name in ("moments", "intra"):
     t = fetch(name)
     if t is None:
+        continue
+    if name == "intra":
+        show_intra(t)
         continue
     n = max(t[0], 1)
     print(name, "fwd: ctas", t[0], " per-CTA avg cycles by slot:")
@@ -44,6 +58,9 @@ if "--bwd" in sys.argv:
     for name in ("moments", "intra"):
         t = fetch(name)
         if t is None:
+            continue
+        if name == "intra":
+            show_intra(t)
             continue
         n = max(t[0], 1)
         print(name, "bwd: ctas", t[0], {i: round(x / n) for i, x in enumerate(t) if x and i})
