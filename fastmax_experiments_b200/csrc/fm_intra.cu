@@ -22,6 +22,7 @@
 #include "fm_common.cuh"
 #include "fm_sm100.cuh"
 #include "fm_moments.cuh"
+#include <type_traits>
 
 namespace fm {
 namespace mom {
@@ -241,7 +242,7 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
     if (MODE == INTRA_DKDV) otile[0] = w, otile[1] = -1, n_ot = 1;
     else otile[0] = w == 0 ? 0 : 1, otile[1] = w == 0 ? 3 : 2, n_ot = 2;
 
-    const float a = P.a, c2 = 0.5f * P.a * P.a;
+    const float a = P.a, c2 = P.p == 2 ? 0.5f * P.a * P.a : 0.f, a1 = P.p == 2 ? P.a : 0.f;
     float gsum[2] = {0.f, 0.f};
     float dlt_row[2] = {0.f, 0.f};
     if constexpr (MODE == INTRA_DQ) {
@@ -291,8 +292,9 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
         const bool diag = MODE == INTRA_DKDV ? (ts < ob + 128) : (ts + 63 > ob);   // tile needs the mask
         uint32_t pk[32];
         uint32_t pe[MODE == INTRA_DKDV ? 32 : 1];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        // two copies of the element loop: interior tiles skip the causal mask (compare + select per score)
+        auto chunk = [&](auto diag_c, int h) {
+          constexpr bool DIAG = decltype(diag_c)::value;
           uint32_t sv[32];
           tmem_ld32(sbuf + 32 * h, sv);
           uint32_t dv[MODE == INTRA_FWD ? 1 : 32];
@@ -311,34 +313,40 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
           for (int c = 0; c < 32; c += 2) {
             float r0, r1, e0 = 0.f, e1 = 0.f;
             const float s0 = __uint_as_float(sv[c]), s1 = __uint_as_float(sv[c + 1]);
-            const int col = ts + 32 * h + c;
-            bool v0 = true, v1 = true;
-            if (diag) {
-              if constexpr (MODE == INTRA_DKDV) v0 = col >= r_abs, v1 = col + 1 >= r_abs;   // query >= key
-              else v0 = col <= r_abs, v1 = col + 1 <= r_abs;                                // key <= query
-            }
+            // f(s) = 1 + a s + c2 s^2 (c2 = 0 for p = 1);  f'(s)/a = 1 + a1 s (a1 = 0 for p = 1)
             if constexpr (MODE == INTRA_FWD) {
-              r0 = P.p == 2 ? fmaf(s0, fmaf(c2, s0, a), 1.f) : fmaf(a, s0, 1.f);
-              r1 = P.p == 2 ? fmaf(s1, fmaf(c2, s1, a), 1.f) : fmaf(a, s1, 1.f);
-              r0 = v0 ? r0 : 0.f, r1 = v1 ? r1 : 0.f;
-              gsum[x] += r0 + r1;
+              r0 = fmaf(s0, fmaf(c2, s0, a), 1.f);
+              r1 = fmaf(s1, fmaf(c2, s1, a), 1.f);
             } else if constexpr (MODE == INTRA_DQ) {
               const float d0 = __uint_as_float(dv[c]) - dlt_row[x], d1 = __uint_as_float(dv[c + 1]) - dlt_row[x];
-              r0 = P.p == 2 ? fmaf(a, s0, 1.f) * d0 : d0;
-              r1 = P.p == 2 ? fmaf(a, s1, 1.f) * d1 : d1;
-              r0 = v0 ? r0 : 0.f, r1 = v1 ? r1 : 0.f;
+              r0 = fmaf(a1, s0, 1.f) * d0;
+              r1 = fmaf(a1, s1, 1.f) * d1;
             } else {
               const float d0 = __uint_as_float(dv[c]) - dl[c], d1 = __uint_as_float(dv[c + 1]) - dl[c + 1];
-              r0 = P.p == 2 ? fmaf(s0, fmaf(c2, s0, a), 1.f) : fmaf(a, s0, 1.f);
-              r1 = P.p == 2 ? fmaf(s1, fmaf(c2, s1, a), 1.f) : fmaf(a, s1, 1.f);
-              e0 = P.p == 2 ? fmaf(a, s0, 1.f) * d0 : d0;
-              e1 = P.p == 2 ? fmaf(a, s1, 1.f) * d1 : d1;
+              r0 = fmaf(s0, fmaf(c2, s0, a), 1.f);
+              r1 = fmaf(s1, fmaf(c2, s1, a), 1.f);
+              e0 = fmaf(a1, s0, 1.f) * d0;
+              e1 = fmaf(a1, s1, 1.f) * d1;
+            }
+            if constexpr (DIAG) {
+              const int col = ts + 32 * h + c;
+              bool v0, v1;
+              if constexpr (MODE == INTRA_DKDV) v0 = col >= r_abs, v1 = col + 1 >= r_abs;   // query >= key
+              else v0 = col <= r_abs, v1 = col + 1 <= r_abs;                                // key <= query
               r0 = v0 ? r0 : 0.f, r1 = v1 ? r1 : 0.f;
               e0 = v0 ? e0 : 0.f, e1 = v1 ? e1 : 0.f;
             }
+            if constexpr (MODE == INTRA_FWD) gsum[x] += r0 + r1;
             pk[16 * h + (c >> 1)] = pack_bf16x2(r0, r1);
             if constexpr (MODE == INTRA_DKDV) pe[16 * h + (c >> 1)] = pack_bf16x2(e0, e1);
           }
+        };
+        if (diag) {
+          chunk(std::true_type{}, 0);
+          chunk(std::true_type{}, 1);
+        } else {
+          chunk(std::false_type{}, 0);
+          chunk(std::false_type{}, 1);
         }
         // ---- result back to tensor memory as the A operand of the accumulating MMAs
         tmem_st32(sbuf, pk);
@@ -420,7 +428,7 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
 #pragma unroll
               for (int c = 0; c < 32; ++c)
                 v[c] = __float_as_uint(__uint_as_float(v[c]) +
-                                       fmaf(P.p == 2 ? a : 0.f, __uint_as_float(tn[c]), __ldg(vec + 64 + 32 * h + c)));
+                                       fmaf(a1, __uint_as_float(tn[c]), __ldg(vec + 64 + 32 * h + c)));
             }
           } else {
             if (has_norm) {   // CTA-uniform
@@ -432,7 +440,7 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
 #pragma unroll
                 for (int c = 0; c < 32; ++c)
                   v[c] = __float_as_uint(__uint_as_float(v[c]) -
-                                         dlt_row[x] * fmaf(P.p == 2 ? a : 0.f, __uint_as_float(tn[c]), __ldg(vec + 64 + 32 * h + c)));
+                                         dlt_row[x] * fmaf(a1, __uint_as_float(tn[c]), __ldg(vec + 64 + 32 * h + c)));
               } else {
                 // g += a q.N1 + (a^2/2) q.T  with the thread's own q row read back from the resident tile
                 const uint8_t* qrow = res + o * 16384 + rloc * 128;
@@ -444,7 +452,7 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
                   for (int j = 0; j < 4; ++j) {
                     const int c = 8 * c8 + 2 * j;
                     const float q0 = __uint_as_float(qw[j] << 16), q1 = __uint_as_float(qw[j] & 0xffff0000u);
-                    const float c2n = P.p == 2 ? c2 : 0.f;
+                    const float c2n = c2;
                     gmom += q0 * fmaf(c2n, __uint_as_float(tn[c]), a * __ldg(vec + 64 + 32 * h + c));
                     gmom += q1 * fmaf(c2n, __uint_as_float(tn[c + 1]), a * __ldg(vec + 64 + 32 * h + c + 1));
                   }
