@@ -336,8 +336,10 @@ def main() -> None:
     achieved_tf = counted / (ms_step * 1e-3) / 1e12
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("dram_bytes_per_step")
+    if os.path.exists(tpath):      # dram__bytes_read.sum + dram__bytes_write.sum of one step (ncu --set full), same config only
+        tj = json.load(open(tpath))
+        if tj.get("config") == {"B": B, "H": H, "N": N, "kept_states": bool(keep)} and pl.algo == 2:
+            traffic = tj.get("dram_bytes_per_step")
     roofline = {
         "bound": "tensor", "achieved": round(achieved_tf, 3), "peak": peak_tf, "unit": "TFLOP/s",
         "frac": round(achieved_tf / peak_tf, 5), "traffic": traffic,

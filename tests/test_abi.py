@@ -74,3 +74,9 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def test_graft_entry_build_runs():
+    """The driver's build check: compiles (or finds up to date) the library and validates the ABI."""
+    import __graft_entry__ as g
+    g.build()
