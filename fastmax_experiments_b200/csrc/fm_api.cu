@@ -101,8 +101,9 @@ int fastmax_plan_make(fastmax_plan* plan, int B, int H, int N, int D, int p, int
     return FASTMAX_ERR_BAD_ARG;
   const bool mom_ok = dtype == FASTMAX_DTYPE_BF16 && D == 64;
   if (algo == FASTMAX_ALGO_MOMENTS && !mom_ok) return FASTMAX_ERR_UNSUPPORTED;
-  // cost model: below ~1k tokens the dense tiles are cheaper than building moment states
-  const bool use_mom = algo == FASTMAX_ALGO_MOMENTS || (algo == FASTMAX_ALGO_AUTO && mom_ok && N >= 1024);
+  // the tcgen05 path also covers short sequences (one segment = dense tensor-core tiles, no moment
+  // states); below a couple of tiles the fp32 CUDA-core kernels are as fast and exact
+  const bool use_mom = algo == FASTMAX_ALGO_MOMENTS || (algo == FASTMAX_ALGO_AUTO && mom_ok && N >= 256);
   if (use_mom) {
     plan->algo = FASTMAX_ALGO_MOMENTS;
     plan->seg_len = fm::moments_seg_len(N);

@@ -756,9 +756,15 @@ static MomLayout mom_layout(int B, int H, int N, int L, int causal, bool bwd) {
   return m;
 }
 
+// Segment length of the chunked scan.  Cost per token: intra-segment tiles ~ L, moment kernels constant
+// (and absent with a single segment).  Measured at D = 64: the moment kernels cost about as much as the
+// intra tiles of a 2048-token segment, so sequences up to 2048 tokens run as ONE segment (pure
+// tensor-core quadratic evaluation, no states); longer ones use 512-token segments, doubled only to keep
+// at most 256 boundary states (140 MB) per (b,h) and direction.
 int moments_seg_len(int N) {
+  if (N <= 2048) return (N + 511) / 512 * 512;
   int L = 512;
-  while ((long long)L * 64 < N) L *= 2;   // keep <= 64 boundary states per sequence
+  while ((long long)L * 256 < N) L *= 2;
   return L;
 }
 

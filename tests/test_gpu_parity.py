@@ -70,6 +70,8 @@ SHAPES = [
     # B, H, N, D   (ragged N, N < tile, N == tile, multi-tile, odd head sizes)
     (1, 1, 1, 64), (1, 2, 7, 32), (2, 1, 64, 64), (1, 3, 65, 64), (1, 1, 257, 128), (2, 2, 300, 32),
     (1, 2, 130, 80), (1, 1, 1024, 64),
+    # longer than 2048 tokens: several 512-token segments + moment states on the tcgen05 path (ragged tail)
+    (1, 2, 2560, 64), (2, 1, 3000, 64),
 ]
 
 
