@@ -149,6 +149,7 @@ def run_sequence_parallel(args, rank: int, world: int, local: int) -> None:
     dev = torch.device("cuda", local)
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     os.environ.setdefault("MASTER_PORT", "29511")
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries exactly one JSON line
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     lib = _lib.load()
     B, H, D, p = 1, HL["H"], HL["D"], HL["p"]
@@ -257,6 +258,7 @@ def main() -> None:
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
 
