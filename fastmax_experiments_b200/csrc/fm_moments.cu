@@ -35,24 +35,36 @@ typedef __nv_bfloat16 bf16;
 // =============================================================================================
 __global__ void __launch_bounds__(256) transpose_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int N,
                                                         int Npad) {
-  __shared__ bf16 tile[64][66];
+  // tile[d][tok ^ 4*(d >> 3)], rows padded to 72 elements (144 B, 16-byte aligned for the vector
+  // read-back).  The XOR spreads the 2-byte transposing stores of a warp (8 feature chunks x 4 tokens)
+  // over the banks: with 16-byte aligned rows an 8-row stride alone always hits one bank.
+  __shared__ __align__(16) bf16 tile[64][72];
   const int bh = blockIdx.y, n0 = blockIdx.x * 64;
   const bf16* src = in + (size_t)bh * N * 64;
   bf16* dst = out + ((size_t)bh * (Npad / 64) + blockIdx.x) * 4096;
-  for (int idx = threadIdx.x; idx < 64 * 32; idx += 256) {
-    int r = idx >> 5, c2 = idx & 31;
-    __nv_bfloat162 v = __floats2bfloat162_rn(0.f, 0.f);
-    if (n0 + r < N) v = *reinterpret_cast<const __nv_bfloat162*>(src + (size_t)(n0 + r) * 64 + 2 * c2);
-    tile[r][2 * c2] = v.x;
-    tile[r][2 * c2 + 1] = v.y;
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int idx = threadIdx.x + 256 * it;       // 512 chunks of 8 features: token r, features [8c, 8c+8)
+    const int r = idx >> 3, c = idx & 7;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (n0 + r < N) v = __ldg(reinterpret_cast<const uint4*>(src + (size_t)(n0 + r) * 64 + 8 * c));
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    const int col = r ^ (4 * c);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      tile[8 * c + 2 * j][col] = __ushort_as_bfloat16((unsigned short)(w[j] & 0xffffu));
+      tile[8 * c + 2 * j + 1][col] = __ushort_as_bfloat16((unsigned short)(w[j] >> 16));
+    }
   }
   __syncthreads();
-  for (int idx = threadIdx.x; idx < 64 * 32; idx += 256) {
-    int d = idx >> 5, t2 = idx & 31;
-    __nv_bfloat162 v;
-    v.x = tile[2 * t2][d];
-    v.y = tile[2 * t2 + 1][d];
-    *reinterpret_cast<__nv_bfloat162*>(dst + d * 64 + 2 * t2) = v;
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int idx = threadIdx.x + 256 * it;       // feature d, tokens [8m, 8m+8)
+    const int d = idx >> 3, m = idx & 7;
+    const int k = d >> 3;                          // tokens were stored at tok ^ 4k
+    uint4 v = *reinterpret_cast<const uint4*>(&tile[d][8 * (m ^ (k >> 1))]);
+    if (k & 1) v = make_uint4(v.z, v.w, v.x, v.y); // 4-token halves of the chunk are swapped
+    *reinterpret_cast<uint4*>(dst + d * 64 + 8 * m) = v;
   }
 }
 
@@ -698,22 +710,36 @@ __global__ void __launch_bounds__(256) prep_bwd_kernel(const bf16* __restrict__ 
                                                         const bf16* __restrict__ d_o, const float* __restrict__ g,
                                                         bf16* __restrict__ u, float* __restrict__ dlt,
                                                         bf16* __restrict__ qd, size_t rows, int N, int Npad) {
-  const size_t row = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
-  const float ig = 1.f / g[row];
-  const __nv_bfloat162 dv = reinterpret_cast<const __nv_bfloat162*>(d_o + row * 64)[lane];
-  const __nv_bfloat162 ov = reinterpret_cast<const __nv_bfloat162*>(o + row * 64)[lane];
-  const __nv_bfloat162 qv = reinterpret_cast<const __nv_bfloat162*>(q + row * 64)[lane];
-  const float d0 = __low2float(dv), d1 = __high2float(dv);
-  float s = d0 * __low2float(ov) + d1 * __high2float(ov);
+  // eight threads per row, 16 bytes (8 features) each; 32 rows per CTA
+  const size_t row = (size_t)blockIdx.x * 32 + (threadIdx.x >> 3);
+  const int c = threadIdx.x & 7;
+  const bool live = row < rows;
+  const size_t off = (live ? row : 0) * 64 + 8 * c;
+  const uint4 dv = __ldg(reinterpret_cast<const uint4*>(d_o + off));
+  const uint4 ov = __ldg(reinterpret_cast<const uint4*>(o + off));
+  const uint4 qv = __ldg(reinterpret_cast<const uint4*>(q + off));
+  const float ig = 1.f / g[live ? row : 0];
+  const uint32_t dw[4] = {dv.x, dv.y, dv.z, dv.w}, ow[4] = {ov.x, ov.y, ov.z, ov.w}, qw[4] = {qv.x, qv.y, qv.z, qv.w};
+  float d[8], qf[8], s = 0.f;
 #pragma unroll
-  for (int x = 16; x; x >>= 1) s += __shfl_xor_sync(0xffffffffu, s, x);
+  for (int j = 0; j < 4; ++j) {
+    d[2 * j] = __uint_as_float(dw[j] << 16), d[2 * j + 1] = __uint_as_float(dw[j] & 0xffff0000u);
+    qf[2 * j] = __uint_as_float(qw[j] << 16), qf[2 * j + 1] = __uint_as_float(qw[j] & 0xffff0000u);
+    s = fmaf(d[2 * j], __uint_as_float(ow[j] << 16), s);
+    s = fmaf(d[2 * j + 1], __uint_as_float(ow[j] & 0xffff0000u), s);
+  }
+#pragma unroll
+  for (int x = 4; x; x >>= 1) s += __shfl_xor_sync(0xffffffffu, s, x);
   const float dl = s * ig;
-  reinterpret_cast<__nv_bfloat162*>(u + row * 64)[lane] = __floats2bfloat162_rn(d0 * ig, d1 * ig);
-  reinterpret_cast<__nv_bfloat162*>(qd + row * 64)[lane] =
-      __floats2bfloat162_rn(-dl * __low2float(qv), -dl * __high2float(qv));
-  if (lane == 0) dlt[(row / N) * Npad + row % N] = dl;   // (BH, Npad) layout, pad stays zero
+  if (!live) return;
+  uint4 uo, qo;
+  uo.x = pack_bf16x2(d[0] * ig, d[1] * ig), uo.y = pack_bf16x2(d[2] * ig, d[3] * ig);
+  uo.z = pack_bf16x2(d[4] * ig, d[5] * ig), uo.w = pack_bf16x2(d[6] * ig, d[7] * ig);
+  qo.x = pack_bf16x2(-dl * qf[0], -dl * qf[1]), qo.y = pack_bf16x2(-dl * qf[2], -dl * qf[3]);
+  qo.z = pack_bf16x2(-dl * qf[4], -dl * qf[5]), qo.w = pack_bf16x2(-dl * qf[6], -dl * qf[7]);
+  *reinterpret_cast<uint4*>(u + off) = uo;
+  *reinterpret_cast<uint4*>(qd + off) = qo;
+  if (c == 0) dlt[(row / N) * Npad + row % N] = dl;   // (BH, Npad) layout, pad stays zero
 }
 
 }  // namespace mom
@@ -880,7 +906,7 @@ int moments_bwd(const Problem& pb, const void* q, const void* k, const void* v, 
   // 1. u = do/g, dlt = (do.o)/g, qd = -dlt*q
   FM_CUDA(cudaMemsetAsync(dlt, 0, (size_t)m.BH * m.Npad * 4, pb.stream));
   FM_LAUNCH("mom_prep_bwd", pb.stream,
-            prep_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, pb.stream>>>(
+            prep_bwd_kernel<<<(unsigned)((rows + 31) / 32), 256, 0, pb.stream>>>(
                 (const bf16*)q, (const bf16*)o, (const bf16*)d_o, g, u, dlt, qd, rows, m.N, m.Npad));
   // 2. forward-direction states of (k, v) (recomputed, not saved) and reverse-direction states of (q, u)
   if (!pb.saved_states) {
@@ -969,7 +995,7 @@ int moments_local_state_rev(const Problem& pb_in, const void* q, const void* o, 
   const size_t rows = (size_t)m.BH * m.N;
   FM_CUDA(cudaMemsetAsync(dlt, 0, (size_t)m.BH * m.Npad * 4, pb.stream));
   FM_LAUNCH("mom_prep_bwd", pb.stream,
-            prep_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, pb.stream>>>(
+            prep_bwd_kernel<<<(unsigned)((rows + 31) / 32), 256, 0, pb.stream>>>(
                 (const bf16*)q, (const bf16*)o, (const bf16*)d_o, g, u, dlt, qd, rows, m.N, m.Npad));
   int rc;
   if ((rc = launch_transpose(pb, q, w8, m.Npad))) return rc;
