@@ -41,6 +41,8 @@ struct IntraParams {
   const uint8_t* state;    // boundary states whose normaliser column is folded in here (FWD, DQ: forward-
                            // direction states; DKDV: reverse-direction states), nullable
   int nseg;
+  int noncausal;           // no intra-segment part at all: only the normaliser column of the one state per (b,h)
+                           // is applied (g; the -dlt(N1 + a N2 q) part of dq; the RN1 + a RN2 k part of dk)
   int edge_state;          // sequence parallel: the first (FWD, DQ) / last (DKDV) local segment has a state too
   float count_offset;      // tokens of earlier ranks (normaliser count term)
 };
@@ -160,13 +162,14 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
   // stream range (absolute token index of the first stream tile, number of 64-token tiles)
   const int st0 = MODE == INTRA_DKDV ? c0 : seg_start;
   const int st1 = MODE == INTRA_DKDV ? seg_end : min(c0 + CT, P.N);
-  const int nstream = (st1 - st0 + 63) / 64;
+  const int nstream = P.noncausal ? 0 : (st1 - st0 + 63) / 64;
   // moment part of the normaliser column (FWD: g, DQ: the -dlt (N1 + a N2 q) term): only segments
   // that have a boundary state
   const int seg = c0 / P.L;
   const bool has_norm =
-      P.state != nullptr && (MODE == INTRA_DKDV ? (seg < P.nseg - 1 || P.edge_state) : (seg > 0 || P.edge_state));
-  const int rec_idx = bh * P.nseg + seg;
+      P.state != nullptr &&
+      (P.noncausal || (MODE == INTRA_DKDV ? (seg < P.nseg - 1 || P.edge_state) : (seg > 0 || P.edge_state)));
+  const int rec_idx = P.noncausal ? bh : bh * P.nseg + seg;
 
   if (warp == 0) {
     tmem_alloc(tmem_slot, 512);
@@ -412,7 +415,9 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
       float gmom = 0.f;   // FWD: a q.N1 + (a^2/2) q.T
       for (int a2 = 0; a2 < nacc; ++a2) {
         const uint32_t col = MODE == INTRA_DKDV ? 128 * o + 64 * a2 : 64 * o;
-        if (nstored > 0) {       // the previous tile's stores have read the staging area
+        const bool store = (a2 == 0 ? P.out0 : P.out1) != nullptr;   // non-causal: some partials do not exist
+        if (!store && MODE != INTRA_FWD) continue;                   // (FWD still needs the pass for g)
+        if (store && nstored > 0) {       // the previous tile's stores have read the staging area
           if (storer) bulk_wait_group_read0();
           asm volatile("bar.sync %0, 128;" ::"r"(1 + w) : "memory");
         }
@@ -461,11 +466,14 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
             }
           }
           tmem_wait_ld();
-          const uint32_t dst = smem_u32(stg) + h * 16384 + rloc * 128;
+          if (store) {
+            const uint32_t dst = smem_u32(stg) + h * 16384 + rloc * 128;
 #pragma unroll
-          for (int c4 = 0; c4 < 8; ++c4)
-            sts128(dst + ((uint32_t)(c4 ^ (rloc & 7)) << 4), v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+            for (int c4 = 0; c4 < 8; ++c4)
+              sts128(dst + ((uint32_t)(c4 ^ (rloc & 7)) << 4), v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+          }
         }
+        if (!store) continue;
         fence_proxy_async();
         asm volatile("bar.sync %0, 128;" ::"r"(1 + w) : "memory");
         if (storer) {
@@ -476,7 +484,10 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
         }
         ++nstored;
       }
-      if (MODE == INTRA_FWD && r_abs < P.N) P.g[grow] = gsum[x] + (has_norm ? (float)(seg * P.L) + P.count_offset + gmom : 0.f);
+      if (MODE == INTRA_FWD && r_abs < P.N) {
+        const float count = P.noncausal ? (float)P.N : (float)(seg * P.L) + P.count_offset;
+        P.g[grow] = gsum[x] + (has_norm ? count + gmom : 0.f);
+      }
     }
     if (storer) bulk_wait_group0();      // shared memory must outlive the bulk stores
   }
@@ -504,10 +515,11 @@ static int launch_intra_t(const Problem& pb, int L, int Npad, const void* r1, co
   }
   IntraParams P{};
   P.N = pb.N, P.Npad = Npad, P.L = L, P.p = pb.p, P.a = pb.inv_c, P.dlt = dlt, P.out0 = out0, P.out1 = out1, P.g = g;
-  P.nseg = (pb.N + L - 1) / L;
+  P.noncausal = !pb.causal;
+  P.nseg = pb.causal ? (pb.N + L - 1) / L : 1;
   P.edge_state = MODE == INTRA_DKDV ? pb.sp_init_rev != nullptr : pb.sp_init_fwd != nullptr;
   P.count_offset = (float)pb.sp_offset;
-  P.state = (P.nseg > 1 || P.edge_state) ? state : nullptr;
+  P.state = (P.nseg > 1 || P.edge_state || P.noncausal) ? state : nullptr;
   CUtensorMap tmS = m[0];
   if (P.state) {
     int rc = make_tmap_bf16_3d(&tmS, state, 64, NSLAB * 64, (uint64_t)BH * P.nseg, 128, REC_BYTES, 64, 64);
@@ -515,7 +527,7 @@ static int launch_intra_t(const Problem& pb, int L, int Npad, const void* r1, co
   }
   CUtensorMap tmO0, tmO1;
   {
-    int rc = make_tmap_f32_3d(&tmO0, out0, 64, pb.N, BH, 256, (uint64_t)pb.N * 256, 32, 128);
+    int rc = make_tmap_f32_3d(&tmO0, out0 ? out0 : out1, 64, pb.N, BH, 256, (uint64_t)pb.N * 256, 32, 128);
     if (rc) return rc;
     tmO1 = tmO0;
     if (out1 && (rc = make_tmap_f32_3d(&tmO1, out1, 64, pb.N, BH, 256, (uint64_t)pb.N * 256, 32, 128))) return rc;

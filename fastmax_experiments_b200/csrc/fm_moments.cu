@@ -644,66 +644,6 @@ apply_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CU
 }
 
 // =============================================================================================
-// norm terms: the normaliser column of the state applied on CUDA cores (1/65 of the work).
-//   forward : g_i (+)= count + a q.N1 + (a^2/2) q^T N2 q                 (fastmax.py:304-322)
-//   dq      : part_i[l] -= dlt_i ( N1[l] + a (N2 q)[l] )                 (z2, z4 of fastmax.py:457-477)
-// One warp per row; N2 (fp32, 16 KiB) staged in shared memory per CTA (rows of one segment).
-// =============================================================================================
-struct NormParams {
-  int N, L, nseg, causal, p, mode /*0 fwd, 1 dq*/, accumulate;
-  float a;
-  const bf16* Q;
-  const float* dlt;       // (BH,N) dq mode
-  float* g;               // fwd mode: (BH,N)
-  float* part;            // dq mode: (BH,N,64)
-  const uint8_t* state;   // forward-direction records
-};
-
-__global__ void __launch_bounds__(256) norm_kernel(const NormParams P) {
-  __shared__ float n2[64][65];
-  __shared__ float n1[64];
-  const int bh = blockIdx.y;
-  const int r0 = blockIdx.x * 64;          // 64 rows per CTA, all in one segment (L % 64 == 0)
-  const int seg = r0 / P.L;
-  const bool has_state = !P.causal || seg > 0;
-  if (!has_state) return;                   // uniform per CTA
-  const float* vec = reinterpret_cast<const float*>(P.state + (size_t)(P.causal ? bh * P.nseg + seg : bh) * REC_BYTES + VEC_OFF);
-  for (int idx = threadIdx.x; idx < 4096; idx += 256) n2[idx >> 6][idx & 63] = P.p == 2 ? vec[128 + idx] : 0.f;
-  if (threadIdx.x < 64) n1[threadIdx.x] = vec[64 + threadIdx.x];
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float count = P.causal ? (float)(seg * P.L) : (float)P.N;
-  for (int r = warp; r < 64; r += 8) {
-    const int i = r0 + r;
-    if (i >= P.N) break;
-    const size_t grow = (size_t)bh * P.N + i;
-    const float q0 = __bfloat162float(P.Q[grow * 64 + lane]), q1 = __bfloat162float(P.Q[grow * 64 + lane + 32]);
-    // w[l] = sum_m N2[l][m] q[m] for l = lane, lane+32
-    float w0 = 0.f, w1 = 0.f;
-    if (P.p == 2) {
-      for (int m = 0; m < 32; ++m) {
-        const float qa = __shfl_sync(0xffffffffu, q0, m), qb = __shfl_sync(0xffffffffu, q1, m);
-        w0 = fmaf(n2[lane][m], qa, fmaf(n2[lane][m + 32], qb, w0));
-        w1 = fmaf(n2[lane + 32][m], qa, fmaf(n2[lane + 32][m + 32], qb, w1));
-      }
-    }
-    if (P.mode == 0) {
-      float s = P.a * (q0 * n1[lane] + q1 * n1[lane + 32]) + 0.5f * P.a * P.a * (q0 * w0 + q1 * w1);
-#pragma unroll
-      for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) P.g[grow] = (P.accumulate ? P.g[grow] : 0.f) + count + s;
-    } else {
-      // mode 1 (dq): -dlt (N1 + a N2 q)  on the forward states;  mode 2 (dk): RN1 + a RN2 k  on the reverse ones
-      const float d = P.mode == 1 ? -P.dlt[(size_t)bh * ((P.N + 63) / 64 * 64) + i] : 1.f;
-      float* pr = P.part + grow * 64;
-      const float b0 = P.accumulate ? pr[lane] : 0.f, b1 = P.accumulate ? pr[lane + 32] : 0.f;
-      pr[lane] = b0 + d * (n1[lane] + P.a * w0);
-      pr[lane + 32] = b1 + d * (n1[lane + 32] + P.a * w1);
-    }
-  }
-}
-
-// =============================================================================================
 // backward prep: u = do/g (bf16), dlt = (do.o)/g (fp32), qd = -dlt*q (bf16).  HBM-bound pass.
 // =============================================================================================
 __global__ void __launch_bounds__(256) prep_bwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ o,
@@ -852,13 +792,6 @@ static int launch_apply(const Problem& pb, const MomLayout& m, const char* name,
   return FASTMAX_OK;
 }
 
-static int launch_norm(const Problem& pb, const MomLayout& m, NormParams P) {
-  P.N = m.N, P.L = m.L, P.nseg = m.nseg, P.causal = pb.causal, P.p = pb.p, P.a = pb.inv_c;
-  dim3 grid((m.N + 63) / 64, m.BH);
-  FM_LAUNCH(P.mode == 0 ? "mom_norm_fwd" : (P.mode == 1 ? "mom_norm_dq" : "mom_norm_dk"), pb.stream,
-            norm_kernel<<<grid, 256, 0, pb.stream>>>(P));
-  return FASTMAX_OK;
-}
 
 int moments_fwd(const Problem& pb, const void* q, const void* k, const void* v, void* o, float* g, void* ws) {
   const MomLayout m = mom_layout(pb.B, pb.H, pb.N, moments_seg_len(pb.N), pb.causal, false);
@@ -871,14 +804,9 @@ int moments_fwd(const Problem& pb, const void* q, const void* k, const void* v, 
   if ((rc = launch_transpose(pb, k, w8 + m.off_xt, m.Npad))) return rc;
   if ((rc = launch_build(pb, m, w8 + m.off_xt, v, k, state, 0, pb.sp_init_fwd))) return rc;
   // 2. intra-segment part (causal only) and the normaliser
-  if (pb.causal) {
-    // intra-segment scores + the normaliser (its moment part rides along as one more score MMA)
-    if ((rc = intra_fwd(pb, m.L, m.Npad, q, k, v, part, g, state))) return rc;
-  } else {
-    NormParams np{};
-    np.mode = 0, np.accumulate = 0, np.Q = (const bf16*)q, np.g = g, np.state = state;
-    if ((rc = launch_norm(pb, m, np))) return rc;
-  }
+  // intra-segment scores + the normaliser (its moment part rides along as one more score MMA); non-causal:
+  // only that MMA runs (no intra-segment part, no partial)
+  if ((rc = intra_fwd(pb, m.L, m.Npad, q, k, v, pb.causal ? part : nullptr, g, state))) return rc;
   // 3. inter-segment part + normalisation
   ApplyParams ap{};
   ap.mode = APPLY_FWD, ap.state_reverse = 0, ap.b_kmajor = 0, ap.edge_state = pb.sp_init_fwd != nullptr;
@@ -916,16 +844,9 @@ int moments_bwd(const Problem& pb, const void* q, const void* k, const void* v, 
   if ((rc = launch_transpose(pb, q, w8 + m.off_xt2, m.Npad))) return rc;
   if ((rc = launch_build(pb, m, w8 + m.off_xt2, u, qd, R, 1, pb.sp_init_rev))) return rc;
   // 3. intra-segment partials
-  if (pb.causal) {
-    if ((rc = intra_dq(pb, m.L, m.Npad, q, u, k, v, dlt, dq_part, S))) return rc;
-    if ((rc = intra_dkdv(pb, m.L, m.Npad, k, v, q, u, dlt, dk_part, dv_part, R))) return rc;
-  } else {
-    NormParams np{};
-    np.mode = 1, np.accumulate = 0, np.Q = (const bf16*)q, np.dlt = dlt, np.part = dq_part, np.state = S;
-    if ((rc = launch_norm(pb, m, np))) return rc;
-    np.mode = 2, np.Q = (const bf16*)k, np.dlt = nullptr, np.part = dk_part, np.state = R;
-    if ((rc = launch_norm(pb, m, np))) return rc;
-  }
+  // (non-causal: the same kernels only apply the normaliser column of the single state: dq_part, dk_part)
+  if ((rc = intra_dq(pb, m.L, m.Npad, q, u, k, v, dlt, dq_part, S))) return rc;
+  if ((rc = intra_dkdv(pb, m.L, m.Npad, k, v, q, u, dlt, dk_part, pb.causal ? dv_part : nullptr, R))) return rc;
   // 4. inter-segment parts
   ApplyParams ap{};
   ap.mode = APPLY_DQ, ap.state_reverse = 0, ap.b_kmajor = 1, ap.edge_state = pb.sp_init_fwd != nullptr;
