@@ -126,7 +126,7 @@ def run_reference(args, rank: int) -> None:
     value = n_sample / dt / HL["H"]
     sample = (f"each step = fwd+bwd of a (B=1,H=1,N={n_sample},D={HL['D']}) fp32 slice of the workload "
               f"(the full shape needs PB-sized intermediates); tokens/s = (b,h,token) units/s / H={HL['H']}")
-    print(json.dumps({
+    _emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -199,7 +199,7 @@ def run_sequence_parallel(args, rank: int, world: int, local: int) -> None:
     peaks = load_peaks()
     ach = B * H * N * (f_fwd + f_bwd) / (ms_step * 1e-3) / 1e12
     if rank == 0:
-        print(json.dumps({
+        _emit(json.dumps({
             "metric": METRIC, "value": B * N / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -397,10 +397,28 @@ def main() -> None:
                       f"(B=1,H=1,N=512,D={D}) slice = {secs:.2f} s; tokens/s = units/s / H={H}"}
 
     if rank == 0:
-        print(json.dumps(out))
+        _emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
 
+def _emit(line: str) -> None:
+    """The one JSON line goes to the process's ORIGINAL stdout (see _quiet_stdout)."""
+    os.write(_REAL_STDOUT, (line + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
+def _quiet_stdout() -> None:
+    """Libraries chat on fd 1 (NCCL prints its version banner there): point fd 1 at stderr for the
+    whole run and keep the original for the result line, so stdout carries exactly one JSON line."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
 if __name__ == "__main__":
+    _quiet_stdout()
     main()
