@@ -106,7 +106,7 @@ int fastmax_plan_make(fastmax_plan* plan, int B, int H, int N, int D, int p, int
   const bool use_mom = algo == FASTMAX_ALGO_MOMENTS || (algo == FASTMAX_ALGO_AUTO && mom_ok && N >= 256);
   if (use_mom) {
     plan->algo = FASTMAX_ALGO_MOMENTS;
-    plan->seg_len = fm::moments_seg_len(N);
+    plan->seg_len = fm::moments_seg_len(B, H, N);
     plan->n_seg = (N + plan->seg_len - 1) / plan->seg_len;
     plan->fwd_workspace_bytes = fm::moments_workspace_bytes(B, H, N, causal, false);
     plan->bwd_workspace_bytes = fm::moments_workspace_bytes(B, H, N, causal, true);

@@ -92,7 +92,7 @@ int intra_dq(const Problem& pb, int L, int Npad, const void* q, const void* u, c
              const float* dlt, float* dq_part, const uint8_t* state);
 int intra_dkdv(const Problem& pb, int L, int Npad, const void* k, const void* v, const void* q, const void* u,
                const float* dlt, float* dk_part, float* dv_part, const uint8_t* rstate);
-int moments_seg_len(int N);
+int moments_seg_len(int B, int H, int N);
 size_t moments_state_bytes(int B, int H);
 size_t moments_saved_state_bytes(int B, int H, int N, int causal);
 size_t moments_local_state_workspace_bytes(int B, int H, int N);
