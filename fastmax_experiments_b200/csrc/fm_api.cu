@@ -106,10 +106,10 @@ int fastmax_plan_make(fastmax_plan* plan, int B, int H, int N, int D, int p, int
   const bool use_mom = algo == FASTMAX_ALGO_MOMENTS || (algo == FASTMAX_ALGO_AUTO && mom_ok && N >= 256);
   if (use_mom) {
     plan->algo = FASTMAX_ALGO_MOMENTS;
-    plan->seg_len = fm::moments_seg_len(B, H, N);
+    plan->seg_len = fm::moments_seg_len(B, H, N, p);
     plan->n_seg = (N + plan->seg_len - 1) / plan->seg_len;
-    plan->fwd_workspace_bytes = fm::moments_workspace_bytes(B, H, N, causal, false);
-    plan->bwd_workspace_bytes = fm::moments_workspace_bytes(B, H, N, causal, true);
+    plan->fwd_workspace_bytes = fm::moments_workspace_bytes(B, H, N, p, causal, false);
+    plan->bwd_workspace_bytes = fm::moments_workspace_bytes(B, H, N, p, causal, true);
     fm::moments_flops(B, H, N, p, causal, &plan->fwd_tensor_flops, &plan->bwd_tensor_flops,
                       &plan->rebuild_tensor_flops);
     return FASTMAX_OK;
@@ -177,7 +177,7 @@ size_t fastmax_saved_state_bytes(int B, int H, int N, int D, int p, int causal, 
   fastmax_plan pl;
   if (fastmax_plan_make(&pl, B, H, N, D, p, causal, dtype, algo)) return 0;
   if (pl.algo != FASTMAX_ALGO_MOMENTS) return 0;
-  return fm::moments_saved_state_bytes(B, H, N, causal);
+  return fm::moments_saved_state_bytes(B, H, N, p, causal);
 }
 
 int fastmax_fwd_ex(const void* q, const void* k, const void* v, void* o, float* g, void* saved_states, int B, int H,
@@ -271,7 +271,7 @@ int fastmax_fwd_sp(const void* q, const void* k, const void* v, void* o, float* 
   if (!q || !k || !v || !o || !g || token_offset < 0) return FASTMAX_ERR_BAD_ARG;
   int rc = check_sp(B, H, N, D, p, dtype);
   if (rc) return rc;
-  const size_t need = fm::moments_workspace_bytes(B, H, N, 1, false);
+  const size_t need = fm::moments_workspace_bytes(B, H, N, p, 1, false);
   if (need > workspace_bytes || !workspace || ((uintptr_t)workspace & 255)) return FASTMAX_ERR_WORKSPACE;
   Problem pb{B, H, N, D, p, 1, dtype, inv_c, (cudaStream_t)stream};
   pb.sp_init_fwd = init_state, pb.sp_offset = token_offset;
@@ -287,7 +287,7 @@ int fastmax_bwd_sp(const void* q, const void* k, const void* v, const void* o, c
   if (!q || !k || !v || !o || !g || !d_o || !dq || !dk || !dv || token_offset < 0) return FASTMAX_ERR_BAD_ARG;
   int rc = check_sp(B, H, N, D, p, dtype);
   if (rc) return rc;
-  const size_t need = fm::moments_workspace_bytes(B, H, N, 1, true);
+  const size_t need = fm::moments_workspace_bytes(B, H, N, p, 1, true);
   if (need > workspace_bytes || !workspace || ((uintptr_t)workspace & 255)) return FASTMAX_ERR_WORKSPACE;
   Problem pb{B, H, N, D, p, 1, dtype, inv_c, (cudaStream_t)stream};
   pb.sp_init_fwd = init_state_fwd, pb.sp_init_rev = init_state_rev, pb.sp_offset = token_offset;

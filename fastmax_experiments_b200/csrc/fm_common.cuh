@@ -92,16 +92,16 @@ int intra_dq(const Problem& pb, int L, int Npad, const void* q, const void* u, c
              const float* dlt, float* dq_part, const uint8_t* state);
 int intra_dkdv(const Problem& pb, int L, int Npad, const void* k, const void* v, const void* q, const void* u,
                const float* dlt, float* dk_part, float* dv_part, const uint8_t* rstate);
-int moments_seg_len(int B, int H, int N);
+int moments_seg_len(int B, int H, int N, int p);
 size_t moments_state_bytes(int B, int H);
-size_t moments_saved_state_bytes(int B, int H, int N, int causal);
+size_t moments_saved_state_bytes(int B, int H, int N, int p, int causal);
 size_t moments_local_state_workspace_bytes(int B, int H, int N);
 int moments_local_state(const Problem& pb, const void* x, const void* w, const void* w2, void* state_out, void* ws);
 int moments_local_state_rev(const Problem& pb, const void* q, const void* o, const float* g, const void* d_o,
                             void* state_out, void* ws);
 size_t moments_local_state_rev_workspace_bytes(int B, int H, int N);
 int moments_reduce_states(const void* gathered, int G, int rank, int dir, void* out, int B, int H, cudaStream_t stream);
-size_t moments_workspace_bytes(int B, int H, int N, int causal, bool bwd);
+size_t moments_workspace_bytes(int B, int H, int N, int p, int causal, bool bwd);
 void moments_flops(int B, int H, int N, int p, int causal, double* fwd, double* bwd, double* rebuild);
 int moments_fwd(const Problem& pb, const void* q, const void* k, const void* v, void* o, float* g, void* ws);
 int moments_bwd(const Problem& pb, const void* q, const void* k, const void* v, const void* o, const float* g,

@@ -727,16 +727,17 @@ static MomLayout mom_layout(int B, int H, int N, int L, int causal, bool bwd) {
 // intra tiles of a 2048-token segment, so sequences up to 2048 tokens run as ONE segment (pure
 // tensor-core quadratic evaluation, no states); longer ones use 512-token segments, doubled only while
 // the boundary states of one direction would exceed 24 GiB (B*H = 32, N = 1M: L = 1024).
-int moments_seg_len(int B, int H, int N) {
-  if (N <= 2048) return (N + 511) / 512 * 512;
+int moments_seg_len(int B, int H, int N, int p) {
+  // (p = 1: the moment kernels handle one slab instead of 65, so segments stay at 512 tokens)
+  if (N <= (p == 2 ? 2048 : 512)) return (N + 511) / 512 * 512;
   int L = 512;
   const double budget = 24.0 * 1024 * 1024 * 1024;
   while ((double)B * H * ((N + L - 1) / L) * (double)REC_BYTES > budget) L *= 2;
   return L;
 }
 
-size_t moments_workspace_bytes(int B, int H, int N, int causal, bool bwd) {
-  return mom_layout(B, H, N, moments_seg_len(B, H, N), causal, bwd).total;
+size_t moments_workspace_bytes(int B, int H, int N, int p, int causal, bool bwd) {
+  return mom_layout(B, H, N, moments_seg_len(B, H, N, p), causal, bwd).total;
 }
 
 static int launch_transpose(const Problem& pb, const void* in, void* out, int Npad) {
@@ -795,7 +796,7 @@ static int launch_apply(const Problem& pb, const MomLayout& m, const char* name,
 
 
 int moments_fwd(const Problem& pb, const void* q, const void* k, const void* v, void* o, float* g, void* ws) {
-  const MomLayout m = mom_layout(pb.B, pb.H, pb.N, moments_seg_len(pb.B, pb.H, pb.N), pb.causal, false);
+  const MomLayout m = mom_layout(pb.B, pb.H, pb.N, moments_seg_len(pb.B, pb.H, pb.N, pb.p), pb.causal, false);
   uint8_t* w8 = (uint8_t*)ws;
   int rc;
   const float a = pb.inv_c;
@@ -819,7 +820,7 @@ int moments_fwd(const Problem& pb, const void* q, const void* k, const void* v, 
 
 int moments_bwd(const Problem& pb, const void* q, const void* k, const void* v, const void* o, const float* g,
                 const void* d_o, void* dq, void* dk, void* dv, void* ws) {
-  const MomLayout m = mom_layout(pb.B, pb.H, pb.N, moments_seg_len(pb.B, pb.H, pb.N), pb.causal, true);
+  const MomLayout m = mom_layout(pb.B, pb.H, pb.N, moments_seg_len(pb.B, pb.H, pb.N, pb.p), pb.causal, true);
   uint8_t* w8 = (uint8_t*)ws;
   int rc;
   const float a = pb.inv_c;
@@ -876,8 +877,8 @@ int moments_bwd(const Problem& pb, const void* q, const void* k, const void* v, 
 // =============================================================================================
 size_t moments_state_bytes(int B, int H) { return (size_t)B * H * REC_BYTES; }
 
-size_t moments_saved_state_bytes(int B, int H, int N, int causal) {
-  const MomLayout m = mom_layout(B, H, N, moments_seg_len(B, H, N), causal, false);
+size_t moments_saved_state_bytes(int B, int H, int N, int p, int causal) {
+  const MomLayout m = mom_layout(B, H, N, moments_seg_len(B, H, N, p), causal, false);
   return (size_t)m.BH * m.nrec * REC_BYTES;
 }
 
@@ -889,7 +890,7 @@ size_t moments_local_state_workspace_bytes(int B, int H, int N) {
 int moments_local_state(const Problem& pb_in, const void* x, const void* w, const void* w2, void* state_out, void* ws) {
   Problem pb = pb_in;
   pb.causal = 0;
-  const MomLayout m = mom_layout(pb.B, pb.H, pb.N, moments_seg_len(pb.B, pb.H, pb.N), 0, false);
+  const MomLayout m = mom_layout(pb.B, pb.H, pb.N, moments_seg_len(pb.B, pb.H, pb.N, pb.p), 0, false);
   int rc;
   if ((rc = launch_transpose(pb, x, ws, m.Npad))) return rc;
   return launch_build(pb, m, ws, w, w2, (uint8_t*)state_out, 0);
@@ -905,7 +906,7 @@ int moments_local_state_rev(const Problem& pb_in, const void* q, const void* o, 
                             void* state_out, void* ws) {
   Problem pb = pb_in;
   pb.causal = 0;
-  const MomLayout m = mom_layout(pb.B, pb.H, pb.N, moments_seg_len(pb.B, pb.H, pb.N), 0, false);
+  const MomLayout m = mom_layout(pb.B, pb.H, pb.N, moments_seg_len(pb.B, pb.H, pb.N, pb.p), 0, false);
   uint8_t* w8 = (uint8_t*)ws;
   const size_t tens = (size_t)m.BH * m.N * 64;
   size_t off = align_up((size_t)m.BH * 64 * m.Npad * 2, 1024);
@@ -953,7 +954,7 @@ int moments_reduce_states(const void* gathered, int G, int rank, int dir, void* 
 
 // executed tensor-core flops of the plan (for the utilisation report; never the algorithmic count)
 void moments_flops(int B, int H, int N, int p, int causal, double* fwd, double* bwd, double* rebuild) {
-  const int L = moments_seg_len(B, H, N);
+  const int L = moments_seg_len(B, H, N, p);
   const MomLayout m = mom_layout(B, H, N, L, causal, false);
   const double mma = 2.0 * 128 * 64 * 16;
   const int nblk = (N + 63) / 64, Lb = L / 64;
