@@ -87,11 +87,14 @@ int exact_bwd_partial(const Problem& pb, const void* q, const void* k, const voi
 
 // tcgen05 moment-scan path (fm_moments.cu): bf16, D = 64
 int intra_fwd(const Problem& pb, int L, int Npad, const void* q, const void* k, const void* v, float* o_part,
-              float* g, const uint8_t* state);
+              float* g, const uint8_t* state, void* o_final = nullptr);
 int intra_dq(const Problem& pb, int L, int Npad, const void* q, const void* u, const void* k, const void* v,
-             const float* dlt, float* dq_part, const uint8_t* state);
+             const float* dlt, float* dq_part, const uint8_t* state, void* dq_final = nullptr);
 int intra_dkdv(const Problem& pb, int L, int Npad, const void* k, const void* v, const void* q, const void* u,
-               const float* dlt, float* dk_part, float* dv_part, const uint8_t* rstate);
+               const float* dlt, float* dk_part, float* dv_part, const uint8_t* rstate, void* dk_final = nullptr,
+               void* dv_final = nullptr);
+// (p = 1 with *_final given: the kernels also apply the first-order state term and write the final bf16
+//  outputs; the *_part arguments are then unused)
 int moments_seg_len(int B, int H, int N, int p);
 size_t moments_state_bytes(int B, int H);
 size_t moments_saved_state_bytes(int B, int H, int N, int p, int causal);

@@ -41,6 +41,8 @@ struct IntraParams {
   const uint8_t* state;    // boundary states whose normaliser column is folded in here (FWD, DQ: forward-
                            // direction states; DKDV: reverse-direction states), nullable
   int nseg;
+  int fused;               // p = 1: the first-order state term (slab 64) is applied here as well and the final
+                           // bf16 outputs are written (no apply kernels, no fp32 partials)
   int noncausal;           // no intra-segment part at all: only the normaliser column of the one state per (b,h)
                            // is applied (g; the -dlt(N1 + a N2 q) part of dq; the RN1 + a RN2 k part of dk)
   int edge_state;          // sequence parallel: the first (FWD, DQ) / last (DKDV) local segment has a state too
@@ -64,7 +66,8 @@ struct IntraDescs {
   unsigned long long resK[8][4];        // resident tile (R1 tiles, then R2 tiles) x k-step, K-major
   unsigned long long strK[6][2][4];     // ring stage x operand (T1, T2) x k-step, K-major
   unsigned long long strMN[6][2][4];    // same tiles read MN-major (B of the accumulating MMAs)
-  unsigned long long normK[4];          // normaliser slab, K-major
+  unsigned long long normK[4];          // normaliser slab (p = 1 fused: the first-order slab), K-major
+  unsigned long long normMN[4];         // same tile read MN-major
 };
 
 template <int MODE> __host__ __device__ constexpr int intra_otile(int w, int x) {
@@ -137,7 +140,8 @@ __global__ void __launch_bounds__(384, 1)
 intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ CUtensorMap tmR2,
              const __grid_constant__ CUtensorMap tmT1, const __grid_constant__ CUtensorMap tmT2,
              const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmO0,
-             const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ IntraDescs DS, const IntraParams P) {
+             const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmB0,
+             const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ IntraDescs DS, const IntraParams P) {
   using C = IntraCfg<MODE>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -185,6 +189,10 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
     tma_prefetch_desc(&tmT2);
     tma_prefetch_desc(&tmO0);
   }
+  // fp32 vector part of the boundary state ([0,64): S0 / R0, [64,128): N1 / RN1), read by every epilogue row
+  float* vec_s = reinterpret_cast<float*>(norm_s + 8192);
+  if (tid < 128)
+    vec_s[tid] = has_norm ? reinterpret_cast<const float*>(P.state + (size_t)rec_idx * REC_BYTES + VEC_OFF)[tid] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -208,7 +216,7 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
     // ---------------------------------------------------------------- TMA producer
     if (lane == 0) {
       mbar_arrive_expect_tx(res_full, C::RES_BYTES + (has_norm ? 8192 : 0));
-      if (has_norm) tma_load_3d(norm_s, &tmS, res_full, 0, 65 * 64, rec_idx);
+      if (has_norm) tma_load_3d(norm_s, &tmS, res_full, 0, (P.fused ? 64 : 65) * 64, rec_idx);
       for (int o = 0; o < C::OUT_TILES; ++o)
         for (int h = 0; h < 2; ++h) {
           tma_load_3d(res + o * 16384 + h * 8192, &tmR1, res_full, 0, c0 + o * 128 + h * 64, bh);
@@ -382,10 +390,35 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
       __syncwarp();
       tc_fence_after();
       if (elect_one()) {
+        if (!P.fused) {
 #pragma unroll
-        for (int x = 0; x < 2; ++x) {
-          if (x >= n_ot) break;
-          FM_INTRA_CALL_WX(intra_issue_norm, DS);
+          for (int x = 0; x < 2; ++x) {
+            if (x >= n_ot) break;
+            FM_INTRA_CALL_WX(intra_issue_norm, DS);
+          }
+        } else {
+          // p = 1: first-order state term of each output tile into the (drained) score buffer.
+          //   FWD : T  = Q . S1        (contract the slab's rows: MN-major B)        -> columns 64x
+          //   DQ  : T' = U . S1^T      (contract its columns: K-major B, A = R2 = U)  -> columns 64x
+          //   DKDV: T  = K . R1 -> columns [0,64)  and  T' = V . R1^T -> columns [64,128)
+          constexpr uint32_t IDK64 = make_idesc_bf16(128, 64, false, false);
+          constexpr uint32_t IDN64 = make_idesc_bf16(128, 64, false, true);
+          const uint32_t sb = 256 + 128 * w;
+          if constexpr (MODE == INTRA_DKDV) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) umma_ss(sb, DS.resK[w][kk], DS.normMN[kk], IDN64, kk > 0);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) umma_ss(sb + 64, DS.resK[C::OUT_TILES + w][kk], DS.normK[kk], IDK64, kk > 0);
+          } else {
+            for (int x = 0; x < 2; ++x) {
+              const int o = otile[x];
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                if constexpr (MODE == INTRA_FWD) umma_ss(sb + 64 * x, DS.resK[o][kk], DS.normMN[kk], IDN64, kk > 0);
+                else umma_ss(sb + 64 * x, DS.resK[C::OUT_TILES + o][kk], DS.normK[kk], IDK64, kk > 0);
+              }
+            }
+          }
         }
       }
       __syncwarp();
@@ -393,6 +426,99 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
     if (issuer) umma_commit(&acc_done[w]);
     mbar_wait(&acc_done[w], 0);
     tc_fence_after();
+    if (P.fused) {
+      // ---------------------------------------------------------------- epilogue, p = 1: final outputs
+      //   FWD : o  = (O + a T + S0) / g,   g = rowsum + count + a q.N1
+      //   DQ  : dq = a (O + T' - dlt N1)
+      //   DKDV: dv = O_dv + a T + R0 ;  dk = a (O_dk + T' + RN1)
+      // (state terms only where the segment has a boundary state), written as bf16 through the free stream
+      // ring with bulk tensor stores.
+      asm volatile("bar.sync 3, 256;" ::: "memory");
+      uint8_t* stg = ring + w * 32768;
+      const bool storer = q == 0 && lane == 0;
+      int nstored = 0;
+#pragma unroll
+      for (int x = 0; x < 2; ++x) {
+        if (x >= n_ot) break;
+        const int o = otile[x];
+        const int ob = c0 + o * 128;
+        const int r_abs = ob + rloc;
+        if (ob >= P.N) continue;                               // uniform over the warpgroup
+        const size_t grow = (size_t)bh * P.N + r_abs;
+        float sc0 = 1.f;
+        if constexpr (MODE == INTRA_FWD) {
+          float gmom = 0.f;
+          if (has_norm) {
+            const uint8_t* qrow = res + o * 16384 + rloc * 128;
+#pragma unroll
+            for (int c8 = 0; c8 < 8; ++c8) {
+              const uint4 qv = *reinterpret_cast<const uint4*>(qrow + ((c8 ^ (rloc & 7)) << 4));
+              const uint32_t qw[4] = {qv.x, qv.y, qv.z, qv.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                gmom = fmaf(__uint_as_float(qw[j] << 16), vec_s[64 + 8 * c8 + 2 * j], gmom);
+                gmom = fmaf(__uint_as_float(qw[j] & 0xffff0000u), vec_s[64 + 8 * c8 + 2 * j + 1], gmom);
+              }
+            }
+          }
+          const float count = P.noncausal ? (float)P.N : (float)(seg * P.L) + P.count_offset;
+          const float gv = gsum[x] + (has_norm ? count + a * gmom : 0.f);
+          if (r_abs < P.N) P.g[grow] = gv;
+          sc0 = 1.f / gv;
+        } else if constexpr (MODE == INTRA_DQ) {
+          sc0 = a;
+        }
+        const int nacc = MODE == INTRA_DKDV ? 2 : 1;
+        for (int a2 = 0; a2 < nacc; ++a2) {
+          const uint32_t col = MODE == INTRA_DKDV ? 128 * o + 64 * a2 : 64 * o;
+          const uint32_t tcol = MODE == INTRA_DKDV ? 64 * a2 : 64 * x;
+          const float sc = (MODE == INTRA_DKDV && a2 == 1) ? a : sc0;
+          if (nstored > 0) {       // the previous tile's stores have read the staging area
+            if (storer) bulk_wait_group_read0();
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + w) : "memory");
+          }
+#pragma unroll 1
+          for (int h = 0; h < 2; ++h) {
+            uint32_t v[32], tn[32];
+            tmem_ld32(lane_addr + col + 32 * h, v);
+            if (has_norm) tmem_ld32(sbuf + tcol + 32 * h, tn);
+            tmem_wait_ld();
+            uint32_t pk[16];
+#pragma unroll
+            for (int c = 0; c < 32; c += 2) {
+              float r[2];
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int idx = 32 * h + c + e;
+                float val = __uint_as_float(v[c + e]);
+                if (has_norm) {
+                  const float t = __uint_as_float(tn[c + e]);
+                  if constexpr (MODE == INTRA_FWD) val += fmaf(a, t, vec_s[idx]);
+                  else if constexpr (MODE == INTRA_DQ) val += t - dlt_row[x] * vec_s[64 + idx];
+                  else val += a2 == 0 ? fmaf(a, t, vec_s[idx]) : t + vec_s[64 + idx];
+                }
+                r[e] = val * sc;
+              }
+              pk[c >> 1] = pack_bf16x2(r[0], r[1]);
+            }
+            const uint32_t dst = smem_u32(stg) + rloc * 128;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              sts128(dst + ((uint32_t)((4 * h + j) ^ (rloc & 7)) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          }
+          fence_proxy_async();
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + w) : "memory");
+          if (storer) {
+            const CUtensorMap* tm = a2 == 0 ? &tmB0 : &tmB1;
+            tma_store_3d(tm, stg, 0, ob, bh);                         // rows past N are clipped by the tensor map
+            if (ob + 64 < P.N) tma_store_3d(tm, stg + 8192, 0, ob + 64, bh);
+            bulk_commit_group();
+          }
+          ++nstored;
+        }
+      }
+      if (storer) bulk_wait_group0();      // shared memory must outlive the bulk stores
+    } else {
     // ---------------------------------------------------------------- epilogue: fp32 partials
     // Written through shared memory with bulk tensor stores: a thread owns a 256-byte output row, so
     // storing from registers means 16-byte pieces at a 256-byte stride (measured: a third of the CTA's
@@ -411,7 +537,6 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
       if (!tile_live) continue;
       const size_t grow = (size_t)bh * P.N + r_abs;
       const int nacc = MODE == INTRA_DKDV ? 2 : 1;
-      const float* vec = has_norm ? reinterpret_cast<const float*>(P.state + (size_t)rec_idx * REC_BYTES + VEC_OFF) : nullptr;
       float gmom = 0.f;   // FWD: a q.N1 + (a^2/2) q.T
       for (int a2 = 0; a2 < nacc; ++a2) {
         const uint32_t col = MODE == INTRA_DKDV ? 128 * o + 64 * a2 : 64 * o;
@@ -433,7 +558,7 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
 #pragma unroll
               for (int c = 0; c < 32; ++c)
                 v[c] = __float_as_uint(__uint_as_float(v[c]) +
-                                       fmaf(a1, __uint_as_float(tn[c]), __ldg(vec + 64 + 32 * h + c)));
+                                       fmaf(a1, __uint_as_float(tn[c]), vec_s[64 + 32 * h + c]));
             }
           } else {
             if (has_norm) {   // CTA-uniform
@@ -445,7 +570,7 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
 #pragma unroll
                 for (int c = 0; c < 32; ++c)
                   v[c] = __float_as_uint(__uint_as_float(v[c]) -
-                                         dlt_row[x] * fmaf(a1, __uint_as_float(tn[c]), __ldg(vec + 64 + 32 * h + c)));
+                                         dlt_row[x] * fmaf(a1, __uint_as_float(tn[c]), vec_s[64 + 32 * h + c]));
               } else {
                 // g += a q.N1 + (a^2/2) q.T  with the thread's own q row read back from the resident tile
                 const uint8_t* qrow = res + o * 16384 + rloc * 128;
@@ -458,8 +583,8 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
                     const int c = 8 * c8 + 2 * j;
                     const float q0 = __uint_as_float(qw[j] << 16), q1 = __uint_as_float(qw[j] & 0xffff0000u);
                     const float c2n = c2;
-                    gmom += q0 * fmaf(c2n, __uint_as_float(tn[c]), a * __ldg(vec + 64 + 32 * h + c));
-                    gmom += q1 * fmaf(c2n, __uint_as_float(tn[c + 1]), a * __ldg(vec + 64 + 32 * h + c + 1));
+                    gmom += q0 * fmaf(c2n, __uint_as_float(tn[c]), a * vec_s[64 + 32 * h + c]);
+                    gmom += q1 * fmaf(c2n, __uint_as_float(tn[c + 1]), a * vec_s[64 + 32 * h + c + 1]);
                   }
                 }
               }
@@ -490,6 +615,7 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
       }
     }
     if (storer) bulk_wait_group0();      // shared memory must outlive the bulk stores
+    }   // !fused
   }
   tc_fence_before();
   __syncthreads();
@@ -504,7 +630,7 @@ using namespace mom;
 template <int MODE>
 static int launch_intra_t(const Problem& pb, int L, int Npad, const void* r1, const void* r2, const void* t1,
                           const void* t2, const float* dlt, float* out0, float* out1, float* g,
-                          const uint8_t* state, const char* name) {
+                          const uint8_t* state, const char* name, void* final0 = nullptr, void* final1 = nullptr) {
   using C = IntraCfg<MODE>;
   const int BH = pb.B * pb.H;
   CUtensorMap m[4];
@@ -516,6 +642,7 @@ static int launch_intra_t(const Problem& pb, int L, int Npad, const void* r1, co
   IntraParams P{};
   P.N = pb.N, P.Npad = Npad, P.L = L, P.p = pb.p, P.a = pb.inv_c, P.dlt = dlt, P.out0 = out0, P.out1 = out1, P.g = g;
   P.noncausal = !pb.causal;
+  P.fused = pb.p == 1 && final0 != nullptr;
   P.nseg = pb.causal ? (pb.N + L - 1) / L : 1;
   P.edge_state = MODE == INTRA_DKDV ? pb.sp_init_rev != nullptr : pb.sp_init_fwd != nullptr;
   P.count_offset = (float)pb.sp_offset;
@@ -527,10 +654,19 @@ static int launch_intra_t(const Problem& pb, int L, int Npad, const void* r1, co
   }
   CUtensorMap tmO0, tmO1;
   {
-    int rc = make_tmap_f32_3d(&tmO0, out0 ? out0 : out1, 64, pb.N, BH, 256, (uint64_t)pb.N * 256, 32, 128);
+    int rc = FASTMAX_OK;
+    if (out0 || out1) rc = make_tmap_f32_3d(&tmO0, out0 ? out0 : out1, 64, pb.N, BH, 256, (uint64_t)pb.N * 256, 32, 128);
+    else tmO0 = m[0];   // p = 1 fused: no fp32 partials
     if (rc) return rc;
     tmO1 = tmO0;
     if (out1 && (rc = make_tmap_f32_3d(&tmO1, out1, 64, pb.N, BH, 256, (uint64_t)pb.N * 256, 32, 128))) return rc;
+  }
+  CUtensorMap tmB0 = tmO0, tmB1 = tmO0;
+  if (P.fused) {
+    int rc = make_tmap_bf16_3d(&tmB0, final0, 64, pb.N, BH, 128, (uint64_t)pb.N * 128, 64, 64);
+    if (rc) return rc;
+    tmB1 = tmB0;
+    if (final1 && (rc = make_tmap_bf16_3d(&tmB1, final1, 64, pb.N, BH, 128, (uint64_t)pb.N * 128, 64, 64))) return rc;
   }
   static_assert(C::STAGES * C::STAGE_STRIDE >= 2 * 32768, "the epilogue stages one fp32 tile per warpgroup in the ring");
   auto kern = intra_kernel<MODE>;
@@ -549,24 +685,30 @@ static int launch_intra_t(const Problem& pb, int L, int Npad, const void* r1, co
           DS.strK[st][op][kk] = sm100::desc_kmajor_sw128_const(a) + kk * 2;
           DS.strMN[st][op][kk] = sm100::desc_mnmajor_sw128_const(a, 8192) + kk * 128;
         }
-    for (int kk = 0; kk < 4; ++kk)
-      DS.normK[kk] = sm100::desc_kmajor_sw128_const(base + C::RES_BYTES + C::STAGES * C::STAGE_STRIDE) + kk * 2;
+    for (int kk = 0; kk < 4; ++kk) {
+      const uint32_t na = base + C::RES_BYTES + C::STAGES * C::STAGE_STRIDE;
+      DS.normK[kk] = sm100::desc_kmajor_sw128_const(na) + kk * 2;
+      DS.normMN[kk] = sm100::desc_mnmajor_sw128_const(na, 8192) + kk * 128;
+    }
   }
-  FM_LAUNCH(name, pb.stream, kern<<<grid, 384, C::SMEM, pb.stream>>>(m[0], m[1], m[2], m[3], tmS, tmO0, tmO1, DS, P));
+  FM_LAUNCH(name, pb.stream, kern<<<grid, 384, C::SMEM, pb.stream>>>(m[0], m[1], m[2], m[3], tmS, tmO0, tmO1, tmB0, tmB1, DS, P));
   return FASTMAX_OK;
 }
 
 int intra_fwd(const Problem& pb, int L, int Npad, const void* q, const void* k, const void* v, float* o_part,
-              float* g, const uint8_t* state) {
-  return launch_intra_t<INTRA_FWD>(pb, L, Npad, q, nullptr, k, v, nullptr, o_part, nullptr, g, state, "mom_intra_fwd");
+              float* g, const uint8_t* state, void* o_final) {
+  return launch_intra_t<INTRA_FWD>(pb, L, Npad, q, nullptr, k, v, nullptr, o_part, nullptr, g, state, "mom_intra_fwd",
+                                   o_final);
 }
 int intra_dq(const Problem& pb, int L, int Npad, const void* q, const void* u, const void* k, const void* v,
-             const float* dlt, float* dq_part, const uint8_t* state) {
-  return launch_intra_t<INTRA_DQ>(pb, L, Npad, q, u, k, v, dlt, dq_part, nullptr, nullptr, state, "mom_intra_dq");
+             const float* dlt, float* dq_part, const uint8_t* state, void* dq_final) {
+  return launch_intra_t<INTRA_DQ>(pb, L, Npad, q, u, k, v, dlt, dq_part, nullptr, nullptr, state, "mom_intra_dq",
+                                  dq_final);
 }
 int intra_dkdv(const Problem& pb, int L, int Npad, const void* k, const void* v, const void* q, const void* u,
-               const float* dlt, float* dk_part, float* dv_part, const uint8_t* rstate) {
-  return launch_intra_t<INTRA_DKDV>(pb, L, Npad, k, v, q, u, dlt, dv_part, dk_part, nullptr, rstate, "mom_intra_dkdv");
+               const float* dlt, float* dk_part, float* dv_part, const uint8_t* rstate, void* dk_final, void* dv_final) {
+  return launch_intra_t<INTRA_DKDV>(pb, L, Npad, k, v, q, u, dlt, dv_part, dk_part, nullptr, rstate, "mom_intra_dkdv",
+                                    dv_final, dk_final);
 }
 
 }  // namespace fm

@@ -808,6 +808,8 @@ int moments_fwd(const Problem& pb, const void* q, const void* k, const void* v, 
   // 2. intra-segment part (causal only) and the normaliser
   // intra-segment scores + the normaliser (its moment part rides along as one more score MMA); non-causal:
   // only that MMA runs (no intra-segment part, no partial)
+  if (pb.p == 1)   // first order: the intra kernel applies the (single-slab) state term itself and writes o
+    return intra_fwd(pb, m.L, m.Npad, q, k, v, nullptr, g, state, o);
   if ((rc = intra_fwd(pb, m.L, m.Npad, q, k, v, pb.causal ? part : nullptr, g, state))) return rc;
   // 3. inter-segment part + normalisation
   ApplyParams ap{};
@@ -847,6 +849,10 @@ int moments_bwd(const Problem& pb, const void* q, const void* k, const void* v, 
   if ((rc = launch_build(pb, m, w8 + m.off_xt2, u, qd, R, 1, pb.sp_init_rev))) return rc;
   // 3. intra-segment partials
   // (non-causal: the same kernels only apply the normaliser column of the single state: dq_part, dk_part)
+  if (pb.p == 1) {   // first order: no apply kernels, no fp32 partials
+    if ((rc = intra_dq(pb, m.L, m.Npad, q, u, k, v, dlt, nullptr, S, dq))) return rc;
+    return intra_dkdv(pb, m.L, m.Npad, k, v, q, u, dlt, nullptr, nullptr, R, dk, dv);
+  }
   if ((rc = intra_dq(pb, m.L, m.Npad, q, u, k, v, dlt, dq_part, S))) return rc;
   if ((rc = intra_dkdv(pb, m.L, m.Npad, k, v, q, u, dlt, dk_part, pb.causal ? dv_part : nullptr, R))) return rc;
   // 4. inter-segment parts
