@@ -366,9 +366,22 @@ def main() -> None:
 
     # ---- e2e: host buffers in, host buffers out, copies inside the timed region ---------------
     if not args.no_e2e:
-        hq, hk, hv, hdo = (t.cpu().pin_memory() for t in (q, k, v, do))
-        outs = tuple(torch.empty_like(hq).pin_memory() for _ in range(4))
+        # 4 GiB of pinned host memory per rank; if any rank cannot get it, every rank skips the e2e leg
+        # together (the collectives below must stay matched) and the line says so
+        try:
+            hq, hk, hv, hdo = (t.cpu().pin_memory() for t in (q, k, v, do))
+            outs = tuple(torch.empty_like(hq).pin_memory() for _ in range(4))
+            have = 1
+        except RuntimeError:
+            have = 0
+        if world > 1:
+            t = torch.tensor([have], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            have = int(t.item())
         n_e2e = max(1, min(args.steps, 3))
+    if not args.no_e2e and not have:
+        out["e2e"] = {"value": None, "unit": UNIT, "error": "pinned host allocation failed on at least one rank"}
+    elif not args.no_e2e:
         for _ in range(2):
             fastmax_fwd_bwd_host(hq, hk, hv, hdo, out=outs, p=p, device=dev)
         barrier()
