@@ -463,17 +463,19 @@ constexpr int A_SMEM = A_RES_BYTES + A_STAGES * A_STAGE_BYTES + 1024 + 1024;
 constexpr int A_THREADS = 19 * 32;                       // 16 epilogue warps, 2 MMA issuers, TMA producer
 
 // Each token tile owns a private 128-column T buffer in tensor memory and its own barrier pair.
-// In-kernel cycle counters (-DFM_TIMING, tools/timing.py) at the headline shape, per CTA: 528 MMAs of
-// 128x128x16 take ~75-95 cycles each while the warpgroups read T out (64 in isolation), and the
-// read-out runs at ~2.6 cycles per 32-lane column per quadrant (1.3 in isolation): MMA accumulation
-// and tcgen05.ld share tensor-memory bandwidth, so the floor of this two-stage scheme is about the sum
-// of the two (~56k cycles per 512 tokens), not their maximum.
-// Measured alternatives (ms per apply launch): this layout 2.3 (additive terms read in the tail) -> see
-// bench; one converged constant-bank issuer that also feeds the TMA ring (17 warps) 2.9; two tiles per
-// CTA, eight warps per tile, two N=128 buffers per tile 3.5; two 64-column buffers per tile (N=64 MMAs
-// from shared memory cost 48 cycles instead of 32) 3.7; two shared N=256 T buffers with one issuer 2.6;
-// two tiles per CTA with a column-split epilogue 2.9; issuing from the epilogue warpgroups 3.2;
-// generated A operands in tensor memory 3.2-5.2.
+// In-kernel cycle counters (-DFM_TIMING, tools/timing.py) at the headline shape: per tile and slab pair
+// the chain  MMA (4 x 128x128x16 = 256 cycles) -> commit -> read-out of 128 columns (~1300 cycles: 16
+// warps share the tensor-memory read path at ~2.6 cycles per 32-lane column per quadrant) -> free  is
+// serial, because 512 columns are exactly four single buffers; tensor pipe ~45 % and read-out warps ~75 %
+// busy.  MMAs and tcgen05.ld do not slow each other (tools/contention.py), but a tcgen05.commit stalls
+// its issuing thread ~90 cycles (tools/multi_issue.py), which is why two issuer warps beat one.
+// Measured alternatives (ms per apply launch; this layout 2.3): one converged constant-bank issuer that
+// also feeds the TMA ring 2.9; register re-balance (setmaxnreg) with two read-out loads in flight 2.9;
+// two tiles per CTA, eight warps per tile, two N=128 buffers per tile, one issuer 3.5, two issuers 3.7
+// (the state is then streamed twice); two 64-column buffers per tile (N=64 MMAs from shared memory cost
+// 48 cycles instead of 32) 3.7; two shared N=256 T buffers with one issuer 2.6; two tiles per CTA with a
+// column-split epilogue 2.9; issuing from the epilogue warpgroups 3.2; generated A operands in tensor
+// memory 3.2-5.2.
 __global__ void __launch_bounds__(A_THREADS, 1)
 apply_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmY, const ApplyParams P) {
   extern __shared__ uint8_t smem_raw[];
