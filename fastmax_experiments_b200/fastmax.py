@@ -17,6 +17,9 @@ Behavioural notes:
   broken: quirk Q5).
 * Inputs must be CUDA tensors: there is no CPU or PyTorch fallback.  Output dtype = input
   dtype (fp32 or bf16); accumulation is always fp32; ``g`` is saved in fp32.
+* bf16 heads narrower than 64 (Pythia: 32) are zero-padded to 64 so that they run on the tcgen05
+  path (D = 64 kernels): zero features change neither the scores nor the normaliser, and the padded
+  output / gradient columns are exactly zero and sliced off.  ``c`` still uses the caller's D.
 """
 from __future__ import annotations
 
@@ -30,6 +33,7 @@ from . import _lib
 __all__ = ["fastmax", "fastattention_einops", "FastmaxFunction", "fastmax_fwd_raw", "fastmax_bwd_raw"]
 
 _DTYPES = {torch.float32: _lib.DTYPE_F32, torch.bfloat16: _lib.DTYPE_BF16}
+_TENSOR_PATH_D = 64      # head size of the tcgen05 kernels
 
 
 def _check_inputs(q, k, v):
@@ -116,6 +120,9 @@ class FastmaxFunction(torch.autograd.Function):
         c = 1.0 if tensors_normalized is True else normalize_term * math.sqrt(D)   # fastmax.py:79-82
         causal = mask is not False                                                 # fastmax.py:85
         q_, k_, v_ = q.contiguous(), k.contiguous(), v.contiguous()
+        pad = _TENSOR_PATH_D - D if (q.dtype == torch.bfloat16 and D < _TENSOR_PATH_D and q.shape[2] >= 256) else 0
+        if pad:
+            q_, k_, v_ = (torch.nn.functional.pad(t, (0, pad)) for t in (q_, k_, v_))
         saved = None
         if any(t.requires_grad for t in (q, k, v)):
             nb = saved_state_bytes(q_, causal, p)
@@ -123,15 +130,20 @@ class FastmaxFunction(torch.autograd.Function):
                 saved = torch.empty(nb, dtype=torch.uint8, device=q.device)
         o, g = fastmax_fwd_raw(q_, k_, v_, causal, 1.0 / c, p, saved=saved)
         ctx.save_for_backward(q_, k_, v_, o, g)                                    # fastmax.py:106
-        ctx.causal, ctx.inv_c, ctx.p, ctx.saved = causal, 1.0 / c, p, saved
-        return o
+        ctx.causal, ctx.inv_c, ctx.p, ctx.saved, ctx.pad = causal, 1.0 / c, p, saved, pad
+        return o[..., :D].contiguous() if pad else o
 
     @staticmethod
     def backward(ctx, o_grad):
         q, k, v, o, g = ctx.saved_tensors
         do = o_grad.to(q.dtype).contiguous()
+        if ctx.pad:
+            do = torch.nn.functional.pad(do, (0, ctx.pad))
         dq, dk, dv = fastmax_bwd_raw(q, k, v, o, g, do, ctx.causal, ctx.inv_c, ctx.p, saved=ctx.saved)
         ctx.saved = None
+        if ctx.pad:
+            D = q.shape[-1] - ctx.pad
+            dq, dk, dv = (t[..., :D].contiguous() for t in (dq, dk, dv))
         return dq, dk, dv, None, None, None, None, None, None                      # fastmax.py:182
 
 

@@ -269,3 +269,21 @@ def test_cuda_graph_capture_replays_the_step():
     ref = orc.dense_fwd_bwd(q.double().cpu(), k.double().cpu(), v.double().cpu(), do.double().cpu(), mask=True, p=2)
     for nm, x, r in zip(("o", "g", "dq", "dk", "dv"), outs, ref):
         assert orc.rel_err(x.double().cpu(), r) <= 2e-2, nm
+
+
+@pytest.mark.parametrize("shape", [(1, 4, 2048, 32), (2, 2, 2600, 32), (1, 2, 300, 48)], ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("causal", [True, False], ids=["causal", "full"])
+def test_narrow_bf16_heads_are_padded_onto_the_tensor_path(shape, causal):
+    """Pythia-sized heads (D = 32) in bf16 go through the public op zero-padded to the D = 64 tcgen05
+    kernels; outputs and gradients keep the caller's D and match the oracle."""
+    B, H, N, D = shape
+    gen = torch.Generator().manual_seed(77 + N + D)
+    q, k, v, do = (torch.randn(B, H, N, D, generator=gen).to(torch.bfloat16) for _ in range(4))
+    ref = orc.dense_fwd_bwd(q.double(), k.double(), v.double(), do.double(), mask=causal, p=2)
+    qc, kc, vc = (t.cuda().requires_grad_(True) for t in (q, k, v))
+    o = fm.fastmax(qc, kc, vc, mask=True if causal else False, p=2)
+    assert o.shape == (B, H, N, D) and o.dtype == torch.bfloat16
+    o.backward(do.cuda())
+    for nm, x, r in (("o", o, ref[0]), ("dq", qc.grad, ref[2]), ("dk", kc.grad, ref[3]), ("dv", vc.grad, ref[4])):
+        assert x.shape == (B, H, N, D)
+        assert orc.rel_err(x.double().cpu(), r) <= 2e-2, nm
