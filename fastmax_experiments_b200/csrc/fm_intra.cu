@@ -248,10 +248,10 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
     const uint32_t lane_addr = tmem + ((uint32_t)(32 * q) << 16);
     const uint32_t sbuf = lane_addr + 256 + 128 * w;      // score buffer of this warpgroup (128 cols)
     // output tiles of this warpgroup
-    int otile[2];
+    // (an expression, not an array: a dynamically indexed local array lives in local memory)
+    auto otile_of = [&](int x) { return intra_otile<MODE>(w, x); };
     int n_ot;
-    if (MODE == INTRA_DKDV) otile[0] = w, otile[1] = -1, n_ot = 1;
-    else otile[0] = w == 0 ? 0 : 1, otile[1] = w == 0 ? 3 : 2, n_ot = 2;
+    n_ot = MODE == INTRA_DKDV ? 1 : 2;
 
     const float a = P.a, c2 = P.p == 2 ? 0.5f * P.a * P.a : 0.f, a1 = P.p == 2 ? P.a : 0.f;
     float gsum[2] = {0.f, 0.f};
@@ -259,7 +259,7 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
     if constexpr (MODE == INTRA_DQ) {
 #pragma unroll
       for (int x = 0; x < 2; ++x) {
-        const int r = c0 + otile[x] * 128 + rloc;
+        const int r = c0 + otile_of(x) * 128 + rloc;
         dlt_row[x] = r < P.N ? P.dlt[(size_t)bh * P.Npad + r] : 0.f;
       }
     }
@@ -276,7 +276,7 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
 #pragma unroll
       for (int x = 0; x < 2; ++x) {
         if (x >= n_ot) break;
-        const int o = otile[x];
+        const int o = otile_of(x);
         const int ob = c0 + o * 128;                      // first row of the output tile
         // does output tile o interact with this stream tile?
         bool need;
@@ -411,7 +411,7 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
             for (int kk = 0; kk < 4; ++kk) umma_ss(sb + 64, DS.resK[C::OUT_TILES + w][kk], DS.normK[kk], IDK64, kk > 0);
           } else {
             for (int x = 0; x < 2; ++x) {
-              const int o = otile[x];
+              const int o = otile_of(x);
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk) {
                 if constexpr (MODE == INTRA_FWD) umma_ss(sb + 64 * x, DS.resK[o][kk], DS.normMN[kk], IDN64, kk > 0);
@@ -440,7 +440,7 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
 #pragma unroll
       for (int x = 0; x < 2; ++x) {
         if (x >= n_ot) break;
-        const int o = otile[x];
+        const int o = otile_of(x);
         const int ob = c0 + o * 128;
         const int r_abs = ob + rloc;
         if (ob >= P.N) continue;                               // uniform over the warpgroup
@@ -531,7 +531,7 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
 #pragma unroll
     for (int x = 0; x < 2; ++x) {
       if (x >= n_ot) break;
-      const int o = otile[x];
+      const int o = otile_of(x);
       const int r_abs = c0 + o * 128 + rloc;
       const bool tile_live = c0 + o * 128 < P.N;          // uniform over the warpgroup
       if (!tile_live) continue;
