@@ -17,6 +17,8 @@ Behavioural notes:
   broken: quirk Q5).
 * Inputs must be CUDA tensors: there is no CPU or PyTorch fallback.  Output dtype = input
   dtype (fp32 or bf16); accumulation is always fp32; ``g`` is saved in fp32.
+* ``mask=False`` accepts N_q != N_k (prefill / decode over the KV cache, model.py:478-487), forward
+  only, with the reference's count term N_q in the normaliser (fastmax.py:269-271, quirk Q2).
 * bf16 heads narrower than 64 (Pythia: 32) are zero-padded to 64 so that they run on the tcgen05
   path (D = 64 kernels): zero features change neither the scores nor the normaliser, and the padded
   output / gradient columns are exactly zero and sliced off.  ``c`` still uses the caller's D.
@@ -36,13 +38,16 @@ _DTYPES = {torch.float32: _lib.DTYPE_F32, torch.bfloat16: _lib.DTYPE_BF16}
 _TENSOR_PATH_D = 64      # head size of the tcgen05 kernels
 
 
-def _check_inputs(q, k, v):
+def _check_inputs(q, k, v, rect_ok=False):
     if not (q.is_cuda and k.is_cuda and v.is_cuda):
         raise _lib.FastmaxError("fastmax_experiments_b200.fastmax needs CUDA tensors "
                                 "(no CPU fallback; the CPU restatement lives in oracle/ for tests only)")
-    if q.dim() != 4 or q.shape != k.shape or q.shape != v.shape:
-        raise ValueError(f"q, k, v must share one (B, H, N, D) shape, got {tuple(q.shape)}, "
-                         f"{tuple(k.shape)}, {tuple(v.shape)}")
+    same = q.shape == k.shape
+    if rect_ok and q.dim() == 4 and k.dim() == 4:     # inference: N_q != N_k allowed
+        same = q.shape[:2] == k.shape[:2] and q.shape[3] == k.shape[3]
+    if q.dim() != 4 or not same or k.shape != v.shape:
+        raise ValueError(f"q, k, v must share one (B, H, N, D) shape (N_q may differ from N_k only with "
+                         f"mask=False), got {tuple(q.shape)}, {tuple(k.shape)}, {tuple(v.shape)}")
     if q.dtype not in _DTYPES or k.dtype != q.dtype or v.dtype != q.dtype:
         raise TypeError(f"q, k, v must all be float32 or all bfloat16, got {q.dtype}, {k.dtype}, {v.dtype}")
 
@@ -104,6 +109,34 @@ def fastmax_bwd_raw(q, k, v, o, g, do, causal: bool, inv_c: float, p: int, algo:
     return dq, dk, dv
 
 
+def _inference_rect(ctx, q, k, v, inv_c, p):
+    """Non-causal forward with N_q != N_k: what the dispatch does for prefill / decode over the KV cache
+    (model.py:478-487 with ``input_pos`` given).  The shorter side is zero-padded along the sequence --
+    zero keys carry zero values and only add to the count term, zero queries are sliced off -- and the
+    count term of the normaliser is set to N_q like the reference's (fastmax.py:269-271, quirk Q2).
+    Forward only: the reference's non-causal backward assumes one N as well."""
+    if any(ctx.needs_input_grad[:3]):
+        raise NotImplementedError("fastmax with N_q != N_k is an inference (forward-only) path")
+    Nq, Nk, D = q.shape[2], k.shape[2], q.shape[3]
+    F = torch.nn.functional
+    q_, k_, v_ = q.contiguous(), k.contiguous(), v.contiguous()
+    if Nq < Nk:
+        q_ = F.pad(q_, (0, 0, 0, Nk - Nq))
+    else:
+        k_, v_ = F.pad(k_, (0, 0, 0, Nq - Nk)), F.pad(v_, (0, 0, 0, Nq - Nk))
+    pad = _TENSOR_PATH_D - D if (q.dtype == torch.bfloat16 and D < _TENSOR_PATH_D and q_.shape[2] >= 256) else 0
+    if pad:
+        q_, k_, v_ = (F.pad(t, (0, pad)) for t in (q_, k_, v_))
+    o, g = fastmax_fwd_raw(q_, k_, v_, False, inv_c, p)
+    o = o[:, :, :Nq, :D]
+    if Nq < Nk:       # our count term is the padded length N_k; the reference's is N_q
+        g = g[:, :, :Nq]
+        o = (o.float() * (g / (g - float(Nk - Nq))).unsqueeze(-1)).to(q.dtype)
+    o = o.contiguous()
+    ctx.mark_non_differentiable(o)
+    return o
+
+
 class FastmaxFunction(torch.autograd.Function):
     """Autograd wrapper with the reference's nine-argument ``apply`` (fastmax.py:42-53)."""
 
@@ -115,10 +148,12 @@ class FastmaxFunction(torch.autograd.Function):
         if create_attn is not False:
             raise NotImplementedError("create_attn=True (dense debug path, fastmax.py:99-104) is not "
                                       "provided; its backward is broken in the reference as well")
-        _check_inputs(q, k, v)
+        causal = mask is not False                                                 # fastmax.py:85
+        _check_inputs(q, k, v, rect_ok=not causal)
         D = q.shape[-1]
         c = 1.0 if tensors_normalized is True else normalize_term * math.sqrt(D)   # fastmax.py:79-82
-        causal = mask is not False                                                 # fastmax.py:85
+        if q.shape[2] != k.shape[2]:
+            return _inference_rect(ctx, q, k, v, 1.0 / c, p)
         q_, k_, v_ = q.contiguous(), k.contiguous(), v.contiguous()
         pad = _TENSOR_PATH_D - D if (q.dtype == torch.bfloat16 and D < _TENSOR_PATH_D and q.shape[2] >= 256) else 0
         if pad:

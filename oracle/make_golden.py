@@ -45,6 +45,15 @@ CASES = [
 ]
 
 
+# inference shapes of the dispatch (model.py:478-481: input_pos given -> mask=False over the KV cache):
+# N_q != N_k, forward only.  (name, B, H, Nq, Nk, D, p, seed)
+RECT_CASES = [
+    ("p2_full_decode_d64",  1, 2,   1, 300, 64, 2, 21),
+    ("p2_full_prefill_d64", 2, 2,  40, 300, 64, 2, 22),
+    ("p1_full_prefill_d32", 1, 2,  17,  96, 32, 1, 23),
+]
+
+
 def bf16_round(x: torch.Tensor) -> torch.Tensor:
     return x.to(torch.bfloat16).to(torch.float32)
 
@@ -96,5 +105,25 @@ def main() -> None:
         print(f"{name}: wrote {os.path.getsize(path)/1e6:.2f} MB  |o|max={o.abs().max():.4f}")
 
 
+def main_rect() -> None:
+    sys.path.insert(0, REF_ROOT)
+    from attention_mechanisms.fastmax import fastmax as ref_fastmax  # the unmodified reference
+
+    for name, B, H, Nq, Nk, D, p, seed in RECT_CASES:
+        gen = torch.Generator().manual_seed(seed)
+        q = bf16_round(torch.randn(B, H, Nq, D, generator=gen))
+        k = bf16_round(torch.randn(B, H, Nk, D, generator=gen))
+        v = bf16_round(torch.randn(B, H, Nk, D, generator=gen))
+        with torch.no_grad():
+            o = ref_fastmax(q.double(), k.double(), v.double(), mask=False, p=p)
+        out = dict(B=B, H=H, Nq=Nq, Nk=Nk, D=D, p=p, q_bf16=bf16_bits(q), k_bf16=bf16_bits(k), v_bf16=bf16_bits(v),
+                   o=o.double().numpy())
+        path = os.path.join(OUT_DIR, name + ".npz")
+        np.savez_compressed(path, **out)
+        print(f"{name}: wrote {os.path.getsize(path)/1e6:.2f} MB  |o|max={o.abs().max():.4f}")
+
+
 if __name__ == "__main__":
-    main()
+    if "--rect-only" not in sys.argv:
+        main()
+    main_rect()

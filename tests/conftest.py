@@ -27,9 +27,29 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip)
 
 
-def golden_names():
+def _all_golden():
     return sorted(os.path.splitext(os.path.basename(p))[0]
                   for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+def golden_names():
+    """Square fixtures (q, k, v of one shape; forward + backward)."""
+    return [n for n in _all_golden() if "decode" not in n and "prefill" not in n]
+
+
+def golden_rect_names():
+    """Inference fixtures (N_q != N_k, non-causal, forward only)."""
+    return [n for n in _all_golden() if "decode" in n or "prefill" in n]
+
+
+def load_golden_rect(name: str) -> dict:
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    d = {k: z[k] for k in z.files}
+    out = dict(name=name, p=int(d["p"]), Nq=int(d["Nq"]), Nk=int(d["Nk"]), D=int(d["D"]))
+    for key in ("q", "k", "v"):
+        out[key] = _from_bf16_bits(d[key + "_bf16"])
+    out["o"] = torch.from_numpy(d["o"]).double()
+    return out
 
 
 def _from_bf16_bits(a: np.ndarray) -> torch.Tensor:

@@ -287,3 +287,33 @@ def test_narrow_bf16_heads_are_padded_onto_the_tensor_path(shape, causal):
     for nm, x, r in (("o", o, ref[0]), ("dq", qc.grad, ref[2]), ("dk", kc.grad, ref[3]), ("dv", vc.grad, ref[4])):
         assert x.shape == (B, H, N, D)
         assert orc.rel_err(x.double().cpu(), r) <= 2e-2, nm
+
+
+from conftest import golden_rect_names, load_golden_rect  # noqa: E402
+
+
+@pytest.mark.parametrize("name", golden_rect_names())
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_inference_shapes_match_reference(name, dtype):
+    """Prefill / decode over a KV cache (N_q != N_k, mask=False, forward only) against fixtures minted
+    from the unmodified reference, including its count term N_q."""
+    gd = load_golden_rect(name)
+    q, k, v = (gd[x].to("cuda", dtype) for x in ("q", "k", "v"))
+    with torch.no_grad():
+        o = fm.fastmax(q, k, v, mask=False, p=gd["p"])
+    assert o.shape == q.shape and o.dtype == dtype
+    assert orc.rel_err(o.double().cpu(), gd["o"]) <= TOL[dtype]
+    # and through the dispatch shim: input_pos given -> non-causal
+    from fastmax_experiments_b200.attention import fastmax_attention
+    with torch.no_grad():
+        o2 = fastmax_attention(q, k, v, input_pos=torch.arange(q.shape[2], device="cuda"), p=gd["p"])
+    assert orc.rel_err(o2.double(), o.double()) <= 2e-3      # (bf16 path: accumulation order varies per launch)
+
+
+def test_inference_shapes_reject_grad():
+    q = torch.randn(1, 1, 4, 64, device="cuda", requires_grad=True)
+    k = torch.randn(1, 1, 9, 64, device="cuda")
+    with pytest.raises(NotImplementedError):
+        fm.fastmax(q, k, k.clone(), mask=False, p=2)
+    with pytest.raises(ValueError):
+        fm.fastmax(q.detach(), k, k.clone(), mask=True, p=2)      # causal needs one N

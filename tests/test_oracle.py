@@ -3,7 +3,7 @@ minted from the unmodified reference, and the two restatements against each othe
 import pytest
 import torch
 
-from conftest import golden_names, load_golden
+from conftest import golden_names, golden_rect_names, load_golden, load_golden_rect
 from oracle import fastmax_oracle as orc
 
 NAMES = golden_names()
@@ -68,3 +68,12 @@ def test_invalid_p_raises_in_backward():
     q = torch.randn(1, 1, 4, 4, dtype=torch.float64)
     with pytest.raises(ValueError):
         orc.factorised_backward(q, q, q, q, torch.ones(1, 1, 4, dtype=torch.float64), q, p=3)
+
+
+@pytest.mark.parametrize("name", golden_rect_names())
+def test_oracle_matches_reference_on_inference_shapes(name):
+    """N_q != N_k, non-causal (the dispatch's KV-cache path, model.py:478-481): the restatement keeps the
+    reference's count term N_q (fastmax.py:269-271)."""
+    gd = load_golden_rect(name)
+    o, _ = orc.factorised_forward(gd["q"].double(), gd["k"].double(), gd["v"].double(), mask=False, p=gd["p"])
+    assert orc.rel_err(o, gd["o"]) <= 1e-12
