@@ -14,7 +14,10 @@ branches are
 transpose heads and time before that reshape; that is the dispatch's behaviour, not the op's, and
 it is left to the caller) -- but stays on the GPU: no host round trip, hand-written sm_100a kernels.
 
-``patch_causal_self_attention(cls)`` rebinds the two methods on a lit_gpt-style class so an
+``linearmax_attention`` does the same for ``CausalSelfAttention.linearmax`` (model.py:460-472,
+``attention_mechanisms/fastmax_hack.py``: first-order FastMax with c = 1 behind a q,k normalisation).
+
+``patch_causal_self_attention(cls)`` rebinds the three methods on a lit_gpt-style class so an
 unmodified ``lit_gpt.model.GPT`` picks the CUDA path up.
 """
 from __future__ import annotations
@@ -24,8 +27,9 @@ from typing import Optional
 import torch
 
 from .fastmax import fastmax
+from .linearmax import linearmax
 
-__all__ = ["fastmax_attention", "linearmax_not_provided", "patch_causal_self_attention"]
+__all__ = ["fastmax_attention", "linearmax_attention", "patch_causal_self_attention"]
 
 
 def fastmax_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor,
@@ -59,10 +63,16 @@ def patch_causal_self_attention(cls) -> type:
             raise TypeError(f"{cls!r} does not look like lit_gpt.model.CausalSelfAttention")
     cls.fastmax = _method_fastmax
     cls.fastmax_cuda = _method_fastmax_cuda
+    cls.linearmax = _method_linearmax
     return cls
 
 
-def linearmax_not_provided(*_a, **_k):
-    """``attn_alg='linearmax'`` (fastmax_hack.py) is a different op (q/k mean-centring + global
-    max-norm prologue, no custom backward) and out of scope."""
-    raise NotImplementedError("linearmax / fastmax_hack is not part of the B200 hot path")
+def linearmax_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor,
+                        input_pos: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Mirror of ``CausalSelfAttention.linearmax(self, q, k, v, input_pos)`` (model.py:460-472):
+    ``fastmax_hack(q, k, v, p=1, mask=input_pos is None)``."""
+    return linearmax(q, k, v, p=1, mask=input_pos is None)
+
+
+def _method_linearmax(self, q, k, v, input_pos):         # bound as CausalSelfAttention.linearmax
+    return linearmax_attention(q, k, v, input_pos)

@@ -299,3 +299,22 @@ def rel_err(x: torch.Tensor, ref: torch.Tensor, floor: float = 1e-300) -> float:
     x = x.detach().double().cpu()
     ref = ref.detach().double().cpu()
     return float((x - ref).abs().max() / ref.abs().max().clamp_min(floor))
+
+
+def linearmax_prologue(q, k):
+    """q, k normalisation of fastmax_hack.py (non-causal :9-15, causal :41-46, identical): subtract the
+    per-token mean over features, then divide by the largest token norm of the (b,h) sequence."""
+    q = q - q.mean(dim=3, keepdim=True)
+    k = k - k.mean(dim=3, keepdim=True)
+    qn = torch.linalg.norm(q, dim=3).amax(dim=2)[:, :, None, None]
+    kn = torch.linalg.norm(k, dim=3).amax(dim=2)[:, :, None, None]
+    return q / qn, k / kn
+
+
+def linearmax_forward(q, k, v, mask=True):
+    """fastmax_hack(q, k, v, p=1, mask) (fastmax_hack.py:5-60): the prologue above, then first-order
+    FastMax with c = 1 (normalize_term = 1, :48; denum_term = 1, :9).  Differentiable with torch autograd,
+    like the reference (which has no custom backward here)."""
+    qn, kn = linearmax_prologue(q, k)
+    o, _ = factorised_forward(qn, kn, v, mask, normalize_term=1, tensors_normalized=True, p=1)
+    return o

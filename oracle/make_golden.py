@@ -54,6 +54,15 @@ RECT_CASES = [
 ]
 
 
+# linearmax (attention_mechanisms/fastmax_hack.py, dispatched at model.py:444-445,460-472): p=1, c=1 after a
+# mean-centre / global-max-norm prologue on q,k; autograd through torch.  (name, B, H, N, D, mask, seed)
+LINEARMAX_CASES = [
+    ("linearmax_causal_d64", 2, 2, 130, 64, True, 31),
+    ("linearmax_full_d64",   1, 2,  96, 64, False, 32),
+    ("linearmax_causal_d32", 1, 3,  70, 32, True, 33),
+]
+
+
 def bf16_round(x: torch.Tensor) -> torch.Tensor:
     return x.to(torch.bfloat16).to(torch.float32)
 
@@ -123,7 +132,30 @@ def main_rect() -> None:
         print(f"{name}: wrote {os.path.getsize(path)/1e6:.2f} MB  |o|max={o.abs().max():.4f}")
 
 
+def main_linearmax() -> None:
+    sys.path.insert(0, REF_ROOT)
+    from attention_mechanisms.fastmax_hack import fastmax_hack as ref_linearmax  # the unmodified reference
+
+    for name, B, H, N, D, mask, seed in LINEARMAX_CASES:
+        gen = torch.Generator().manual_seed(seed)
+        q, k, v, do = (bf16_round(torch.randn(B, H, N, D, generator=gen)) for _ in range(4))
+        qq, kk, vv = (t.double().clone().requires_grad_(True) for t in (q, k, v))
+        o = ref_linearmax(qq, kk, vv, p=1, mask=mask)
+        o.backward(do.double())
+        out = dict(B=B, H=H, N=N, D=D, mask=mask, q_bf16=bf16_bits(q), k_bf16=bf16_bits(k), v_bf16=bf16_bits(v),
+                   do_bf16=bf16_bits(do), o=o.detach().numpy(), dq=qq.grad.numpy(), dk=kk.grad.numpy(),
+                   dv=vv.grad.numpy())
+        path = os.path.join(OUT_DIR, name + ".npz")
+        np.savez_compressed(path, **out)
+        print(f"{name}: wrote {os.path.getsize(path)/1e6:.2f} MB  |o|max={o.abs().max():.4f}")
+
+
 if __name__ == "__main__":
-    if "--rect-only" not in sys.argv:
+    only = [a for a in sys.argv[1:] if a.startswith("--only=")]
+    which = only[0].split("=")[1] if only else "all"
+    if which in ("all", "square"):
         main()
-    main_rect()
+    if which in ("all", "rect") or "--rect-only" in sys.argv:
+        main_rect()
+    if which in ("all", "linearmax"):
+        main_linearmax()

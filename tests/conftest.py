@@ -34,12 +34,28 @@ def _all_golden():
 
 def golden_names():
     """Square fixtures (q, k, v of one shape; forward + backward)."""
-    return [n for n in _all_golden() if "decode" not in n and "prefill" not in n]
+    return [n for n in _all_golden() if "decode" not in n and "prefill" not in n and not n.startswith("linearmax")]
 
 
 def golden_rect_names():
     """Inference fixtures (N_q != N_k, non-causal, forward only)."""
     return [n for n in _all_golden() if "decode" in n or "prefill" in n]
+
+
+def golden_linearmax_names():
+    """linearmax fixtures (fastmax_hack.py: forward + torch-autograd gradients)."""
+    return [n for n in _all_golden() if n.startswith("linearmax")]
+
+
+def load_golden_linearmax(name: str) -> dict:
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    d = {k: z[k] for k in z.files}
+    out = dict(name=name, mask=bool(d["mask"]))
+    for key in ("q", "k", "v", "do"):
+        out[key] = _from_bf16_bits(d[key + "_bf16"])
+    for key in ("o", "dq", "dk", "dv"):
+        out[key] = torch.from_numpy(d[key]).double()
+    return out
 
 
 def load_golden_rect(name: str) -> dict:

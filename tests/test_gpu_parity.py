@@ -317,3 +317,21 @@ def test_inference_shapes_reject_grad():
         fm.fastmax(q, k, k.clone(), mask=False, p=2)
     with pytest.raises(ValueError):
         fm.fastmax(q.detach(), k, k.clone(), mask=True, p=2)      # causal needs one N
+
+
+from conftest import golden_linearmax_names, load_golden_linearmax  # noqa: E402
+
+
+@pytest.mark.parametrize("name", golden_linearmax_names())
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_linearmax_matches_reference(name, dtype):
+    """attn_alg="linearmax" (fastmax_hack.py): torch prologue + the p = 1 CUDA path, forward and backward,
+    against fixtures minted from the unmodified reference."""
+    from fastmax_experiments_b200 import linearmax
+    gd = load_golden_linearmax(name)
+    q, k, v = (gd[x].to("cuda", dtype).requires_grad_(True) for x in ("q", "k", "v"))
+    o = linearmax(q, k, v, p=1, mask=gd["mask"])
+    assert o.dtype == dtype and o.shape == q.shape
+    o.backward(gd["do"].to("cuda", dtype))
+    for nm, x in (("o", o), ("dq", q.grad), ("dk", k.grad), ("dv", v.grad)):
+        assert orc.rel_err(x.double().cpu(), gd[nm]) <= TOL[dtype], (name, nm)

@@ -3,7 +3,8 @@ minted from the unmodified reference, and the two restatements against each othe
 import pytest
 import torch
 
-from conftest import golden_names, golden_rect_names, load_golden, load_golden_rect
+from conftest import (golden_linearmax_names, golden_names, golden_rect_names, load_golden, load_golden_linearmax,
+                      load_golden_rect)
 from oracle import fastmax_oracle as orc
 
 NAMES = golden_names()
@@ -77,3 +78,14 @@ def test_oracle_matches_reference_on_inference_shapes(name):
     gd = load_golden_rect(name)
     o, _ = orc.factorised_forward(gd["q"].double(), gd["k"].double(), gd["v"].double(), mask=False, p=gd["p"])
     assert orc.rel_err(o, gd["o"]) <= 1e-12
+
+
+@pytest.mark.parametrize("name", golden_linearmax_names())
+def test_oracle_linearmax_matches_reference(name):
+    """fastmax_hack.py (attn_alg="linearmax"): prologue + first-order FastMax with c = 1, gradients by autograd."""
+    gd = load_golden_linearmax(name)
+    q, k, v = (gd[x].double().requires_grad_(True) for x in ("q", "k", "v"))
+    o = orc.linearmax_forward(q, k, v, mask=gd["mask"])
+    o.backward(gd["do"].double())
+    for nm, x in (("o", o.detach()), ("dq", q.grad), ("dk", k.grad), ("dv", v.grad)):
+        assert orc.rel_err(x, gd[nm]) <= 1e-10, nm
