@@ -50,15 +50,26 @@ def fastmax_fwd_bwd_host(q, k, v, do, out=None, mask=True, normalize_term=8, ten
     dev = torch.device(device)
     if out is None:
         out = tuple(torch.empty_like(q).pin_memory() for _ in range(4))
-    chunks = min(B, chunks or B)
-    bounds = [(i * B // chunks, (i + 1) * B // chunks) for i in range(chunks)]
+    # (b,h) units are independent: slice the flattened (B*H) axis, so the pipeline has enough stages to
+    # hide its fill and drain (one slice of H2D before, one of D2H after the overlapped part) even at small B
+    BH = B * H
+    flat = all(t.is_contiguous() for t in (q, k, v, do) + tuple(out))
+    if flat:
+        q, k, v, do = (t.view(BH, 1, N, D) for t in (q, k, v, do))
+        out_v = tuple(t.view(BH, 1, N, D) for t in out)
+        units = BH
+    else:
+        out_v, units = out, B
+    chunks = max(1, min(units, chunks or 16))
+    bounds = [(i * units // chunks, (i + 1) * units // chunks) for i in range(chunks)]
     s_in, s_cmp, s_out = _streams(dev)
     ev_in = [torch.cuda.Event() for _ in bounds]
     ev_cmp = [torch.cuda.Event() for _ in bounds]
     keep = []
     for i, (b0, b1) in enumerate(bounds):
         with torch.cuda.stream(s_in):
-            dq_, dk_, dv_, ddo = (t[b0:b1].to(dev, non_blocking=True) for t in (q, k, v, do))
+            # (.to() keeps a strided host view's strides; the kernels take dense (B,H,N,D))
+            dq_, dk_, dv_, ddo = (t[b0:b1].to(dev, non_blocking=True).contiguous() for t in (q, k, v, do))
             ev_in[i].record(s_in)
         with torch.cuda.stream(s_cmp):
             s_cmp.wait_event(ev_in[i])
@@ -69,7 +80,7 @@ def fastmax_fwd_bwd_host(q, k, v, do, out=None, mask=True, normalize_term=8, ten
             ev_cmp[i].record(s_cmp)
         with torch.cuda.stream(s_out):
             s_out.wait_event(ev_cmp[i])
-            for dst, src in zip(out, (o, gq, gk, gv)):
+            for dst, src in zip(out_v, (o, gq, gk, gv)):
                 dst[b0:b1].copy_(src, non_blocking=True)
         keep.append((dq_, dk_, dv_, ddo, o, g, gq, gk, gv, saved))   # keep alive until the streams drain
     s_out.synchronize()
