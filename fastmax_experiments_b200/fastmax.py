@@ -72,13 +72,21 @@ def saved_state_bytes(q, causal: bool, p: int, algo: int = _lib.ALGO_AUTO) -> in
     return _lib.load().fastmax_saved_state_bytes(B, H, N, D, p, int(causal), _DTYPES[q.dtype], algo)
 
 
+def _require_dense(**tensors):
+    """The C ABI takes dense (B,H,N,D) buffers: a strided view would be read as if it were dense."""
+    for name, t in tensors.items():
+        if not t.is_contiguous():
+            raise ValueError(f"{name} must be contiguous (got strides {tuple(t.stride())} for shape {tuple(t.shape)})")
+
+
 def fastmax_fwd_raw(q, k, v, causal: bool, inv_c: float, p: int, algo: int = _lib.ALGO_AUTO, saved=None):
     """One call of the C ABI ``fastmax_fwd`` (``fastmax_fwd_ex`` when ``saved`` is a state buffer) on
     contiguous (B,H,N,D) CUDA tensors -> (o, g)."""
     lib = _lib.load()
+    _require_dense(q=q, k=k, v=v)
     B, H, N, D = q.shape
     dt = _DTYPES[q.dtype]
-    o = torch.empty_like(q)
+    o = torch.empty(q.shape, dtype=q.dtype, device=q.device)
     g = torch.empty(B, H, N, dtype=torch.float32, device=q.device)
     nbytes = lib.fastmax_fwd_workspace_bytes(B, H, N, D, p, int(causal), dt, algo)
     ws = _workspace(nbytes, q.device)
@@ -94,9 +102,10 @@ def fastmax_fwd_raw(q, k, v, causal: bool, inv_c: float, p: int, algo: int = _li
 def fastmax_bwd_raw(q, k, v, o, g, do, causal: bool, inv_c: float, p: int, algo: int = _lib.ALGO_AUTO, saved=None):
     """One call of the C ABI ``fastmax_bwd`` (``fastmax_bwd_ex`` with kept states) -> (dq, dk, dv)."""
     lib = _lib.load()
+    _require_dense(q=q, k=k, v=v, o=o, g=g, do=do)
     B, H, N, D = q.shape
     dt = _DTYPES[q.dtype]
-    dq, dk, dv = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
+    dq, dk, dv = (torch.empty(q.shape, dtype=q.dtype, device=q.device) for _ in range(3))
     nbytes = lib.fastmax_bwd_workspace_bytes(B, H, N, D, p, int(causal), dt, algo)
     ws = _workspace(nbytes, q.device)
     with torch.cuda.device(q.device):

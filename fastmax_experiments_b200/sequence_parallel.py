@@ -20,6 +20,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
+from .fastmax import _require_dense
 
 __all__ = ["partition", "exchange_states", "fastmax_sp", "FastmaxSPFunction", "sp_local_state",
            "sp_local_state_rev", "sp_reduce", "sp_fwd", "sp_bwd"]
@@ -45,6 +46,7 @@ def _ws(nbytes, dev):
 # ---- thin wrappers over the C ABI (one call each) -------------------------------------------------
 def sp_local_state(k, v, p: int) -> torch.Tensor:
     lib = _lib.load()
+    _require_dense(k=k, v=v)
     B, H, N, D = k.shape
     out = torch.empty(lib.fastmax_sp_state_bytes(B, H), dtype=torch.uint8, device=k.device)
     nb = lib.fastmax_sp_local_state_workspace_bytes(B, H, N, 0)
@@ -58,6 +60,7 @@ def sp_local_state(k, v, p: int) -> torch.Tensor:
 
 def sp_local_state_rev(q, o, g, do, p: int) -> torch.Tensor:
     lib = _lib.load()
+    _require_dense(q=q, o=o, g=g, do=do)
     B, H, N, D = q.shape
     out = torch.empty(lib.fastmax_sp_state_bytes(B, H), dtype=torch.uint8, device=q.device)
     nb = lib.fastmax_sp_local_state_workspace_bytes(B, H, N, 1)

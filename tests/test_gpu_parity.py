@@ -178,7 +178,8 @@ def test_kept_forward_states_match_rebuilt():
     saved = torch.empty(nb, dtype=torch.uint8, device="cuda")
     o1, g1 = fastmax_fwd_raw(q, k, v, True, inv_c, 2, _lib.ALGO_MOMENTS, saved=saved)
     o0, g0 = fastmax_fwd_raw(q, k, v, True, inv_c, 2, _lib.ALGO_MOMENTS)
-    assert orc.rel_err(o1.double(), o0.double()) <= 1e-3 and orc.rel_err(g1.double(), g0.double()) <= 1e-5
+    # (one bf16 ulp at the largest element is 4e-3)
+    assert orc.rel_err(o1.double(), o0.double()) <= 1e-2 and orc.rel_err(g1.double(), g0.double()) <= 1e-5
     a = fastmax_bwd_raw(q, k, v, o1, g1, do, True, inv_c, 2, _lib.ALGO_MOMENTS, saved=saved)
     b = fastmax_bwd_raw(q, k, v, o0, g0, do, True, inv_c, 2, _lib.ALGO_MOMENTS)
     qq, kk, vv = (t.clone().requires_grad_(True) for t in (q, k, v))
@@ -186,8 +187,8 @@ def test_kept_forward_states_match_rebuilt():
     ref = orc.dense_fwd_bwd(q.double().cpu(), k.double().cpu(), v.double().cpu(), do.double().cpu(),
                             mask=True, p=2)[-3:]
     for x, y, z, r in zip(a, b, (qq.grad, kk.grad, vv.grad), ref):
-        assert orc.rel_err(x.double(), y.double()) <= 2e-3
-        assert orc.rel_err(z.double(), y.double()) <= 2e-3
+        assert orc.rel_err(x.double(), y.double()) <= 1e-2
+        assert orc.rel_err(z.double(), y.double()) <= 1e-2
         assert orc.rel_err(x.double().cpu(), r) <= 2e-2
 
 
@@ -307,7 +308,8 @@ def test_inference_shapes_match_reference(name, dtype):
     from fastmax_experiments_b200.attention import fastmax_attention
     with torch.no_grad():
         o2 = fastmax_attention(q, k, v, input_pos=torch.arange(q.shape[2], device="cuda"), p=gd["p"])
-    assert orc.rel_err(o2.double(), o.double()) <= 2e-3      # (bf16 path: accumulation order varies per launch)
+    # (bf16 path: accumulation order varies per launch, and one bf16 ulp at the largest element is 4e-3)
+    assert orc.rel_err(o2.double(), o.double()) <= 1e-2
 
 
 def test_inference_shapes_reject_grad():
@@ -354,3 +356,9 @@ def test_host_buffer_entry_matches_oracle(contig):
     for nm, x, r in (("o", o, ref[0]), ("dq", dq, ref[2]), ("dk", dk, ref[3]), ("dv", dv, ref[4])):
         assert not x.is_cuda and x.shape == (B, H, N, D)
         assert orc.rel_err(x.double(), r) <= 2e-2, nm
+
+
+def test_raw_entry_rejects_strided_views():
+    q = torch.randn(1, 64, 2, 64, device="cuda").transpose(1, 2)      # (1, 2, 64, 64) view, not dense
+    with pytest.raises(ValueError):
+        fastmax_fwd_raw(q, q, q, True, 1.0 / 64, 2)
