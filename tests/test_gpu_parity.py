@@ -362,3 +362,17 @@ def test_raw_entry_rejects_strided_views():
     q = torch.randn(1, 64, 2, 64, device="cuda").transpose(1, 2)      # (1, 2, 64, 64) view, not dense
     with pytest.raises(ValueError):
         fastmax_fwd_raw(q, q, q, True, 1.0 / 64, 2)
+
+
+def test_inference_shape_with_more_queries_than_keys():
+    """N_q > N_k (not produced by the reference's dispatch, but accepted by its op): keys are padded instead
+    of queries; checked against the oracle restatement, which keeps the count term N_q."""
+    gen = torch.Generator().manual_seed(41)
+    q = torch.randn(1, 2, 90, 64, generator=gen).to(torch.bfloat16)
+    k, v = (torch.randn(1, 2, 33, 64, generator=gen).to(torch.bfloat16) for _ in range(2))
+    ref, _ = orc.factorised_forward(q.double(), k.double(), v.double(), mask=False, p=2)
+    with torch.no_grad():
+        o32 = fm.fastmax(q.cuda().float(), k.cuda().float(), v.cuda().float(), mask=False, p=2)
+        o16 = fm.fastmax(q.cuda(), k.cuda(), v.cuda(), mask=False, p=2)
+    assert orc.rel_err(o32.double().cpu(), ref) <= 1e-4
+    assert orc.rel_err(o16.double().cpu(), ref) <= 2e-2
