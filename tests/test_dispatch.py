@@ -26,6 +26,7 @@ def test_patch_rebinds_methods():
     assert FakeCSA.fastmax is attention._method_fastmax
     assert list(inspect.signature(FakeCSA.fastmax).parameters) == ["self", "q", "k", "v", "input_pos"]
     assert list(inspect.signature(FakeCSA.fastmax_cuda).parameters) == ["self", "q", "k", "v"]
+    assert list(inspect.signature(FakeCSA.linearmax).parameters) == ["self", "q", "k", "v", "input_pos"]
     with pytest.raises(TypeError):
         attention.patch_causal_self_attention(object)
 
@@ -37,6 +38,8 @@ def test_reference_method_signatures_match():
     assert "def fastmax(\n        self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, input_pos: torch.Tensor" in src
     assert "def fastmax_cuda(\n        self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor\n" in src
     assert "o = fastmax(q, k, v, p=2, mask=mask)" in src
+    assert "def linearmax(\n        self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, input_pos: torch.Tensor" in src
+    assert "o = fastmax_hack(q, k, v, p=1, mask=mask)" in src
 
 
 def test_compat_rejects_undefined_extras():
