@@ -487,9 +487,9 @@ apply_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CU
   uint64_t* empty = bars + 6;       // [6] slab pair consumed by the MMAs of all four tiles (count 2: one per issuer)
   uint64_t* t_full = bars + 12;     // [4] T tile of (slab pair, tile t) is in tensor memory
   uint64_t* t_free = bars + 16;     // [4] ... and has been read out by warpgroup t (count 4: one per warp)
-  uint64_t* res_full = bars + 20;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
-  float* vec_s = reinterpret_cast<float*>(bars + 24);  // [64]
+  uint64_t* res_full = bars + 20;    // [4] resident Y tile t landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  float* vec_s = reinterpret_cast<float*>(bars + 26);  // [64]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int bh = blockIdx.y;
@@ -507,7 +507,7 @@ apply_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CU
   if (tid == 0) {
     for (int i = 0; i < A_STAGES; ++i) mbar_init(&full[i], 1), mbar_init(&empty[i], 2);
     for (int i = 0; i < 4; ++i) mbar_init(&t_full[i], 1), mbar_init(&t_free[i], 4);
-    mbar_init(res_full, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&res_full[i], 1);
     fence_barrier_init();
     tma_prefetch_desc(&tmS);
     tma_prefetch_desc(&tmY);
@@ -526,9 +526,13 @@ apply_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CU
   if (warp == 18) {
     // ---------------------------------------------------------------- TMA producer
     if (lane == 0 && has_state) {
-      mbar_arrive_expect_tx(res_full, A_RES_BYTES);
-      for (int t = 0; t < 4; ++t)
-        for (int h = 0; h < 2; ++h) tma_load_3d(res + t * 16384 + h * 8192, &tmY, res_full, 0, t0 + t * 128 + h * 64, bh);
+      // operands of the very first MMAs first: Y tile 0, slab pair 0, then the other tiles
+      auto load_tile = [&](int t) {
+        mbar_arrive_expect_tx(&res_full[t], 16384);
+        for (int h = 0; h < 2; ++h)
+          tma_load_3d(res + t * 16384 + h * 8192, &tmY, &res_full[t], 0, t0 + t * 128 + h * 64, bh);
+      };
+      load_tile(0);
       for (int gi = 0; gi < ngroups; ++gi) {
         const int st = gi % A_STAGES, ph = (gi / A_STAGES) & 1;
         const bool last = gi == ngroups - 1;
@@ -541,6 +545,8 @@ apply_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CU
           tma_load_3d(dst, &tmS, &full[st], 0, (2 * gi) * 64, rec_idx);
           tma_load_3d(dst + 8192, &tmS, &full[st], 0, (2 * gi + 1) * 64, rec_idx);
         }
+        if (gi == 0)
+          for (int t = 1; t < 4; ++t) load_tile(t);
       }
     }
   } else if (warp >= 16) {
@@ -551,7 +557,6 @@ apply_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CU
       const uint32_t id128 = make_idesc_bf16(128, 128, false, !P.b_kmajor);
       const uint32_t id64 = make_idesc_bf16(128, 64, false, !P.b_kmajor);
       const uint32_t kstep = P.b_kmajor ? 2 : 128;
-      mbar_wait(res_full, 0);
       for (int gi = 0; gi < ngroups; ++gi) {
         const int st = gi % A_STAGES;
         const bool last = gi == ngroups - 1;
@@ -563,6 +568,7 @@ apply_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CU
         for (int tt = 0; tt < 2; ++tt) {
           const int t = tb + tt;
           if (gi > 0) mbar_wait(&t_free[t], (gi - 1) & 1, 3000 + gi);
+          else mbar_wait(&res_full[t], 0, 5000 + t);
           tc_fence_after();
           const uint64_t ad = desc_kmajor_sw128(smem_u32(res + t * 16384));
 #pragma unroll
