@@ -187,7 +187,6 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
     tma_prefetch_desc(&tmR1);
     tma_prefetch_desc(&tmT1);
     tma_prefetch_desc(&tmT2);
-    tma_prefetch_desc(&tmO0);
   }
   // fp32 vector part of the boundary state ([0,64): S0 / R0, [64,128): N1 / RN1), read by every epilogue row
   float* vec_s = reinterpret_cast<float*>(norm_s + 8192);
@@ -523,7 +522,7 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
     // Written through shared memory with bulk tensor stores: a thread owns a 256-byte output row, so
     // storing from registers means 16-byte pieces at a 256-byte stride (measured: a third of the CTA's
     // time).  Once both warpgroups' MMAs are complete the stream ring is free; each warpgroup stages one
-    // 128x64 fp32 tile there (two 128-byte-swizzled halves of 32 columns) and one thread sends it.
+    // 128x64 fp32 tile there in the blocked partial layout and one thread sends it as a 32 KiB bulk copy.
     asm volatile("bar.sync 3, 256;" ::: "memory");
     uint8_t* stg = ring + w * 32768;
     const bool storer = q == 0 && lane == 0;
@@ -591,20 +590,20 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
             }
           }
           tmem_wait_ld();
-          if (store) {
-            const uint32_t dst = smem_u32(stg) + h * 16384 + rloc * 128;
+          if (store) {   // staging in the partial's own layout [c4][row] (fm_moments.cuh): conflict-free 512-byte rows
+            const uint32_t dst = smem_u32(stg) + (uint32_t)(8 * h) * 2048 + rloc * 16;
 #pragma unroll
             for (int c4 = 0; c4 < 8; ++c4)
-              sts128(dst + ((uint32_t)(c4 ^ (rloc & 7)) << 4), v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+              sts128(dst + c4 * 2048, v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
           }
         }
         if (!store) continue;
         fence_proxy_async();
         asm volatile("bar.sync %0, 128;" ::"r"(1 + w) : "memory");
-        if (storer) {
-          const CUtensorMap* tm = a2 == 0 ? &tmO0 : &tmO1;
-          tma_store_3d(tm, stg, 0, c0 + o * 128, bh);          // rows past N are clipped by the tensor map
-          tma_store_3d(tm, stg + 16384, 32, c0 + o * 128, bh);
+        if (storer) {   // one contiguous 32 KiB block per tile (the buffer is padded to whole tiles)
+          float* outp = a2 == 0 ? P.out0 : P.out1;
+          const size_t tile = (size_t)bh * ((P.N + 127) / 128) + (size_t)(c0 / 128 + o);
+          bulk_store_1d(outp + tile * PART_TILE_FLOATS, stg, 32768);
           bulk_commit_group();
         }
         ++nstored;
@@ -652,15 +651,7 @@ static int launch_intra_t(const Problem& pb, int L, int Npad, const void* r1, co
     int rc = make_tmap_bf16_3d(&tmS, state, 64, NSLAB * 64, (uint64_t)BH * P.nseg, 128, REC_BYTES, 64, 64);
     if (rc) return rc;
   }
-  CUtensorMap tmO0, tmO1;
-  {
-    int rc = FASTMAX_OK;
-    if (out0 || out1) rc = make_tmap_f32_3d(&tmO0, out0 ? out0 : out1, 64, pb.N, BH, 256, (uint64_t)pb.N * 256, 32, 128);
-    else tmO0 = m[0];   // p = 1 fused: no fp32 partials
-    if (rc) return rc;
-    tmO1 = tmO0;
-    if (out1 && (rc = make_tmap_f32_3d(&tmO1, out1, 64, pb.N, BH, 256, (uint64_t)pb.N * 256, 32, 128))) return rc;
-  }
+  CUtensorMap tmO0 = m[0], tmO1 = m[0];   // (fp32 partials are plain bulk copies now; parameters kept for layout stability)
   CUtensorMap tmB0 = tmO0, tmB1 = tmO0;
   if (P.fused) {
     int rc = make_tmap_bf16_3d(&tmB0, final0, 64, pb.N, BH, 128, (uint64_t)pb.N * 128, 64, 64);

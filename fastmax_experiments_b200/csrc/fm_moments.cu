@@ -589,10 +589,15 @@ apply_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CU
     // wait for the first T tile and the tail is stores only (the tail read cost 15 % of the CTA time)
     float O[64];
     {
-      const float4* part = (valid && P.partial) ? reinterpret_cast<const float4*>(P.partial + grow * 64) : nullptr;
+      // blocked partial layout (fm_moments.cuh): [tile][c4][row] float4, 512 contiguous bytes per warp and load
+      const float4* part = nullptr;
+      if (P.partial)
+        part = reinterpret_cast<const float4*>(P.partial + ((size_t)bh * ((P.N + 127) / 128) + (size_t)(t0 / 128 + t)) *
+                                                               PART_TILE_FLOATS) + (32 * q + lane);
+      if (t0 + 128 * t >= P.N) part = nullptr;    // tile beyond the sequence
 #pragma unroll
       for (int c4 = 0; c4 < 16; ++c4) {
-        float4 pv = part ? __ldg(part + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 pv = part ? __ldg(part + c4 * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
         O[4 * c4 + 0] = pv.x + vec_s[4 * c4 + 0];
         O[4 * c4 + 1] = pv.y + vec_s[4 * c4 + 1];
         O[4 * c4 + 2] = pv.z + vec_s[4 * c4 + 2];
@@ -718,14 +723,15 @@ static MomLayout mom_layout(int B, int H, int N, int L, int causal, bool bwd) {
     return o;
   };
   const size_t tens = (size_t)m.BH * N * 64;
+  const size_t part_floats = (size_t)m.BH * ((N + 127) / 128) * PART_TILE_FLOATS;   // whole 128-token tiles
   m.off_xt = take((size_t)m.BH * 64 * m.Npad * 2);
   m.off_state = take((size_t)m.BH * m.nrec * REC_BYTES);
-  m.off_part = take(tens * 4);
+  m.off_part = take(part_floats * 4);
   if (bwd) {
     m.off_xt2 = take((size_t)m.BH * 64 * m.Npad * 2);
     m.off_state2 = take((size_t)m.BH * m.nrec * REC_BYTES);
-    m.off_part2 = take(tens * 4);
-    m.off_part3 = take(tens * 4);
+    m.off_part2 = take(part_floats * 4);
+    m.off_part3 = take(part_floats * 4);
     m.off_u = take(tens * 2);
     m.off_qd = take(tens * 2);
     m.off_dlt = take((size_t)m.BH * m.Npad * 4);

@@ -29,6 +29,10 @@ constexpr int VEC_FLOATS = 128 + 64 * 64;
 constexpr size_t REC_BYTES = ((VEC_OFF + VEC_FLOATS * 4 + 1023) / 1024) * 1024;
 constexpr int TILE_TOK = 128;               // rows of one MMA tile
 constexpr int APPLY_TOK = 512;              // tokens per apply CTA (4 tiles)
+// fp32 partials between the intra and the apply kernels: per 128-token tile one 32 KiB block laid out
+// [16-byte column chunk c4 = 0..15][row 0..127], so that a warp of row-owning threads reads or writes 512
+// contiguous bytes per instruction (a row-major partial means 16 bytes per lane at a 256-byte stride).
+constexpr int PART_TILE_FLOATS = 128 * 64;
 constexpr int BLK_TOK = 64;                 // tokens per build step
 
 }  // namespace mom
