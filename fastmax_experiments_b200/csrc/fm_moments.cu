@@ -518,6 +518,21 @@ apply_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CU
       v = reinterpret_cast<const float*>(P.state + (size_t)rec_idx * REC_BYTES + VEC_OFF)[P.vec_sel * 64 + tid];
     vec_s[tid] = v;
   }
+  // The output rows start from the additive terms.  The intra-segment partial (fp32, blocked layout of
+  // fm_moments.cuh: [tile][c4][row] float4, 512 contiguous bytes per warp and load) is requested first
+  // thing, before the set-up barrier: it is the longest latency in front of the first read-out.
+  float O[64];
+  if (warp < 16) {
+    const float4* part = nullptr;
+    if (P.partial && t0 + 128 * (warp >> 2) < P.N)
+      part = reinterpret_cast<const float4*>(P.partial + ((size_t)bh * ((P.N + 127) / 128) + (size_t)(t0 / 128 + (warp >> 2))) *
+                                                             PART_TILE_FLOATS) + (32 * (warp & 3) + lane);
+#pragma unroll
+    for (int c4 = 0; c4 < 16; ++c4) {
+      const float4 pv = part ? __ldg(part + c4 * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+      O[4 * c4 + 0] = pv.x, O[4 * c4 + 1] = pv.y, O[4 * c4 + 2] = pv.z, O[4 * c4 + 3] = pv.w;
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -585,25 +600,8 @@ apply_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CU
     const bool valid = i < P.N;
     const size_t grow = (size_t)bh * P.N + i;
     const uint32_t tbuf = tmem + ((uint32_t)(32 * q) << 16) + 128 * t;
-    // O starts from the additive terms (state vector + intra-segment partial): their loads overlap the
-    // wait for the first T tile and the tail is stores only (the tail read cost 15 % of the CTA time)
-    float O[64];
-    {
-      // blocked partial layout (fm_moments.cuh): [tile][c4][row] float4, 512 contiguous bytes per warp and load
-      const float4* part = nullptr;
-      if (P.partial)
-        part = reinterpret_cast<const float4*>(P.partial + ((size_t)bh * ((P.N + 127) / 128) + (size_t)(t0 / 128 + t)) *
-                                                               PART_TILE_FLOATS) + (32 * q + lane);
-      if (t0 + 128 * t >= P.N) part = nullptr;    // tile beyond the sequence
 #pragma unroll
-      for (int c4 = 0; c4 < 16; ++c4) {
-        float4 pv = part ? __ldg(part + c4 * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
-        O[4 * c4 + 0] = pv.x + vec_s[4 * c4 + 0];
-        O[4 * c4 + 1] = pv.y + vec_s[4 * c4 + 1];
-        O[4 * c4 + 2] = pv.z + vec_s[4 * c4 + 2];
-        O[4 * c4 + 3] = pv.w + vec_s[4 * c4 + 3];
-      }
-    }
+    for (int c = 0; c < 64; ++c) O[c] += vec_s[c];
     if (has_state) {
       const uint32_t* xrow = reinterpret_cast<const uint32_t*>(P.X + (valid ? grow : 0) * 64);
       // the pair of X coefficients of the NEXT group is fetched one iteration ahead (ncu: 8 % of the
