@@ -197,7 +197,9 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   assert_bases(tmem, smem);
-  // the output accumulators start at zero; every accumulating MMA then has accumulate = 1
+  // the output accumulators start at zero; every accumulating MMA then has accumulate = 1.  Only the
+  // compute warpgroups wait for that (each zeroes half of the columns, so they wait for each other); the
+  // producer warp starts its loads right away.
   if (warp >= 4) {
     uint32_t z[32];
 #pragma unroll
@@ -206,10 +208,10 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
 #pragma unroll
     for (int i = 0; i < 4; ++i) tmem_st32(la + 32 * i, z);
     tmem_wait_st();
+    tc_fence_before();
+    asm volatile("bar.sync 4, 256;" ::: "memory");
+    tc_fence_after();
   }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
 
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer
