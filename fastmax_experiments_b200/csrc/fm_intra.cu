@@ -518,7 +518,7 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
           ++nstored;
         }
       }
-      if (storer) bulk_wait_group0();      // shared memory must outlive the bulk stores
+      if (storer) bulk_wait_group_read0();   // shared memory must outlive the bulk stores' reads (not their global writes)
     } else {
     // ---------------------------------------------------------------- epilogue: fp32 partials
     // Written through shared memory with bulk tensor stores: a thread owns a 256-byte output row, so
@@ -615,7 +615,7 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
         P.g[grow] = gsum[x] + (has_norm ? count + gmom : 0.f);
       }
     }
-    if (storer) bulk_wait_group0();      // shared memory must outlive the bulk stores
+    if (storer) bulk_wait_group_read0();   // shared memory must outlive the bulk stores' reads (not their global writes)
     }   // !fused
   }
   tc_fence_before();

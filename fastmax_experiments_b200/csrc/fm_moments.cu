@@ -414,7 +414,7 @@ build_kernel(const __grid_constant__ CUtensorMap tmXT, const __grid_constant__ C
       }
       ++kq;
     }
-    if (storer) bulk_wait_group0();                 // shared memory must outlive the bulk stores
+    if (storer) bulk_wait_group_read0();            // shared memory must outlive the bulk stores' reads (not their global writes)
   }
   tc_fence_before();
   __syncthreads();
