@@ -602,6 +602,8 @@ apply_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CU
     const uint32_t tbuf = tmem + ((uint32_t)(32 * q) << 16) + 128 * t;
 #pragma unroll
     for (int c = 0; c < 64; ++c) O[c] += vec_s[c];
+    // (the normaliser of the row is fetched here, not in the tail where its latency would be exposed)
+    const float inv_g = (valid && P.gden) ? 1.f / __ldg(P.gden + grow) : 1.f;
     if (has_state) {
       const uint32_t* xrow = reinterpret_cast<const uint32_t*>(P.X + (valid ? grow : 0) * 64);
       // the pair of X coefficients of the NEXT group is fetched one iteration ahead (ncu: 8 % of the
@@ -638,8 +640,7 @@ apply_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CU
         if (lane == 0) mbar_arrive(&t_free[t]);
       }
     }
-    float scale = P.out_scale;
-    if (valid && P.gden) scale *= 1.f / P.gden[grow];
+    const float scale = P.out_scale * inv_g;
     if (valid) {
       uint4* dst = reinterpret_cast<uint4*>(P.out + grow * 64);
 #pragma unroll
