@@ -139,8 +139,7 @@ template <int MODE>
 __global__ void __launch_bounds__(384, 1)
 intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ CUtensorMap tmR2,
              const __grid_constant__ CUtensorMap tmT1, const __grid_constant__ CUtensorMap tmT2,
-             const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmO0,
-             const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmB0,
+             const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmB0,
              const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ IntraDescs DS, const IntraParams P) {
   using C = IntraCfg<MODE>;
   extern __shared__ uint8_t smem_raw[];
@@ -653,8 +652,7 @@ static int launch_intra_t(const Problem& pb, int L, int Npad, const void* r1, co
     int rc = make_tmap_bf16_3d(&tmS, state, 64, NSLAB * 64, (uint64_t)BH * P.nseg, 128, REC_BYTES, 64, 64);
     if (rc) return rc;
   }
-  CUtensorMap tmO0 = m[0], tmO1 = m[0];   // (fp32 partials are plain bulk copies now; parameters kept for layout stability)
-  CUtensorMap tmB0 = tmO0, tmB1 = tmO0;
+  CUtensorMap tmB0 = m[0], tmB1 = m[0];   // bf16 outputs of the fused p = 1 mode (fp32 partials are plain bulk copies)
   if (P.fused) {
     int rc = make_tmap_bf16_3d(&tmB0, final0, 64, pb.N, BH, 128, (uint64_t)pb.N * 128, 64, 64);
     if (rc) return rc;
@@ -684,7 +682,7 @@ static int launch_intra_t(const Problem& pb, int L, int Npad, const void* r1, co
       DS.normMN[kk] = sm100::desc_mnmajor_sw128_const(na, 8192) + kk * 128;
     }
   }
-  FM_LAUNCH(name, pb.stream, kern<<<grid, 384, C::SMEM, pb.stream>>>(m[0], m[1], m[2], m[3], tmS, tmO0, tmO1, tmB0, tmB1, DS, P));
+  FM_LAUNCH(name, pb.stream, kern<<<grid, 384, C::SMEM, pb.stream>>>(m[0], m[1], m[2], m[3], tmS, tmB0, tmB1, DS, P));
   return FASTMAX_OK;
 }
 

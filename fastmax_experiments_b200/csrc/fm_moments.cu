@@ -9,8 +9,10 @@
 //           generated in registers and written to TMEM, B = the V tile brought by TMA) and
 //           snapshots the running state as bf16 at every segment boundary.
 //   apply : per 512 tokens, streams the 65 slabs of the boundary state through shared memory
-//           with TMA and contracts them with A = q[x]*q[y] rows (again generated into TMEM).
-//   The same two kernels serve the backward pass with other operands (see moments_bwd).
+//           with TMA; two-stage contraction: T_x = Y_tile . slab_x on the tensor pipe, then
+//           O += X[x] * T_x on the CUDA cores while T is read out of tensor memory.
+//   The same two kernels serve the backward pass with other operands (see moments_bwd); for
+//   p = 1 the intra kernels (fm_intra.cu) apply the single-slab state term themselves.
 //
 // Reference functions covered: compute_F_masked / compute_g_masked (fastmax.py:219-322) and
 // gradient_o_{q,k,v}_masked (fastmax.py:433-691); the non-causal variants use one whole-sequence
