@@ -19,6 +19,8 @@ Behavioural notes:
   dtype (fp32 or bf16); accumulation is always fp32; ``g`` is saved in fp32.
 * ``mask=False`` accepts N_q != N_k (prefill / decode over the KV cache, model.py:478-487), forward
   only, with the reference's count term N_q in the normaliser (fastmax.py:269-271, quirk Q2).
+* Meta tensors pass through shape-only (the pretrain scripts' flop count runs the model on the meta
+  device, where the reference's own host hop fails: quirk Q7).
 * bf16 heads narrower than 64 (Pythia: 32) are zero-padded to 64 so that they run on the tcgen05
   path (D = 64 kernels): zero features change neither the scores nor the normaliser, and the padded
   output / gradient columns are exactly zero and sliced off.  ``c`` still uses the caller's D.
@@ -158,6 +160,12 @@ class FastmaxFunction(torch.autograd.Function):
             raise NotImplementedError("create_attn=True (dense debug path, fastmax.py:99-104) is not "
                                       "provided; its backward is broken in the reference as well")
         causal = mask is not False                                                 # fastmax.py:85
+        if q.device.type == "meta":
+            # shape-only pass (pretrain/openwebtext.py:146-156 runs the model on the meta device to count
+            # flops; the reference's .cpu() hop crashes there: quirk Q7)
+            ctx.meta = True
+            return torch.empty_like(q)
+        ctx.meta = False
         _check_inputs(q, k, v, rect_ok=not causal)
         D = q.shape[-1]
         c = 1.0 if tensors_normalized is True else normalize_term * math.sqrt(D)   # fastmax.py:79-82
@@ -179,6 +187,8 @@ class FastmaxFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, o_grad):
+        if ctx.meta:
+            return (torch.empty_like(o_grad),) * 3 + (None,) * 6
         q, k, v, o, g = ctx.saved_tensors
         do = o_grad.to(q.dtype).contiguous()
         if ctx.pad:

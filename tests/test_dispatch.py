@@ -75,3 +75,14 @@ def test_fastmax_cuda_compat_layout_roundtrip():
     assert orc.rel_err(o[:, d, :].transpose(0, 1).unsqueeze(0), ref[1]) <= 1e-4
     for x, r in zip((gq, gk, gv), ref[2:]):
         assert orc.rel_err(as4(x), r) <= 1e-4
+
+
+def test_meta_device_pass_is_shape_only():
+    """pretrain/openwebtext.py:146-156 runs GPT.forward on the meta device to count flops (quirk Q7)."""
+    import torch
+    import fastmax_experiments_b200 as fm
+    q = torch.empty(2, 4, 128, 64, device="meta", requires_grad=True)
+    o = fm.fastmax(q, q, q, p=2)
+    assert o.device.type == "meta" and o.shape == q.shape
+    o.sum().backward()
+    assert q.grad is not None and q.grad.shape == q.shape
