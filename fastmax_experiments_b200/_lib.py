@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfastmax_b200.so")
+# FASTMAX_LIB: developer override (a variant build, e.g. with -DFM_TIMING); the default is the in-tree library
+LIB_PATH = os.environ.get("FASTMAX_LIB") or os.path.join(HERE, "libfastmax_b200.so")
 
 OK, ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_WORKSPACE, ERR_CUDA = 0, -1, -2, -3, -4
 DTYPE_F32, DTYPE_BF16 = 0, 1

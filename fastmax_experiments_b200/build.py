@@ -36,6 +36,20 @@ def _digest() -> str:
     return h.hexdigest()
 
 
+def build_variant(name: str, extra: list[str], verbose: bool = False) -> str:
+    """Developer helper: a second copy of the library under .variants/<name>/ compiled with extra nvcc
+    flags (-DFM_TIMING, experiment switches); select it at run time with FASTMAX_LIB=<path>."""
+    global LIB, OBJ, NVCC_FLAGS
+    keep = (LIB, OBJ, NVCC_FLAGS)
+    root = os.path.join(HERE, "..", ".variants", name)
+    os.makedirs(root, exist_ok=True)
+    LIB, OBJ, NVCC_FLAGS = os.path.join(root, "libfastmax_b200.so"), os.path.join(root, "build"), keep[2] + list(extra)
+    try:
+        return build(force=False, verbose=verbose)
+    finally:
+        LIB, OBJ, NVCC_FLAGS = keep
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile every .cu under csrc/ for sm_100a and link libfastmax_b200.so in-tree.
     Skips the work when the sources are unchanged since the last build."""
@@ -72,4 +86,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 if __name__ == "__main__":
     import sys
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--variant" in sys.argv:      # python -m fastmax_experiments_b200.build --variant NAME -DFOO ...
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -95,6 +95,8 @@ int intra_dkdv(const Problem& pb, int L, int Npad, const void* k, const void* v,
                void* dv_final = nullptr);
 // (p = 1 with *_final given: the kernels also apply the first-order state term and write the final bf16
 //  outputs; the *_part arguments are then unused)
+namespace mom { struct ApplyDesc; }
+int launch_apply_gen(const Problem& pb, int BH, int nrec, const char* name, const mom::ApplyDesc& d, int variant);
 int moments_seg_len(int B, int H, int N, int p);
 size_t moments_state_bytes(int B, int H);
 size_t moments_saved_state_bytes(int B, int H, int N, int p, int causal);

@@ -75,7 +75,8 @@ __global__ void __launch_bounds__(256) transpose_kernel(const bf16* __restrict__
 // =============================================================================================
 struct BuildParams {
   int N, nblk, nproc, Lb, nseg, reverse, causal, p;
-  int special_cx;   // blockIdx.x of the CTA that owns the special tile (S1 | normaliser): 8 for p=2, 0 for p=1
+  int special_cx;   // blockIdx.x of the CTA that owns the special tile (S1 | normaliser): last CTA for p=2, 0 for p=1
+  int packed;       // 1: symmetric-packed second-order tiles (5 regular CTAs per (b,h)), 0: all 64x64 pairs (8 CTAs)
   uint8_t* state;   // records: causal -> [bh][nseg], else [bh]
   const uint8_t* init;   // sequence parallel: record per (b,h) the scan starts from (nullable)
   unsigned long long dW[4][4];    // B-operand descriptors [ring stage][k-step] of the W tile (host-built)
@@ -94,9 +95,31 @@ struct BuildParams {
 constexpr int B_STAGES = 4;
 constexpr int B_STAGE_BYTES = 3 * 8192;
 constexpr int B_SNAP_BYTES = 8 * SLAB_BYTES;             // bf16 staging of the CTA's eight slabs at a boundary
-constexpr int B_SMEM = B_STAGES * B_STAGE_BYTES + B_SNAP_BYTES + 1024 /*barriers*/ + 1024 /*align slack*/;
+constexpr int B_MIRROR_BYTES = 8 * SLAB_BYTES;           // ... and of their mirror images (packed tiles)
+constexpr int B_SMEM = B_STAGES * B_STAGE_BYTES + B_SNAP_BYTES + B_MIRROR_BYTES + 1024 /*barriers*/ + 1024 /*align slack*/;
 constexpr int B_ACOL = 256;
 constexpr int B_CTAS_P2 = 9;
+constexpr int B_CTAS_P2_PACKED = 6;
+
+// Symmetric packing.  S2[x][y][a] = S2[y][x][a], so only the 16x16 blocks (gx, by) of the (x, y) plane with
+// by >= gx are accumulated: ten blocks of 256 rows = twenty 128-row tiles instead of thirty-two, four tiles
+// (two blocks) per CTA.  Row r of a tile covers x = 16 gx + 8 half + (r >> 4), y = 16 by + (r & 15).  At a
+// segment boundary the off-diagonal blocks are written twice, as rows y of slab x and as rows x of slab y,
+// so the state record stays the full symmetric tensor that the K-major contractions (dq, dk) need.
+__device__ __forceinline__ void packed_block(int b, int& gx, int& by) {
+  gx = b < 4 ? 0 : (b < 7 ? 1 : (b < 9 ? 2 : 3));
+  by = gx + b - (gx == 0 ? 0 : (gx == 1 ? 4 : (gx == 2 ? 7 : 9)));
+}
+// feature pair (x, y) accumulated in row `row` of tile `t` of regular CTA `cx`
+__device__ __forceinline__ void tile_row_xy(int packed, int cx, int t, int row, int& x, int& y) {
+  if (packed) {
+    int gx, by;
+    packed_block(2 * cx + (t >> 1), gx, by);
+    x = 16 * gx + 8 * (t & 1) + (row >> 4), y = 16 * by + (row & 15);
+  } else {
+    x = 8 * cx + 2 * t + (row >> 6), y = row & 63;
+  }
+}
 constexpr int B_THREADS = 25 * 32;
 
 // Segment-boundary schedule of the scan without integer division in the hot loops.
@@ -126,11 +149,13 @@ __device__ __forceinline__ void lds128(uint32_t saddr, uint32_t* r) {
 
 __global__ void __launch_bounds__(B_THREADS, 1)
 build_kernel(const __grid_constant__ CUtensorMap tmXT, const __grid_constant__ CUtensorMap tmW,
-             const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmS, const BuildParams P) {
+             const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmS,
+             const __grid_constant__ CUtensorMap tmS16, const BuildParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* snap = smem + B_STAGES * B_STAGE_BYTES;   // [8 slabs][8 KiB], 128B-swizzled rows (TMA store source)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(snap + B_SNAP_BYTES);
+  uint8_t* mir = snap + B_SNAP_BYTES;                 // packed tiles: the same rows transposed (rows x of slab y)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(mir + B_MIRROR_BYTES);
   uint64_t* full = bars;                 // [4] block operands landed (TMA)
   uint64_t* done = bars + 4;             // [4] every MMA of the block in this ring slot complete (count ntile)
   uint64_t* a_ready = bars + 8;          // [4 tiles][2] A buffer written by the 4 warps of the group (count 4)
@@ -170,11 +195,14 @@ build_kernel(const __grid_constant__ CUtensorMap tmXT, const __grid_constant__ C
   const bool has_init = P.init != nullptr;
   if (warp < 16 && (warp >> 2) < ntile) {
     const int g = warp >> 2, q = warp & 3;
-    const int row = 32 * q + lane, xsel = row >> 6, y = row & 63;
+    const int row = 32 * q + lane;
+    int xg, y;
+    tile_row_xy(P.packed, cx, g, row, xg, y);
+    if (special) y = row & 63;
     const uint8_t* rec = has_init ? P.init + (size_t)bh * REC_BYTES : nullptr;
     const int nacc = special ? 2 : 1;
     for (int a2 = 0; a2 < nacc; ++a2) {
-      const int slab = special ? 64 + a2 : 8 * cx + 2 * g + xsel;
+      const int slab = special ? 64 + a2 : xg;
 #pragma unroll 1
       for (int h = 0; h < 2; ++h) {
         uint32_t v[32];
@@ -217,18 +245,20 @@ build_kernel(const __grid_constant__ CUtensorMap tmXT, const __grid_constant__ C
     // once and multiplies it with the runs of the tiles' x rows.  (One group per tile would re-read
     // the y rows four times: 640 shared-memory wavefronts per block against 512 cycles of MMA.)
     const int k = warp >> 2, q = warp & 3;
-    const int row = 32 * q + lane;                // TMEM lane == feature row (xsel, y) of every tile
-    const int xsel = row >> 6, y = row & 63;
+    const int row = 32 * q + lane;                // TMEM lane == feature pair (x, y) of every tile
     // byte offsets inside the 128B-swizzled XT tile of the two 16-byte chunks holding tokens
-    // [16k, 16k+16) of row y and of the x rows of the four tiles
-    uint32_t yo[2], xo[4][2];
+    // [16k, 16k+16) of the y rows (one per pair of tiles) and of the x rows of the four tiles
+    uint32_t yo[2][2], xo[4][2];
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      yo[c] = (uint32_t)y * 128 + ((uint32_t)((2 * k + c) ^ (y & 7)) << 4);
+    for (int t = 0; t < 4; ++t) {
+      int x, y;
+      tile_row_xy(P.packed, cx, t, row, x, y);
+      if (special) x = 0, y = row & 63;
+      x &= 63;
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int x = (8 * cx + 2 * t + xsel) & 63;
+      for (int c = 0; c < 2; ++c) {
         xo[t][c] = (uint32_t)x * 128 + ((uint32_t)((2 * k + c) ^ (x & 7)) << 4);
+        if ((t & 1) == 0) yo[t >> 1][c] = (uint32_t)y * 128 + ((uint32_t)((2 * k + c) ^ (y & 7)) << 4);
       }
     }
     const uint32_t fill = row == 64 ? 0x3F803F80u : 0u;
@@ -238,20 +268,28 @@ build_kernel(const __grid_constant__ CUtensorMap tmXT, const __grid_constant__ C
       const int s = it & 3, ph = (it >> 2) & 1, buf = it & 1;
       mbar_wait(&full[s], ph);
       const uint32_t xt = FM_SMEM_BASE + s * B_STAGE_BYTES;
-      uint32_t yr[8], a[4][8];
-      lds128(xt + yo[0], yr);
-      lds128(xt + yo[1], yr + 4);
+      uint32_t a[4][8];
       if (!special) {
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          uint32_t v[8];
-          lds128(xt + xo[t][0], v);
-          lds128(xt + xo[t][1], v + 4);
+        for (int tp = 0; tp < 2; ++tp) {         // a pair of tiles shares its y rows
+          uint32_t yr[8];
+          lds128(xt + yo[tp][0], yr);
+          lds128(xt + yo[tp][1], yr + 4);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) a[t][i] = mul_bf16x2(v[i], yr[i]);
+          for (int th = 0; th < 2; ++th) {
+            const int t = 2 * tp + th;
+            uint32_t v[8];
+            lds128(xt + xo[t][0], v);
+            lds128(xt + xo[t][1], v + 4);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[t][i] = mul_bf16x2(v[i], yr[i]);
+          }
         }
       } else {
         // special tile: rows 0..63 = Y (S1 / normaliser matrix), row 64 = ones (S0 / normaliser vector)
+        uint32_t yr[8];
+        lds128(xt + yo[0][0], yr);
+        lds128(xt + yo[0][1], yr + 4);
 #pragma unroll
         for (int i = 0; i < 8; ++i) a[0][i] = row < 64 ? yr[i] : fill;
       }
@@ -271,7 +309,7 @@ build_kernel(const __grid_constant__ CUtensorMap tmXT, const __grid_constant__ C
     // issuer kk: k-step kk of every tile, as soon as generator group kk has written it
     const int kk = warp - 16;
     constexpr uint32_t IDESC = make_idesc_bf16(128, 64, false, true);
-    constexpr uint32_t BAR0 = FM_SMEM_BASE + B_STAGES * B_STAGE_BYTES + B_SNAP_BYTES;   // shared address of bars[0]
+    constexpr uint32_t BAR0 = FM_SMEM_BASE + B_STAGES * B_STAGE_BYTES + B_SNAP_BYTES + B_MIRROR_BYTES;   // shared address of bars[0]
     BoundaryIter bi(P);
     int snaps = 0;
     bool pending = false;
@@ -283,9 +321,14 @@ build_kernel(const __grid_constant__ CUtensorMap tmXT, const __grid_constant__ C
         if (it < P.nproc) {
           const bool bnd = bi.step(it);
           if (lane == 0) {
+            [[maybe_unused]] const long long i0 = FM_NOW();
             if (pending) mbar_wait(acc_free, (snaps - 1) & 1);
+            [[maybe_unused]] const long long i1 = FM_NOW();
             // group kk read the block's tiles itself, so their TMA has landed
             mbar_wait(&a_ready[kk * 2 + (j & 1)], (it >> 1) & 1);
+#ifdef FM_TIMING
+            if (kk == 0 && cx == 0) FM_T(20, i1 - i0), FM_T(21, FM_NOW() - i1), FM_T(22, 1);
+#endif
           }
           __syncwarp();
           tc_fence_after();
@@ -335,6 +378,12 @@ build_kernel(const __grid_constant__ CUtensorMap tmXT, const __grid_constant__ C
     const int xsel = row >> 6, y = row & 63;
     const uint32_t lane_addr = tmem + ((uint32_t)(32 * q) << 16);
     const bool storer = warp == 21 && lane == 0;
+    // packed tiles: the CTA's two blocks (gx, by); off-diagonal ones are also stored mirrored
+    int pgx[2] = {0, 0}, pby[2] = {0, 0};
+    if (P.packed && !special) {
+      packed_block(2 * cx, pgx[0], pby[0]);
+      packed_block(2 * cx + 1, pgx[1], pby[1]);
+    }
     BoundaryIter bi(P);
     int kq = 0;
     for (int it = 0; it < P.nproc; ++it) {
@@ -343,8 +392,10 @@ build_kernel(const __grid_constant__ CUtensorMap tmXT, const __grid_constant__ C
       const int seg = !P.causal ? 0 : (P.reverse ? b / P.Lb - 1 : (b + 1) / P.Lb);
       const int rec_idx = P.causal ? bh * P.nseg + seg : bh;
       uint8_t* rec = P.state + (size_t)rec_idx * REC_BYTES;
-      if (storer) bulk_wait_group_read0();          // previous boundary's stores have left the staging tiles
+      if (storer || (P.packed && !special && lane == 0)) bulk_wait_group_read0();   // previous boundary's stores have left the staging tiles
+      [[maybe_unused]] const long long s0 = FM_NOW();
       mbar_wait(acc_full, kq & 1);
+      [[maybe_unused]] const long long s1 = FM_NOW();
       tc_fence_after();
       if (!special) {
         named_barrier_sync(1, 128);
@@ -355,11 +406,15 @@ build_kernel(const __grid_constant__ CUtensorMap tmXT, const __grid_constant__ C
           tmem_ld32(lane_addr + 64 * g + 32, v1);
           tmem_wait_ld_dep32(v0);
           tmem_wait_ld_dep32(v1);
-          const uint32_t dst = smem_u32(snap) + (uint32_t)(2 * g + xsel) * SLAB_BYTES + (uint32_t)y * 128;
+          // staging row of this thread: unpacked -> slab (2g + xsel) of the CTA, row y;
+          // packed -> 16-row unit (8g + (row >> 4)) = rows [16 by, 16 by + 16) of slab x, row (row & 15)
+          const int srow = P.packed ? (row & 15) : y;
+          const uint32_t dst = smem_u32(snap) + (P.packed ? (uint32_t)(8 * g + (row >> 4)) * 2048u + (uint32_t)srow * 128
+                                                          : (uint32_t)(2 * g + xsel) * SLAB_BYTES + (uint32_t)y * 128);
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             const uint32_t* v = c < 4 ? v0 + 8 * c : v1 + 8 * (c - 4);
-            sts128(dst + ((uint32_t)(c ^ (y & 7)) << 4),
+            sts128(dst + ((uint32_t)(c ^ (srow & 7)) << 4),
                    pack_bf16x2(__uint_as_float(v[0]), __uint_as_float(v[1])),
                    pack_bf16x2(__uint_as_float(v[2]), __uint_as_float(v[3])),
                    pack_bf16x2(__uint_as_float(v[4]), __uint_as_float(v[5])),
@@ -369,13 +424,55 @@ build_kernel(const __grid_constant__ CUtensorMap tmXT, const __grid_constant__ C
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_free);
+        [[maybe_unused]] const long long s2 = FM_NOW();
         fence_proxy_async();
         named_barrier_sync(1, 128);
-        if (storer) {
+        if (!P.packed) {
+          if (storer) {
 #pragma unroll 1
-          for (int sl = 0; sl < 8; ++sl) tma_store_3d(&tmS, snap + sl * SLAB_BYTES, 0, (8 * cx + sl) * 64, rec_idx);
-          bulk_commit_group();
+            for (int sl = 0; sl < 8; ++sl) tma_store_3d(&tmS, snap + sl * SLAB_BYTES, 0, (8 * cx + sl) * 64, rec_idx);
+            bulk_commit_group();
+          }
+        } else {
+          if (lane == 0) {
+            // unit u = 16 blk + xr  ->  rows [16 by, +16) of slab x = 16 gx + xr.  One storing lane per warp: 64
+            // bulk stores per boundary from a single thread took longer than the scan needs between boundaries.
+#pragma unroll 1
+            for (int u = q; u < 32; u += 4)
+              tma_store_3d(&tmS16, snap + u * 2048, 0, (16 * pgx[u >> 4] + (u & 15)) * 64 + 16 * pby[u >> 4], rec_idx);
+          }
+          // Mirror images of the off-diagonal blocks: atom (xr, yi, chunk c) of the staging moves from unit xr,
+          // row yi to unit yi, row xr.  Lane l of an 8-lane phase takes xr = l (mod 8), yi = l + s (mod 8) with one
+          // chunk c, so the eight 16-byte reads and the eight writes of a phase each cover all 32 banks once.
+          const int l7 = lane & 7, gid = 4 * q + (lane >> 3);
+          const int xr = 8 * (gid & 1) + l7, yh = (gid >> 1) & 1, s_lo = gid >> 2;
+#pragma unroll 1
+          for (int blk = 0; blk < 2; ++blk) {
+            if (pgx[blk] == pby[blk]) continue;
+#pragma unroll 4
+            for (int i2 = 0; i2 < 16; ++i2) {
+              const int sft = s_lo + 4 * (i2 >> 3), c = i2 & 7;
+              const int yi = 8 * yh + ((l7 + sft) & 7);
+              uint32_t w[4];
+              lds128(smem_u32(snap) + (uint32_t)(16 * blk + xr) * 2048u + (uint32_t)yi * 128 + ((uint32_t)(c ^ (yi & 7)) << 4), w);
+              sts128(smem_u32(mir) + (uint32_t)(16 * blk + yi) * 2048u + (uint32_t)xr * 128 + ((uint32_t)(c ^ (xr & 7)) << 4),
+                     w[0], w[1], w[2], w[3]);
+            }
+          }
+          fence_proxy_async();
+          named_barrier_sync(1, 128);
+          if (lane == 0) {
+            // unit u = 16 blk + yi  ->  rows [16 gx, +16) of slab y = 16 by + yi
+#pragma unroll 1
+            for (int u = q; u < 32; u += 4)
+              if (pgx[u >> 4] != pby[u >> 4])
+                tma_store_3d(&tmS16, mir + u * 2048, 0, (16 * pby[u >> 4] + (u & 15)) * 64 + 16 * pgx[u >> 4], rec_idx);
+            bulk_commit_group();
+          }
         }
+#ifdef FM_TIMING
+        if (storer && cx == 0) FM_T(16, 1), FM_T(17, s1 - s0), FM_T(18, s2 - s1), FM_T(19, FM_NOW() - s2);
+#endif
       } else {
         // special tile (S1 | normaliser matrix, row 64: S0 | normaliser vector): 1/33 of the state, stored directly
         for (int a2 = 0; a2 < 2; ++a2) {
@@ -416,7 +513,7 @@ build_kernel(const __grid_constant__ CUtensorMap tmXT, const __grid_constant__ C
       }
       ++kq;
     }
-    if (storer) bulk_wait_group_read0();            // shared memory must outlive the bulk stores' reads (not their global writes)
+    if (storer || (P.packed && !special && lane == 0)) bulk_wait_group_read0();   // shared memory must outlive the bulk stores' reads (not their global writes)
   }
   tc_fence_before();
   __syncthreads();
@@ -766,18 +863,32 @@ static int launch_transpose(const Problem& pb, const void* in, void* out, int Np
   return FASTMAX_OK;
 }
 
+// developer switch: FASTMAX_BUILD=full accumulates all 64x64 feature pairs (round-1 layout, 9 CTAs per (b,h));
+// default: symmetric-packed tiles (6 CTAs)
+static int build_packed() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("FASTMAX_BUILD");
+    v = (e && !strcmp(e, "full")) ? 0 : 1;
+  }
+  return v;
+}
+
 static int launch_build(const Problem& pb, const MomLayout& m, const void* xt, const void* w, const void* w2,
                         uint8_t* state, int reverse, const void* init = nullptr) {
-  CUtensorMap tmXT, tmW, tmW2, tmS;
+  CUtensorMap tmXT, tmW, tmW2, tmS, tmS16;
   int rc;
   if ((rc = make_tmap_bf16_3d(&tmS, state, 64, NSLAB * 64, (uint64_t)m.BH * m.nrec, 128, REC_BYTES, 64, 64))) return rc;
+  if ((rc = make_tmap_bf16_3d(&tmS16, state, 64, NSLAB * 64, (uint64_t)m.BH * m.nrec, 128, REC_BYTES, 64, 16))) return rc;
   if ((rc = make_tmap_bf16_3d(&tmXT, xt, 64, m.Npad, m.BH, 128, (uint64_t)m.Npad * 128, 64, 64))) return rc;
   if ((rc = make_tmap_bf16_3d(&tmW, w, 64, m.N, m.BH, 128, (uint64_t)m.N * 128, 64, 64))) return rc;
   if ((rc = make_tmap_bf16_3d(&tmW2, w2, 64, m.N, m.BH, 128, (uint64_t)m.N * 128, 64, 64))) return rc;
   BuildParams P{};
   P.N = m.N, P.nblk = (m.N + 63) / 64, P.Lb = m.L / 64, P.nseg = m.nseg, P.reverse = reverse, P.causal = pb.causal;
   P.p = pb.p, P.state = state, P.init = (const uint8_t*)init;
-  P.special_cx = pb.p == 2 ? B_CTAS_P2 - 1 : 0;
+  P.packed = pb.p == 2 && build_packed();
+  const int nctas = pb.p == 2 ? (P.packed ? B_CTAS_P2_PACKED : B_CTAS_P2) : 1;
+  P.special_cx = nctas - 1;
   for (int st = 0; st < B_STAGES; ++st)
     for (int kk = 0; kk < 4; ++kk) {
       const uint32_t base = sm100::FM_SMEM_BASE + st * B_STAGE_BYTES;
@@ -795,13 +906,31 @@ static int launch_build(const Problem& pb, const MomLayout& m, const void* xt, c
   else P.nproc = (m.nseg - 1) * P.Lb;
   if (P.nproc <= 0) return FASTMAX_OK;   // single segment: no boundary state needed
   FM_CUDA(cudaFuncSetAttribute(build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
-  dim3 grid(pb.p == 2 ? B_CTAS_P2 : 1, m.BH);
+  dim3 grid(nctas, m.BH);
   FM_LAUNCH(reverse ? "mom_build_rev" : "mom_build", pb.stream,
-            build_kernel<<<grid, B_THREADS, B_SMEM, pb.stream>>>(tmXT, tmW, tmW2, tmS, P));
+            build_kernel<<<grid, B_THREADS, B_SMEM, pb.stream>>>(tmXT, tmW, tmW2, tmS, tmS16, P));
   return FASTMAX_OK;
 }
 
+// developer switch: FASTMAX_APPLY=gen selects the generated-operand kernel (fm_apply.cu: correct, still slower
+// than the two-stage kernel below); default: two-stage
+static int apply_variant() {
+  static int v = -2;
+  if (v == -2) {
+    const char* e = getenv("FASTMAX_APPLY");
+    v = (e && !strcmp(e, "gen")) ? 0 : -1;
+  }
+  return v;
+}
+
 static int launch_apply(const Problem& pb, const MomLayout& m, const char* name, ApplyParams P, const void* Y) {
+  if (apply_variant() >= 0 && pb.p == 2) {
+    ApplyDesc d{};
+    d.L = m.L, d.nseg = m.nseg, d.state_reverse = P.state_reverse, d.b_kmajor = P.b_kmajor, d.edge_state = P.edge_state;
+    d.vec_sel = P.vec_sel, d.coef_reg = P.coef_reg, d.coef64 = P.coef64, d.out_scale = P.out_scale;
+    d.X = P.X, d.Y = Y, d.partial = P.partial, d.gden = P.gden, d.out = P.out, d.state = P.state;
+    return launch_apply_gen(pb, m.BH, m.nrec, name, d, apply_variant());
+  }
   CUtensorMap tmS, tmY;
   int rc;
   if ((rc = make_tmap_bf16_3d(&tmS, P.state, 64, NSLAB * 64, (uint64_t)m.BH * m.nrec, 128, REC_BYTES, 64, 64))) return rc;
@@ -983,15 +1112,19 @@ void moments_flops(int B, int H, int N, int p, int causal, double* fwd, double* 
   const MomLayout m = mom_layout(B, H, N, L, causal, false);
   const double mma = 2.0 * 128 * 64 * 16;
   const int nblk = (N + 63) / 64, Lb = L / 64;
-  const double acc = p == 2 ? 34 : 2;
+  const double acc = p == 2 ? (build_packed() ? 22 : 34) : 2;   // 128x64 accumulators per (b,h): second-order tiles + 2 special
   const double nproc_f = causal ? (double)(m.nseg - 1) * Lb : nblk;
   const double nproc_r = causal ? (double)(nblk - Lb) : nblk;
   const double build_f = m.BH * (nproc_f > 0 ? nproc_f : 0) * acc * 4 * mma;
   const double build_r = m.BH * (nproc_r > 0 ? nproc_r : 0) * acc * 4 * mma;
   const double ctas = (double)((N + APPLY_TOK - 1) / APPLY_TOK);
   const double with_state = causal ? (ctas - (double)L / APPLY_TOK > 0 ? ctas - (double)L / APPLY_TOK : 0) : ctas;
-  const double slabs = p == 2 ? 65 : 1;
-  const double apply = m.BH * with_state * slabs * (APPLY_TOK / 128 * 4) * mma;
+  // k-steps of one 128-token tile against the state: 65 slabs x 4 (the round-1 kernel, dq, dk); the symmetric
+  // contractions (o, dv) of the generated-operand kernel skip the blocks below the diagonal: 160 + 4
+  const bool gen = apply_variant() >= 0;
+  const double ks_full = p == 2 ? 65 * 4 : 4, ks_sym = p == 2 ? (gen ? 164 : 260) : 4;
+  const double apply_full = m.BH * with_state * (APPLY_TOK / 128) * ks_full * mma;
+  const double apply_sym = m.BH * with_state * (APPLY_TOK / 128) * ks_sym * mma;
   // intra-segment tiles (causal only): 128x128x64 GEMMs on the lower-triangular tile pairs of each
   // segment; forward 2 per pair (scores, P.V), dq 3, dkdv 4
   double intra_pair = 0;
@@ -1000,8 +1133,8 @@ void moments_flops(int B, int H, int N, int p, int causal, double* fwd, double* 
     const double full_segs = (double)(N / L), rem = t - full_segs * ts;
     intra_pair = m.BH * (full_segs * ts * (ts + 1) / 2 + rem * (rem + 1) / 2) * 2.0 * 128 * 128 * 64;
   }
-  *fwd = build_f + apply + 2 * intra_pair;
-  *bwd = build_f + build_r + 3 * apply + 7 * intra_pair;
+  *fwd = build_f + apply_sym + 2 * intra_pair;
+  *bwd = build_f + build_r + apply_sym + 2 * apply_full + 7 * intra_pair;
   *rebuild = build_f;   // skipped by backward when the forward states were kept
 }
 

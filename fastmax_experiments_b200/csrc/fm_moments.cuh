@@ -35,5 +35,22 @@ constexpr int APPLY_TOK = 512;              // tokens per apply CTA (4 tiles)
 constexpr int PART_TILE_FLOATS = 128 * 64;
 constexpr int BLK_TOK = 64;                 // tokens per build step
 
+// One inter-segment contraction (fm_apply.cu):
+//   out = out_scale * [1/g] * ( coef_reg * sum_x X[x] (Y . B_x) + coef64 * (Y . B_64) + vec + partial )
+struct ApplyDesc {
+  int L, nseg;
+  int state_reverse;        // 1: records are exclusive suffixes (the last segment has none)
+  int b_kmajor;             // 1: contraction over the slab's contiguous index (dq, dk); 0: over its rows (o, dv; X == Y)
+  int edge_state;           // sequence parallel: first (forward states) / last (reverse) local segment has a state
+  int vec_sel;              // -1 none, 0: vec[0:64), 1: vec[64:128)
+  float coef_reg, coef64, out_scale;
+  const void* X;            // (BH, N, 64) bf16 per-token scalars
+  const void* Y;            // (BH, N, 64) bf16 per-token vectors
+  const float* partial;     // blocked fp32 intra-segment partial, nullable
+  const float* gden;        // (BH, N) fp32 normaliser the rows are divided by (forward), nullable
+  void* out;                // (BH, N, 64) bf16
+  const void* state;
+};
+
 }  // namespace mom
 }  // namespace fm

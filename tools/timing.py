@@ -27,7 +27,7 @@ def fetch(name, reset=1):
 
 for _ in range(2):
     o, g = fastmax_fwd_raw(q, k, v, True, 1.0 / 64, 2, _lib.ALGO_MOMENTS)
-fetch("moments"); fetch("intra")
+fetch("moments"); fetch("intra"); fetch("apply")
 o, g = fastmax_fwd_raw(q, k, v, True, 1.0 / 64, 2, _lib.ALGO_MOMENTS)
 def show_intra(t):
     for mode, nm in enumerate(("fwd", "dq", "dkdv")):
@@ -40,27 +40,43 @@ def show_intra(t):
               f"CTA end {round(t[24 + mode] / c)}")
 
 
-for name in ("moments", "intra"):
+def show_apply(t, what):
+    n = max(t[0], 1)
+    print(f"apply ({what}): CTAs with state {t[0]}; per CTA (warp 0 / issuer 0): generator loop {t[1] // n}, "
+          f"of which waiting for a free A buffer {t[2] // n}, st+fence+arrive {t[3] // n}; epilogue {t[4] // n}; "
+          f"issuer: in slab loads (ring stage free) {t[5] // n}, waiting slab landed {t[6] // n}, waiting A ready {t[7] // n}, "
+          f"issue+commit region {t[9] // n}")
+
+
+for name in ("moments", "intra", "apply"):
     t = fetch(name)
     if t is None:
         continue
     if name == "intra":
         show_intra(t)
         continue
+    if name == "apply":
+        show_apply(t, "fwd")
+        continue
     n = max(t[0], 1)
     print(name, "fwd: ctas", t[0], " per-CTA avg cycles by slot:")
     print("  ", {i: round(x / n) for i, x in enumerate(t) if x and 0 < i < 16})
     if t[16]:
         nb = t[16]
-        print("   build (per snapshot of cx=0 CTAs):", nb, {i: round(x / nb) for i, x in enumerate(t) if x and i > 16})
+        print(f"   build, cx=0 CTAs, per boundary ({nb} boundaries): snapshot warps idle {t[17] // nb}, read-out + staging "
+              f"{t[18] // nb}, stores / mirror {t[19] // nb}; issuer 0 per block ({t[22]} blocks): stalled on the snapshot "
+              f"{t[20] / max(t[22], 1):.0f}, waiting for the generators {t[21] / max(t[22], 1):.0f}")
 if "--bwd" in sys.argv:
     fastmax_bwd_raw(q, k, v, o, g, do, True, 1.0 / 64, 2, _lib.ALGO_MOMENTS)
-    for name in ("moments", "intra"):
+    for name in ("moments", "intra", "apply"):
         t = fetch(name)
         if t is None:
             continue
         if name == "intra":
             show_intra(t)
+            continue
+        if name == "apply":
+            show_apply(t, "dq + dv + dk")
             continue
         n = max(t[0], 1)
         print(name, "bwd: ctas", t[0], {i: round(x / n) for i, x in enumerate(t) if x and i})
