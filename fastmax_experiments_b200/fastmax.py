@@ -34,7 +34,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["fastmax", "fastattention_einops", "FastmaxFunction", "fastmax_fwd_raw", "fastmax_bwd_raw"]
+__all__ = ["fastmax", "fastattention_einops", "FastmaxFunction", "fastmax_fwd_raw", "fastmax_bwd_raw", "rect_forward"]
 
 _DTYPES = {torch.float32: _lib.DTYPE_F32, torch.bfloat16: _lib.DTYPE_BF16}
 _TENSOR_PATH_D = 64      # head size of the tcgen05 kernels
@@ -120,14 +120,12 @@ def fastmax_bwd_raw(q, k, v, o, g, do, causal: bool, inv_c: float, p: int, algo:
     return dq, dk, dv
 
 
-def _inference_rect(ctx, q, k, v, inv_c, p):
-    """Non-causal forward with N_q != N_k: what the dispatch does for prefill / decode over the KV cache
-    (model.py:478-487 with ``input_pos`` given).  The shorter side is zero-padded along the sequence --
-    zero keys carry zero values and only add to the count term, zero queries are sliced off -- and the
-    count term of the normaliser is set to N_q like the reference's (fastmax.py:269-271, quirk Q2).
-    Forward only: the reference's non-causal backward assumes one N as well."""
-    if any(ctx.needs_input_grad[:3]):
-        raise NotImplementedError("fastmax with N_q != N_k is an inference (forward-only) path")
+def rect_forward(q, k, v, inv_c: float, p: int, count: str = "q"):
+    """Non-causal forward with N_q != N_k (prefill / decode over the KV cache, model.py:478-487 with
+    ``input_pos`` given).  The shorter side is zero-padded along the sequence -- zero keys carry zero values
+    and only add to the count term, zero queries are sliced off -- and the count term of the normaliser is
+    then set to what the reference uses: ``count="q"``: N_q (fastmax.py:269-271, quirk Q2);
+    ``count="k"``: N_k (fastmax_hack.py:21, the linearmax dispatch)."""
     Nq, Nk, D = q.shape[2], k.shape[2], q.shape[3]
     F = torch.nn.functional
     q_, k_, v_ = q.contiguous(), k.contiguous(), v.contiguous()
@@ -139,11 +137,19 @@ def _inference_rect(ctx, q, k, v, inv_c, p):
     if pad:
         q_, k_, v_ = (F.pad(t, (0, pad)) for t in (q_, k_, v_))
     o, g = fastmax_fwd_raw(q_, k_, v_, False, inv_c, p)
-    o = o[:, :, :Nq, :D]
-    if Nq < Nk:       # our count term is the padded length N_k; the reference's is N_q
-        g = g[:, :, :Nq]
-        o = (o.float() * (g / (g - float(Nk - Nq))).unsqueeze(-1)).to(q.dtype)
-    o = o.contiguous()
+    o, g = o[:, :, :Nq, :D], g[:, :, :Nq]
+    have = max(Nq, Nk)                       # count term of the padded problem
+    want = Nq if count == "q" else Nk
+    if have != want:
+        o = (o.float() * (g / (g - float(have - want))).unsqueeze(-1)).to(q.dtype)
+    return o.contiguous()
+
+
+def _inference_rect(ctx, q, k, v, inv_c, p):
+    """Forward only: the reference's non-causal backward assumes one N as well."""
+    if any(ctx.needs_input_grad[:3]):
+        raise NotImplementedError("fastmax with N_q != N_k is an inference (forward-only) path")
+    o = rect_forward(q, k, v, inv_c, p, count="q")
     ctx.mark_non_differentiable(o)
     return o
 

@@ -11,7 +11,7 @@ from __future__ import annotations
 
 import torch
 
-from .fastmax import fastmax
+from .fastmax import _check_inputs, fastmax, rect_forward
 
 __all__ = ["linearmax", "linearmax_prologue"]
 
@@ -35,4 +35,11 @@ def linearmax(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, p: int = 1, mas
     if p != 1:
         raise ValueError(f"linearmax is the first-order kernel (the reference dispatch passes p=1), got p={p}")
     qn, kn = linearmax_prologue(q, k)
+    if not mask and q.shape[2] != k.shape[2]:
+        # prefill / decode over the KV cache (model.py:460-472 with input_pos given): forward only, and the count
+        # term of the normaliser is the number of KEYS (fastmax_hack.py:21), not fastmax.py's N_q
+        if torch.is_grad_enabled() and any(t.requires_grad for t in (q, k, v)):
+            raise NotImplementedError("linearmax with N_q != N_k is an inference (forward-only) path")
+        _check_inputs(qn, kn, v, rect_ok=True)
+        return rect_forward(qn, kn, v, 1.0, 1, count="k")
     return fastmax(qn, kn, v, mask=True if mask else False, tensors_normalized=True, p=1)

@@ -316,5 +316,11 @@ def linearmax_forward(q, k, v, mask=True):
     FastMax with c = 1 (normalize_term = 1, :48; denum_term = 1, :9).  Differentiable with torch autograd,
     like the reference (which has no custom backward here)."""
     qn, kn = linearmax_prologue(q, k)
+    if mask is False and q.shape[2] != k.shape[2]:
+        # KV-cache shapes (N_q != N_k): the non-causal branch counts the KEYS, div1 = k.shape[2]
+        # (fastmax_hack.py:21) -- unlike fastmax.py's compute_g_unmasked, whose count term is N_q
+        num = qn @ (kn.transpose(-1, -2) @ v) + v.sum(-2, keepdim=True)            # fastmax_hack.py:18-19,24,27-28
+        den = qn @ kn.sum(-2).unsqueeze(-1) + float(k.shape[2])                    # fastmax_hack.py:21-22,25,29-30
+        return num / den
     o, _ = factorised_forward(qn, kn, v, mask, normalize_term=1, tensors_normalized=True, p=1)
     return o

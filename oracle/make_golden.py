@@ -42,6 +42,10 @@ CASES = [
     ("p2_causal_d64_nt1",  1, 2,  64,  64, 2, True,  1, False, 10),
     ("p2_causal_d32_tn",   1, 2,  64,  32, 2, True,  8, True,  11),
     ("p1_causal_d32_odd",  2, 3,  33,  32, 1, True,  8, False, 12),
+    # long enough for the chunked scan of the tcgen05 path (D = 32 runs zero-padded on the D = 64 kernels):
+    # several 512-token segments, i.e. the build / apply moment kernels, pinned directly to the reference
+    ("p2_causal_d32_multiseg", 1, 1, 2600, 32, 2, True, 8, False, 13),
+    ("p1_causal_d32_multiseg", 1, 2, 1100, 32, 1, True, 8, False, 14),
 ]
 
 
@@ -62,6 +66,19 @@ LINEARMAX_CASES = [
     ("linearmax_causal_d32", 1, 3,  70, 32, True, 33),
 ]
 
+# linearmax over a KV cache (input_pos given -> mask=False, N_q != N_k): the count term of fastmax_hack.py:21 is
+# N_k, unlike fastmax.py's N_q.  Forward only.  (name, B, H, Nq, Nk, D, seed)
+LINEARMAX_RECT_CASES = [
+    ("linearmax_full_prefill_d64", 1, 2, 17, 96, 64, 34),
+    ("linearmax_full_decode_d32",  2, 2,  1, 40, 32, 35),
+]
+
+# model level: the unmodified lit_gpt GPT, attn_alg="fastmax", on the host -- including
+# the dispatch's missing head transpose (quirk Q1), which lives in CausalSelfAttention.forward, not in the op
+MODEL_CASES = [
+    ("model_pythia14m_seq256", "pythia-14m", 256, 0),
+]
+
 
 def bf16_round(x: torch.Tensor) -> torch.Tensor:
     return x.to(torch.bfloat16).to(torch.float32)
@@ -77,6 +94,8 @@ def main() -> None:
 
     os.makedirs(OUT_DIR, exist_ok=True)
     for name, B, H, N, D, p, mask, nt, tn, seed in CASES:
+        if NAMES and name not in NAMES:
+            continue
         gen = torch.Generator().manual_seed(seed)
         scale = 0.25 if tn else 1.0   # tensors_normalized => c = 1: keep |s| small like normalised q,k
         q = bf16_round(torch.randn(B, H, N, D, generator=gen) * scale)
@@ -119,6 +138,8 @@ def main_rect() -> None:
     from attention_mechanisms.fastmax import fastmax as ref_fastmax  # the unmodified reference
 
     for name, B, H, Nq, Nk, D, p, seed in RECT_CASES:
+        if NAMES and name not in NAMES:
+            continue
         gen = torch.Generator().manual_seed(seed)
         q = bf16_round(torch.randn(B, H, Nq, D, generator=gen))
         k = bf16_round(torch.randn(B, H, Nk, D, generator=gen))
@@ -137,6 +158,8 @@ def main_linearmax() -> None:
     from attention_mechanisms.fastmax_hack import fastmax_hack as ref_linearmax  # the unmodified reference
 
     for name, B, H, N, D, mask, seed in LINEARMAX_CASES:
+        if NAMES and name not in NAMES:
+            continue
         gen = torch.Generator().manual_seed(seed)
         q, k, v, do = (bf16_round(torch.randn(B, H, N, D, generator=gen)) for _ in range(4))
         qq, kk, vv = (t.double().clone().requires_grad_(True) for t in (q, k, v))
@@ -150,9 +173,64 @@ def main_linearmax() -> None:
         print(f"{name}: wrote {os.path.getsize(path)/1e6:.2f} MB  |o|max={o.abs().max():.4f}")
 
 
+def main_linearmax_rect() -> None:
+    sys.path.insert(0, REF_ROOT)
+    from attention_mechanisms.fastmax_hack import fastmax_hack as ref_linearmax  # the unmodified reference
+
+    for name, B, H, Nq, Nk, D, seed in LINEARMAX_RECT_CASES:
+        if NAMES and name not in NAMES:
+            continue
+        gen = torch.Generator().manual_seed(seed)
+        q = bf16_round(torch.randn(B, H, Nq, D, generator=gen))
+        k = bf16_round(torch.randn(B, H, Nk, D, generator=gen))
+        v = bf16_round(torch.randn(B, H, Nk, D, generator=gen))
+        with torch.no_grad():
+            o = ref_linearmax(q.double(), k.double(), v.double(), p=1, mask=False)
+        out = dict(B=B, H=H, Nq=Nq, Nk=Nk, D=D, p=1, q_bf16=bf16_bits(q), k_bf16=bf16_bits(k), v_bf16=bf16_bits(v),
+                   o=o.double().numpy())
+        path = os.path.join(OUT_DIR, name + ".npz")
+        np.savez_compressed(path, **out)
+        print(f"{name}: wrote {os.path.getsize(path)/1e6:.2f} MB  |o|max={o.abs().max():.4f}")
+
+
+def main_model() -> None:
+    """Logits and loss of the unmodified reference model (fp32, host).  The full logits are 51 MB, so the
+    fixture keeps the loss, every position's log-sum-exp and a strided sample of the logits; inputs and
+    weights are re-created from the seed (oracle/ref_loader.py::build_gpt)."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    from oracle import ref_loader as rl
+
+    for name, model_name, T, seed in MODEL_CASES:
+        if NAMES and name not in NAMES:
+            continue
+        with rl.cuda_hop_neutralised():
+            model, cfg = rl.build_gpt(model_name, attn_alg="fastmax", block_size=T, seed=seed)
+            idx = torch.randint(0, cfg.padded_vocab_size, (1, T), generator=torch.Generator().manual_seed(seed + 1))
+            logits = model(idx)
+            loss = torch.nn.functional.cross_entropy(logits.view(-1, logits.size(-1)), idx.view(-1))
+            loss.backward()
+        gnorm = torch.sqrt(sum((p.grad.double() ** 2).sum() for p in model.parameters() if p.grad is not None))
+        out = dict(model=model_name, T=T, seed=seed, idx=idx.numpy(), loss=float(loss),
+                   lse=torch.logsumexp(logits.detach().double(), -1).numpy(),
+                   logits_sample=logits.detach()[:, ::8, ::64].numpy(), grad_norm=float(gnorm),
+                   wte_grad_sample=model.transformer.wte.weight.grad[idx[0, :8]].numpy())
+        path = os.path.join(OUT_DIR, name + ".npz")
+        np.savez_compressed(path, **out)
+        print(f"{name}: wrote {os.path.getsize(path)/1e6:.2f} MB  loss={float(loss):.6f} grad_norm={float(gnorm):.6f}")
+
+
+NAMES: set = set()
+
 if __name__ == "__main__":
     only = [a for a in sys.argv[1:] if a.startswith("--only=")]
     which = only[0].split("=")[1] if only else "all"
+    names = [a for a in sys.argv[1:] if a.startswith("--names=")]
+    if names:
+        NAMES = set(names[0].split("=")[1].split(","))
+    if which in ("all", "linearmax_rect"):
+        main_linearmax_rect()
+    if which in ("all", "model"):
+        main_model()
     if which in ("all", "square"):
         main()
     if which in ("all", "rect") or "--rect-only" in sys.argv:

@@ -32,19 +32,40 @@ def _all_golden():
                   for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
 
 
+def _is_rect(n):
+    return "decode" in n or "prefill" in n
+
+
 def golden_names():
     """Square fixtures (q, k, v of one shape; forward + backward)."""
-    return [n for n in _all_golden() if "decode" not in n and "prefill" not in n and not n.startswith("linearmax")]
+    return [n for n in _all_golden() if not _is_rect(n) and not n.startswith(("linearmax", "model_"))]
 
 
 def golden_rect_names():
     """Inference fixtures (N_q != N_k, non-causal, forward only)."""
-    return [n for n in _all_golden() if "decode" in n or "prefill" in n]
+    return [n for n in _all_golden() if _is_rect(n) and not n.startswith("linearmax")]
 
 
 def golden_linearmax_names():
     """linearmax fixtures (fastmax_hack.py: forward + torch-autograd gradients)."""
-    return [n for n in _all_golden() if n.startswith("linearmax")]
+    return [n for n in _all_golden() if n.startswith("linearmax") and not _is_rect(n)]
+
+
+def golden_linearmax_rect_names():
+    """linearmax over a KV cache (N_q != N_k, forward only; count term N_k, fastmax_hack.py:21)."""
+    return [n for n in _all_golden() if n.startswith("linearmax") and _is_rect(n)]
+
+
+def golden_model_names():
+    return [n for n in _all_golden() if n.startswith("model_")]
+
+
+def load_golden_model(name: str) -> dict:
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    d = {k: z[k] for k in z.files}
+    return dict(name=name, model=str(d["model"]), T=int(d["T"]), seed=int(d["seed"]), idx=torch.from_numpy(d["idx"]),
+                loss=float(d["loss"]), lse=torch.from_numpy(d["lse"]), logits_sample=torch.from_numpy(d["logits_sample"]),
+                grad_norm=float(d["grad_norm"]), wte_grad_sample=torch.from_numpy(d["wte_grad_sample"]))
 
 
 def load_golden_linearmax(name: str) -> dict:

@@ -192,53 +192,78 @@ def test_kept_forward_states_match_rebuilt():
         assert orc.rel_err(x.double().cpu(), r) <= 2e-2
 
 
+def _rows_ok(x, ref, tol=2e-2):
+    err = (x - ref).abs().reshape(ref.shape[0], -1).max(-1).values
+    ref_mag = ref.abs().reshape(ref.shape[0], -1).max(-1).values
+    return bool((err <= tol * ref_mag).all()), (err / ref_mag).tolist()
+
+
+def _sampled_rows_and_columns_check(q, k, v, do, o, g, dq, dk, dv, b, h, rows, cols, c, fwd=True):
+    """Sampled rows of o, g, dq and sampled columns of dk, dv of one (b,h) against the dense formula evaluated in
+    fp64 on the host for those rows only.  Judged per row (gradient magnitudes fall like 1/i along the
+    sequence).  Row 0 must be left out of `rows`: there dq = 0 exactly (u.v_0 = dlt), see the N = 1 seeded case."""
+    N = q.shape[2]
+    Q, K, V, DO, O, G = (t[b, h].double().cpu() for t in (q, k, v, do, o, g))
+    idx = torch.arange(N)
+    # rows i: everything from keys j <= i
+    s = Q[rows] @ K.T / c
+    m = (idx[None, :] <= rows[:, None]).double()
+    w = (1 + s + 0.5 * s * s) * m
+    gr = w.sum(-1)
+    o_ref = (w @ V) / gr[:, None]
+    if fwd:
+        assert _rows_ok(G[rows], gr)[0], _rows_ok(G[rows], gr)
+        assert _rows_ok(O[rows], o_ref)[0], _rows_ok(O[rows], o_ref)
+    u = DO[rows] / gr[:, None]
+    dlt = (DO[rows] * o_ref).sum(-1) / gr
+    e = (1 + s) * (u @ V.T - dlt[:, None]) * m
+    ok = _rows_ok(dq[b, h].double().cpu()[rows], e @ K / c)
+    assert ok[0], ("dq", b, h, ok)
+    # columns j: everything from queries i >= j needs u_i, dlt_i of ALL later rows: use the kernel's own
+    # o, g (validated on samples) to form them -- the check is then on the dk/dv contractions
+    Uall = DO / G[:, None]
+    Dall = (DO * O).sum(-1) / G
+    st = K[cols] @ Q.T / c                                   # (cols, N) scores s_ij for j in cols
+    mt = (idx[None, :] >= cols[:, None]).double()
+    wt = (1 + st + 0.5 * st * st) * mt
+    et = (1 + st) * (V[cols] @ Uall.T - Dall[None, :]) * mt
+    ok = _rows_ok(dv[b, h].double().cpu()[cols], wt @ Uall)
+    assert ok[0], ("dv", b, h, ok)
+    ok = _rows_ok(dk[b, h].double().cpu()[cols], et @ Q / c)
+    assert ok[0], ("dk", b, h, ok)
+
+
 def test_long_sequence_sampled_rows_fwd_bwd():
-    """N = 65536 (128 segments, far beyond what the oracle can hold): sampled rows of o, g, dq and sampled
-    columns of dk, dv against the dense formula evaluated in fp64 on the host for those rows only.
-    Judged per row (gradient magnitudes fall like 1/i along the sequence).  Row 0 is left out of the dq
-    check: there dq = 0 exactly (u.v_0 = dlt), see the N = 1 case of the seeded tests."""
+    """N = 65536 (128 segments, far beyond what the oracle can hold): sampled rows / columns of every output."""
     B, H, N, D, p = 1, 2, 65536, 64, 2
     gen = torch.Generator(device="cuda").manual_seed(5)
     q, k, v, do = (torch.randn(B, H, N, D, device="cuda", generator=gen).to(torch.bfloat16) for _ in range(4))
     c = orc.denominator_c(D)
     o, g = fastmax_fwd_raw(q, k, v, True, 1.0 / c, p)
     dq, dk, dv = fastmax_bwd_raw(q, k, v, o, g, do, True, 1.0 / c, p)
-
-    def rows_ok(x, ref, tol=2e-2):
-        err = (x - ref).abs().reshape(ref.shape[0], -1).max(-1).values
-        ref_mag = ref.abs().reshape(ref.shape[0], -1).max(-1).values
-        return bool((err <= tol * ref_mag).all()), (err / ref_mag).tolist()
-
     rows = torch.tensor([1, 511, 512, 513, 4095, 30000, 65535])
+    cols = torch.tensor([0, 511, 512, 40000, 65534])
     for h in range(H):
-        Q, K, V, DO, O, G = (t[0, h].double().cpu() for t in (q, k, v, do, o, g))
-        idx = torch.arange(N)
-        # rows i: everything from keys j <= i
-        s = Q[rows] @ K.T / c
-        m = (idx[None, :] <= rows[:, None]).double()
-        w = (1 + s + 0.5 * s * s) * m
-        gr = w.sum(-1)
-        o_ref = (w @ V) / gr[:, None]
-        assert rows_ok(G[rows], gr)[0], rows_ok(G[rows], gr)
-        assert rows_ok(O[rows], o_ref)[0], rows_ok(O[rows], o_ref)
-        u = DO[rows] / gr[:, None]
-        dlt = (DO[rows] * o_ref).sum(-1) / gr
-        e = (1 + s) * (u @ V.T - dlt[:, None]) * m
-        ok = rows_ok(dq[0, h].double().cpu()[rows], e @ K / c)
-        assert ok[0], ok
-        # columns j: everything from queries i >= j needs u_i, dlt_i of ALL later rows: use the kernel's own
-        # o, g (validated above on samples) to form them -- the check is then on the dk/dv contractions
-        Uall = DO / G[:, None]
-        Dall = (DO * O).sum(-1) / G
-        cols = torch.tensor([0, 511, 512, 40000, 65534])
-        st = K[cols] @ Q.T / c                                   # (cols, N) scores s_ij for j in cols
-        mt = (idx[None, :] >= cols[:, None]).double()
-        wt = (1 + st + 0.5 * st * st) * mt
-        et = (1 + st) * (V[cols] @ Uall.T - Dall[None, :]) * mt
-        ok = rows_ok(dv[0, h].double().cpu()[cols], wt @ Uall)
-        assert ok[0], ok
-        ok = rows_ok(dk[0, h].double().cpu()[cols], et @ Q / c)
-        assert ok[0], ok
+        _sampled_rows_and_columns_check(q, k, v, do, o, g, dq, dk, dv, 0, h, rows, cols, c)
+
+
+def test_headline_shape_backward_sampled():
+    """BASELINE.json full size, forward AND backward (B*H = 256 (b,h) units, 32 segments each, forward states kept
+    for backward as bench.py does): sampled rows of dq and sampled columns of dk, dv for (b,h) units across the
+    whole batch-head range against the dense formula."""
+    from fastmax_experiments_b200.fastmax import saved_state_bytes
+    B, H, N, D, p = 8, 32, 16384, 64, 2
+    gen = torch.Generator(device="cuda").manual_seed(17)
+    q, k, v, do = (torch.randn(B, H, N, D, device="cuda", generator=gen).to(torch.bfloat16) for _ in range(4))
+    c = orc.denominator_c(D)
+    saved = torch.empty(saved_state_bytes(q, True, p), dtype=torch.uint8, device="cuda")
+    o, g = fastmax_fwd_raw(q, k, v, True, 1.0 / c, p, saved=saved)
+    dq, dk, dv = fastmax_bwd_raw(q, k, v, o, g, do, True, 1.0 / c, p, saved=saved)
+    del saved
+    rows = torch.tensor([1, 127, 511, 512, 8191, 8192, 16383])
+    cols = torch.tensor([0, 511, 512, 9000, 15871, 16382])
+    for (b, h) in ((0, 0), (7, 31), (3, 17), (5, 1)):
+        _sampled_rows_and_columns_check(q, k, v, do, o, g, dq, dk, dv, b, h, rows, cols, c)
 
 
 def test_cuda_graph_capture_replays_the_step():
@@ -337,6 +362,27 @@ def test_linearmax_matches_reference(name, dtype):
     o.backward(gd["do"].to("cuda", dtype))
     for nm, x in (("o", o), ("dq", q.grad), ("dk", k.grad), ("dv", v.grad)):
         assert orc.rel_err(x.double().cpu(), gd[nm]) <= TOL[dtype], (name, nm)
+
+
+from conftest import golden_linearmax_rect_names  # noqa: E402
+
+
+@pytest.mark.parametrize("name", golden_linearmax_rect_names())
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_linearmax_kv_cache_shapes_match_reference(name, dtype):
+    """linearmax with input_pos given (mask=False, N_q != N_k): the count term is N_k (fastmax_hack.py:21)."""
+    from fastmax_experiments_b200 import linearmax
+    from fastmax_experiments_b200.attention import linearmax_attention
+    gd = load_golden_rect(name)
+    q, k, v = (gd[x].to("cuda", dtype) for x in ("q", "k", "v"))
+    with torch.no_grad():
+        o = linearmax(q, k, v, p=1, mask=False)
+        o2 = linearmax_attention(q, k, v, input_pos=torch.arange(q.shape[2], device="cuda"))
+    assert o.shape == q.shape and o.dtype == dtype
+    assert orc.rel_err(o.double().cpu(), gd["o"]) <= TOL[dtype]
+    assert orc.rel_err(o2.double(), o.double()) <= 1e-2
+    with pytest.raises(NotImplementedError):
+        linearmax(q.clone().requires_grad_(True), k, v, p=1, mask=False)
 
 
 @pytest.mark.parametrize("contig", [True, False], ids=["contiguous", "strided"])

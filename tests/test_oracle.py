@@ -3,8 +3,8 @@ minted from the unmodified reference, and the two restatements against each othe
 import pytest
 import torch
 
-from conftest import (golden_linearmax_names, golden_names, golden_rect_names, load_golden, load_golden_linearmax,
-                      load_golden_rect)
+from conftest import (golden_linearmax_names, golden_linearmax_rect_names, golden_names, golden_rect_names,
+                      load_golden, load_golden_linearmax, load_golden_rect)
 from oracle import fastmax_oracle as orc
 
 NAMES = golden_names()
@@ -89,3 +89,11 @@ def test_oracle_linearmax_matches_reference(name):
     o.backward(gd["do"].double())
     for nm, x in (("o", o.detach()), ("dq", q.grad), ("dk", k.grad), ("dv", v.grad)):
         assert orc.rel_err(x, gd[nm]) <= 1e-10, nm
+
+
+@pytest.mark.parametrize("name", golden_linearmax_rect_names())
+def test_oracle_linearmax_kv_cache_shapes_count_the_keys(name):
+    """fastmax_hack.py non-causal with N_q != N_k: count term N_k (fastmax_hack.py:21), not fastmax.py's N_q."""
+    gd = load_golden_rect(name)
+    o = orc.linearmax_forward(gd["q"].double(), gd["k"].double(), gd["v"].double(), mask=False)
+    assert orc.rel_err(o, gd["o"]) <= 1e-12
