@@ -89,51 +89,191 @@ class ClockSampler(threading.Thread):
 
 
 # ----------------------------------------------------------------------------------------------
-def cpu_port_rate(n_sample: int, d: int, repeats: int, threads: int) -> tuple[float, float]:
-    """Times the oracle's factorised restatement (same einsum/cumsum structure as the reference's
-    fastmax.py) on a (1,1,n_sample,d) fp32 slice of the workload.  Returns (tokens/s at H=32,
-    seconds per fwd+bwd of the sample)."""
-    from oracle import fastmax_oracle as orc
+def _cpu_step_fn(n_sample: int, d: int, threads: int):
+    """One fwd+bwd of the reference's CPU implementation on a (1,1,n_sample,d) fp32 slice of the workload.
+    Returns (callable, kind): the UNMODIFIED attention_mechanisms/fastmax.py from baseline/_ref when it is
+    installed ("reference"), else the oracle's factorised restatement of it ("port")."""
     torch.set_num_threads(threads)
     gen = torch.Generator().manual_seed(0)
     q, k, v, do = (torch.randn(1, 1, n_sample, d, generator=gen) for _ in range(4))
+    try:
+        from oracle import ref_loader
+        if not ref_loader.installed():
+            raise ImportError
+        ref_fastmax, _ = ref_loader.reference_op()
+
+        def step():
+            qq, kk, vv = (t.clone().requires_grad_(True) for t in (q, k, v))
+            ref_fastmax(qq, kk, vv, mask=True, p=HL["p"]).backward(do)
+        return step, "reference"
+    except ImportError:
+        from oracle import fastmax_oracle as orc
+        return (lambda: orc.factorised_fwd_bwd(q, k, v, do, mask=True, p=HL["p"])), "port"
+
+
+def cpu_rate(n_sample: int, d: int, repeats: int, threads: int) -> tuple[float, float, str]:
+    """(tokens/s at H=32, seconds per fwd+bwd of the sample, kind) -- best of `repeats`."""
+    step, kind = _cpu_step_fn(n_sample, d, threads)
     best = float("inf")
     for _ in range(repeats):
         t0 = time.perf_counter()
-        orc.factorised_fwd_bwd(q, k, v, do, mask=True, p=HL["p"])
+        step()
         best = min(best, time.perf_counter() - t0)
-    units_per_s = n_sample / best
-    return units_per_s / HL["H"], best
+    return n_sample / best / HL["H"], best, kind
+
+
+def _cpu_sample_text(kind: str, n_sample: int) -> str:
+    what = ("the unmodified attention_mechanisms/fastmax.py (baseline/_ref)" if kind == "reference"
+            else "oracle port of fastmax.py (factorised einsum/cumsum)")
+    return (f"{what}, fp32, fwd+bwd of a (B=1,H=1,N={n_sample},D={HL['D']}) slice of the workload (the full shape "
+            f"needs PB-sized intermediates in the reference); tokens/s = (b,h,token) units/s / H={HL['H']}")
 
 
 def run_reference(args, rank: int) -> None:
-    """--impl reference: the reference's CPU algorithm (oracle port of fastmax.py; the reference
-    itself is Python and cannot travel to the GPU box) on this box's host cores."""
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores."""
     if rank != 0:
         return
+    if args.workload == "model":
+        return run_reference_model(args)
     threads = os.cpu_count() or 1
     n_sample = 512
-    from oracle import fastmax_oracle as orc
-    torch.set_num_threads(threads)
-    gen = torch.Generator().manual_seed(0)
-    q, k, v, do = (torch.randn(1, 1, n_sample, HL["D"], generator=gen) for _ in range(4))
+    step, kind = _cpu_step_fn(n_sample, HL["D"], threads)
     for _ in range(args.warmup):
-        orc.factorised_fwd_bwd(q, k, v, do, mask=True, p=HL["p"])
+        step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        orc.factorised_fwd_bwd(q, k, v, do, mask=True, p=HL["p"])
+        step()
     dt = (time.perf_counter() - t0) / args.steps
     value = n_sample / dt / HL["H"]
-    sample = (f"each step = fwd+bwd of a (B=1,H=1,N={n_sample},D={HL['D']}) fp32 slice of the workload "
-              f"(the full shape needs PB-sized intermediates); tokens/s = (b,h,token) units/s / H={HL['H']}")
     _emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "fastmax p=2 causal fwd+bwd B=8 H=32 N=16384 D=64 (CPU: bounded sample)", **HL},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
+                         "sample": "each step = " + _cpu_sample_text(kind, n_sample)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+    }))
+
+
+# ----------------------------------------------------------------------------------------------
+MODEL_SEQ = {"pythia-14m": 2048, "tiny-llama-1.1b": 8192, "Llama-2-7b-hf": 4096}     # BASELINE.json configs 1, 3, 4
+LORA = dict(r=8, alpha=16, dropout=0.05, to_query=True, to_key=False, to_value=True, to_projection=False,
+            to_mlp=False, to_head=False)                                               # finetune/lora.py:40-48
+
+
+def _model_step_fn(model, cfg, T: int, device, opt=None):
+    idx = torch.randint(0, cfg.padded_vocab_size, (1, T), generator=torch.Generator().manual_seed(0)).to(device)
+
+    def step():
+        model.zero_grad(set_to_none=True)
+        logits = model(idx)
+        loss = torch.nn.functional.cross_entropy(logits.view(-1, logits.size(-1)).float(), idx.view(-1))
+        loss.backward()
+        if opt is not None:
+            opt.step()
+        return loss
+    return step, idx
+
+
+def run_model(args, local: int) -> None:
+    """BASELINE.json configs 3 / 4 (and config 1's model on the GPU): the UNMODIFIED reference model
+    (lit_gpt.model.GPT from baseline/_ref, random-init weights, synthetic tokens) with its attention
+    dispatch rebound to the CUDA path; one step = forward + backward (+ an AdamW step on the LoRA
+    parameters for the Llama-2 fine-tune config).  Reports tokens/s and the share of the step spent in
+    the FastMax kernels (their own CUDA-event times)."""
+    from oracle import ref_loader as rl          # bench infrastructure: builds the reference's model
+    from fastmax_experiments_b200 import _lib
+    from fastmax_experiments_b200.attention import patch_causal_self_attention
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    name = args.model
+    T = args.seq if args.seq != HL["N"] else MODEL_SEQ.get(name, 2048)
+    lora = LORA if name.startswith("Llama-2") else None
+    rl.reference_model()
+    from lit_gpt.model import CausalSelfAttention
+    patch_causal_self_attention(CausalSelfAttention)
+    model, cfg = rl.build_gpt(name, attn_alg="fastmax", block_size=T, lora=lora, device=dev, dtype=torch.bfloat16)
+    opt = None
+    if lora:
+        from lit_gpt.lora import mark_only_lora_as_trainable
+        mark_only_lora_as_trainable(model)
+        opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=3e-4)
+    step, idx = _model_step_fn(model, cfg, T, dev, opt)
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.finish()
+    ms_step = e0.elapsed_time(e1) / args.steps
+    _lib.profile_enable(True)
+    step()
+    torch.cuda.synchronize()
+    recs = _lib.profile_fetch()
+    _lib.profile_enable(False)
+    attn_ms = sum(ms for _, ms in recs)
+    kern = {}
+    for nm, ms in recs:
+        a = kern.setdefault(nm, [0, 0.0])
+        a[0] += 1
+        a[1] += ms
+    nparam = sum(p.numel() for p in model.parameters())
+    _emit(json.dumps({
+        "metric": "model_fwd_bwd_tokens_per_s", "value": T / (ms_step * 1e-3), "unit": UNIT, "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"{name} (unmodified lit_gpt model, random init, {nparam / 1e6:.0f} M parameters"
+                               f"{', LoRA r=8 on q,v, base frozen (bf16: no bitsandbytes in this image)' if lora else ''}) "
+                               f"with fastmax p=2 causal attention on the CUDA path, B=1, seq {T}, forward+backward"
+                               f"{' + AdamW step on the LoRA parameters' if lora else ''}",
+                   "model": name, "seq": T, "n_layer": cfg.n_layer, "n_head": cfg.n_head,
+                   "n_query_groups": cfg.n_query_groups, "head_size": cfg.head_size, "attn_alg": "fastmax"},
+        "clocks": clocks, "loss": float(loss), "gpu_launches": len(recs) * args.steps,
+        "attention": {"ms_per_step": round(attn_ms, 3), "share_of_step": round(attn_ms / ms_step, 4),
+                      "kernels": {n: {"launches": a[0], "ms": round(a[1], 3)} for n, a in
+                                  sorted(kern.items(), key=lambda kv: -kv[1][1])}},
+    }))
+
+
+def run_reference_model(args) -> None:
+    """BASELINE.json config 1: the unmodified reference model with its own attention path (q,k,v -> host ->
+    attention_mechanisms/fastmax.py, lit_gpt/model.py:475-487) forward+backward on the host cores."""
+    from oracle import ref_loader as rl
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    name = args.model
+    T = args.seq if args.seq != HL["N"] else MODEL_SEQ.get(name, 2048)
+    with rl.cuda_hop_neutralised():
+        model, cfg = rl.build_gpt(name, attn_alg="fastmax", block_size=T)
+        step, _ = _model_step_fn(model, cfg, T, "cpu")
+        warm = min(args.warmup, 1 if T <= 512 else 0)     # a step takes about a minute at seq 2048
+        for _ in range(warm):
+            step()
+        steps = max(1, min(args.steps, 3 if T <= 512 else 1))
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            loss = step()
+        dt = (time.perf_counter() - t0) / steps
+    value = T / dt
+    _emit(json.dumps({
+        "impl": "reference", "metric": "model_fwd_bwd_tokens_per_s", "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{name} with the reference's own fastmax p=2 causal attention, forward+backward on the "
+                               f"host, B=1, seq {T}, synthetic tokens (BASELINE.json configs[0])",
+                   "model": name, "seq": T, "attn_alg": "fastmax"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference",
+                         "sample": f"{steps} whole step(s) of the unmodified lit_gpt model + attention_mechanisms/fastmax.py"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "loss": float(loss), "gpu_launches": 0,
     }))
 
 
@@ -227,9 +367,12 @@ def main() -> None:
     ap.add_argument("--algo", default="auto", choices=["auto", "exact", "moments"])
     ap.add_argument("--seq", type=int, default=HL["N"], help="override N (diagnostics only)")
     ap.add_argument("--batch", type=int, default=HL["B"], help="override B (diagnostics only)")
-    ap.add_argument("--workload", default="headline", choices=["headline", "sp"],
+    ap.add_argument("--workload", default="headline", choices=["headline", "sp", "model"],
                     help="headline: (b,h)-sharded op at B=8,H=32,N=16k (default); sp: sequence-parallel "
-                         "long-context scan, B=1,H=32, --seq tokens split over the ranks (BASELINE config 5)")
+                         "long-context scan, B=1,H=32, --seq tokens split over the ranks (BASELINE config 5); "
+                         "model: the unmodified reference model with the CUDA attention path (configs 1, 3, 4)")
+    ap.add_argument("--model", default="pythia-14m", choices=sorted(MODEL_SEQ),
+                    help="--workload model: which lit_gpt config (default sequence lengths: BASELINE.json configs)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -245,6 +388,10 @@ def main() -> None:
         return
     if args.workload == "sp":
         run_sequence_parallel(args, rank, world, local)
+        return
+    if args.workload == "model":
+        if rank == 0:
+            run_model(args, local)
         return
 
     import torch.distributed as dist
@@ -425,11 +572,9 @@ def main() -> None:
     # ---- CPU baseline beside it (rank 0, N=1 only) ------------------------------------------------
     if rank == 0 and world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
-        rate, secs = cpu_port_rate(512, D, repeats=3, threads=threads)
-        out["cpu_baseline"] = {
-            "value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"oracle port of fastmax.py (factorised einsum/cumsum), fp32, best of 3 fwd+bwd on a "
-                      f"(B=1,H=1,N=512,D={D}) slice = {secs:.2f} s; tokens/s = units/s / H={H}"}
+        rate, secs, kind = cpu_rate(512, D, repeats=3, threads=threads)
+        out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": kind,
+                               "sample": f"best of 3 ({secs:.2f} s each): " + _cpu_sample_text(kind, 512)}
 
     if rank == 0:
         _emit(json.dumps(out))

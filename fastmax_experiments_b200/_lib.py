@@ -40,20 +40,39 @@ class FastmaxError(RuntimeError):
 
 
 _lib = None
+_dev = None
+ABI_VERSION = 3          # FASTMAX_B200_ABI_VERSION of include/fastmax_b200.h these argtypes were written for
+
+
+def load_dev() -> C.CDLL:
+    """The developer library (product + csrc/dev/: micro-benchmarks, primitive self-test); tools and one test only."""
+    global _dev
+    if _dev is None:
+        load()
+        _dev = C.CDLL(os.path.join(os.path.dirname(LIB_PATH), "libfastmax_b200_dev.so"))
+    return _dev
 
 
 def load() -> C.CDLL:
-    """dlopen the in-tree library (building it first if nvcc is available and it is stale)."""
+    """dlopen the in-tree library.  With nvcc on the PATH the library is (re)built first when its sources
+    changed (a digest check, so the common case costs a few file reads); without nvcc -- the GPU box -- the
+    prebuilt file is used as is.  Either way its ABI version must be the one this binding was written for."""
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        from . import build as _build
-        _build.build()
+    if "FASTMAX_LIB" not in os.environ:
+        import shutil
+        if shutil.which("nvcc") or not os.path.exists(LIB_PATH):
+            from . import build as _build
+            _build.build()
     if not os.path.exists(LIB_PATH):
         raise FastmaxError(f"{LIB_PATH} is missing: run `python -m fastmax_experiments_b200.build` "
                            "(there is no CPU/PyTorch fallback)")
     lib = C.CDLL(LIB_PATH)
+    lib.fastmax_abi_version.restype = C.c_int
+    if lib.fastmax_abi_version() != ABI_VERSION:
+        raise FastmaxError(f"{LIB_PATH} has ABI version {lib.fastmax_abi_version()}, this binding expects "
+                           f"{ABI_VERSION}: rebuild with `python -m fastmax_experiments_b200.build --force`")
     vp, i32, f32, sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
     lib.fastmax_abi_version.restype = i32
     lib.fastmax_error_string.restype = C.c_char_p

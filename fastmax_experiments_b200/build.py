@@ -11,6 +11,9 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfastmax_b200.so")
+# developer library: the product objects plus csrc/dev/ (micro-benchmarks and the known-answer test of the
+# sm_100a primitives; tools/*.py and tests/test_gpu_umma.py load it) -- kept out of the product .so
+DEV_LIB_NAME = "libfastmax_b200_dev.so"
 OBJ = os.path.join(HERE, "build")
 
 NVCC_FLAGS = [
@@ -25,9 +28,14 @@ def sources() -> list[str]:
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
+def dev_sources() -> list[str]:
+    d = os.path.join(CSRC, "dev")
+    return sorted(os.path.join(d, f) for f in os.listdir(d) if f.endswith(".cu"))
+
+
 def _digest() -> str:
     h = hashlib.sha256()
-    for root in (CSRC, os.path.join(HERE, "..", "include")):
+    for root in (CSRC, os.path.join(CSRC, "dev"), os.path.join(HERE, "..", "include")):
         for f in sorted(os.listdir(root)):
             if f.endswith((".cu", ".cuh", ".h")):
                 with open(os.path.join(root, f), "rb") as fh:
@@ -76,9 +84,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with cf.ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
         objs = list(ex.map(compile_one, sources()))
-    r = subprocess.run([nvcc, "-shared", "-o", LIB, *objs, "-lcudart"], capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+        dev_objs = list(ex.map(compile_one, dev_sources()))
+    for out, oo in ((LIB, objs), (os.path.join(os.path.dirname(LIB), DEV_LIB_NAME), objs + dev_objs)):
+        r = subprocess.run([nvcc, "-shared", "-o", out, *oo, "-lcudart"], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     with open(stamp, "w") as fh:
         fh.write(digest)
     return LIB

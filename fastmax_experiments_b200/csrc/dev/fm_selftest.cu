@@ -3,8 +3,8 @@
 // shared memory (SS) and from tensor memory (TS), TMEM ld/st lane mapping.  tests/ compare the
 // four 128x64 products against torch.matmul.  (Test infrastructure inside the library so the
 // primitives are validated on the same code path the production kernels use.)
-#include "fm_common.cuh"
-#include "fm_sm100.cuh"
+#include "../fm_common.cuh"
+#include "../fm_sm100.cuh"
 
 namespace fm {
 namespace {

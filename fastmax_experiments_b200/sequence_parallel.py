@@ -142,20 +142,35 @@ def _token_offset(n_local: int, group, device) -> int:
     return int(counts[:rank].sum().item())
 
 
+def _require_supported(q) -> None:
+    if not q.is_cuda or q.dtype != torch.bfloat16 or q.shape[-1] != 64:
+        raise _lib.FastmaxError("fastmax_sp: bf16 CUDA tensors with D = 64 only (no CPU fallback)")
+
+
+def _zero_state(B: int, H: int, device) -> torch.Tensor:
+    """The moment state of no tokens (all-zero record): what a rank with an empty token range contributes."""
+    return torch.zeros(_lib.load().fastmax_sp_state_bytes(B, H), dtype=torch.uint8, device=device)
+
+
 class FastmaxSPFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, q, k, v, group, normalize_term, tensors_normalized, p):
+    def forward(ctx, q, k, v, group, normalize_term, tensors_normalized, p, token_offset):
         if p not in (1, 2):
             raise ValueError(f"p should be 1 or 2, got p={p}")
-        if not q.is_cuda or q.dtype != torch.bfloat16 or q.shape[-1] != 64:
-            raise _lib.FastmaxError("fastmax_sp: bf16 CUDA tensors with D = 64 only")
+        _require_supported(q)
         B, H, N, D = q.shape
         c = 1.0 if tensors_normalized is True else normalize_term * math.sqrt(D)
         q_, k_, v_ = q.contiguous(), k.contiguous(), v.contiguous()
-        offset = _token_offset(N, group, q.device)
+        offset = _token_offset(N, group, q.device) if token_offset is None else int(token_offset)
         red = lambda gathered, world, rank, d: sp_reduce(gathered, world, rank, d, B, H)
-        init = exchange_states(sp_local_state(k_, v_, p), group, 0, red)
-        o, g = sp_fwd(q_, k_, v_, init, offset, 1.0 / c, p)
+        # a rank whose token range is empty (partition() of a short sequence) still takes part in both
+        # exchanges, with the state of no tokens, and returns empty outputs
+        local = sp_local_state(k_, v_, p) if N > 0 else _zero_state(B, H, q.device)
+        init = exchange_states(local, group, 0, red)
+        if N > 0:
+            o, g = sp_fwd(q_, k_, v_, init, offset, 1.0 / c, p)
+        else:
+            o, g = torch.empty_like(q_), torch.empty(B, H, 0, dtype=torch.float32, device=q.device)
         ctx.save_for_backward(q_, k_, v_, o, g)
         ctx.init, ctx.offset, ctx.inv_c, ctx.p, ctx.group = init, offset, 1.0 / c, p, group
         return o
@@ -166,12 +181,18 @@ class FastmaxSPFunction(torch.autograd.Function):
         B, H, N, D = q.shape
         do = o_grad.to(q.dtype).contiguous()
         red = lambda gathered, world, rank, d: sp_reduce(gathered, world, rank, d, B, H)
-        init_rev = exchange_states(sp_local_state_rev(q, o, g, do, ctx.p), ctx.group, 1, red)
-        dq, dk, dv = sp_bwd(q, k, v, o, g, do, ctx.init, init_rev, ctx.offset, ctx.inv_c, ctx.p)
-        return dq, dk, dv, None, None, None, None
+        local = sp_local_state_rev(q, o, g, do, ctx.p) if N > 0 else _zero_state(B, H, q.device)
+        init_rev = exchange_states(local, ctx.group, 1, red)
+        if N > 0:
+            dq, dk, dv = sp_bwd(q, k, v, o, g, do, ctx.init, init_rev, ctx.offset, ctx.inv_c, ctx.p)
+        else:
+            dq, dk, dv = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
+        return dq, dk, dv, None, None, None, None, None
 
 
-def fastmax_sp(q, k, v, group=None, normalize_term=8, tensors_normalized=False, p=2):
+def fastmax_sp(q, k, v, group=None, normalize_term=8, tensors_normalized=False, p=2, token_offset=None):
     """Causal FastMax over a sequence sharded across `group` (default: the world group): every rank
-    passes its own contiguous token range (B, H, N_local, 64) in rank order."""
-    return FastmaxSPFunction.apply(q, k, v, group, normalize_term, tensors_normalized, p)
+    passes its own contiguous token range (B, H, N_local, 64) in rank order (N_local may be 0).
+    `token_offset` = number of tokens held by earlier ranks; a caller that knows its partition passes it
+    (``partition(n, world, rank)[0]``), otherwise it is found with one small all-gather and a host read."""
+    return FastmaxSPFunction.apply(q, k, v, group, normalize_term, tensors_normalized, p, token_offset)

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define FASTMAX_B200_ABI_VERSION 2
+#define FASTMAX_B200_ABI_VERSION 3
 
 /* error codes */
 #define FASTMAX_OK              0

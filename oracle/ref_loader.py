@@ -142,7 +142,7 @@ def cuda_hop_neutralised():
 
 
 def build_gpt(name: str, attn_alg: str = "fastmax", block_size: int | None = None, seed: int = 0, lora: dict | None = None,
-              **overrides):
+              device=None, dtype=None, **overrides):
     """Random-init reference model ``GPT(Config.from_name(name, attn_alg=...))`` with ``_init_weights``
     (lit_gpt/model.py:245-252).  ``lora``: kwargs of lit_gpt.lora.Config (r, alpha, to_query, ...) to build the
     LoRA variant (finetune/lora.py:40-48) instead."""
@@ -152,12 +152,19 @@ def build_gpt(name: str, attn_alg: str = "fastmax", block_size: int | None = Non
     if block_size is not None:
         kw["block_size"] = block_size
     torch.manual_seed(seed)
-    if lora:
-        from lit_gpt import lora as lit_lora
-        cfg = lit_lora.Config.from_name(name, **kw, **lora)
-        model = lit_lora.GPT(cfg)
-    else:
-        cfg = lit_gpt.Config.from_name(name, **kw)
-        model = lit_gpt.GPT(cfg)
-    model.apply(model._init_weights)
+    old_dtype = torch.get_default_dtype()
+    if dtype is not None:
+        torch.set_default_dtype(dtype)
+    try:
+        with (torch.device(device) if device is not None else contextlib.nullcontext()):
+            if lora:
+                from lit_gpt import lora as lit_lora
+                cfg = lit_lora.Config.from_name(name, **kw, **lora)
+                model = lit_lora.GPT(cfg)
+            else:
+                cfg = lit_gpt.Config.from_name(name, **kw)
+                model = lit_gpt.GPT(cfg)
+            model.apply(model._init_weights)
+    finally:
+        torch.set_default_dtype(old_dtype)
     return model, cfg

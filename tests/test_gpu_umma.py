@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 
 
 def test_umma_selftest_matches_matmul():
-    lib = _lib.load()
+    lib = _lib.load_dev()
     lib.fastmax_selftest_umma.restype = ctypes.c_int
     lib.fastmax_selftest_umma.argtypes = [ctypes.c_void_p] * 5
     torch.manual_seed(0)

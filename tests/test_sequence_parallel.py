@@ -63,6 +63,54 @@ def test_exchange_states_gloo(world):
     assert all(ret[r] for r in range(world)), dict(ret)
 
 
+def _toy_worker(rank, world, port, n_total, ret):
+    """FastmaxSPFunction's control flow over gloo with toy stand-ins for the five kernel wrappers (a "state" is
+    the sum of the local k rows; o = q + state of everything before; the reverse state is the sum of do): ranks
+    with an EMPTY token range must take part in both exchanges instead of leaving the others in the collective."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sp._require_supported = lambda q: None
+        sp._zero_state = lambda B, H, dev: torch.zeros(B, H, 4)
+        sp.sp_local_state = lambda k, v, p: k.sum(2)
+        sp.sp_local_state_rev = lambda q, o, g, do, p: do.sum(2)
+        sp.sp_reduce = lambda gathered, w, r, d, B, H: (gathered[:r] if d == 0 else gathered[r + 1:]).sum(0)
+
+        def toy_fwd(q, k, v, init, off, inv_c, p):
+            pre = torch.cumsum(k, 2) - k + (init[:, :, None] if init is not None else 0)
+            return q + pre, torch.full(q.shape[:3], float(off))
+
+        def toy_bwd(q, k, v, o, g, do, init_f, init_r, off, inv_c, p):
+            suf = torch.flip(torch.cumsum(torch.flip(do, [2]), 2), [2]) - do + (init_r[:, :, None] if init_r is not None else 0)
+            return do.clone(), suf, torch.zeros_like(v)
+
+        sp.sp_fwd, sp.sp_bwd = toy_fwd, toy_bwd
+        gen = torch.Generator().manual_seed(0)
+        q, k, v, do = (torch.randint(-3, 4, (1, 2, n_total, 4), generator=gen).float() for _ in range(4))
+        a0, a1 = sp.partition(n_total, world, rank)
+        ql, kl, vl = (t[:, :, a0:a1].clone().requires_grad_(True) for t in (q, k, v))
+        o = sp.fastmax_sp(ql, kl, vl, p=2, token_offset=a0)
+        o.backward(do[:, :, a0:a1])
+        ok = o.shape[2] == a1 - a0
+        ok &= bool((o.detach() == (q + torch.cumsum(k, 2) - k)[:, :, a0:a1]).all())
+        suf_full = torch.flip(torch.cumsum(torch.flip(do, [2]), 2), [2]) - do
+        ok &= bool((kl.grad == suf_full[:, :, a0:a1]).all())
+        ret[rank] = (bool(ok), a1 - a0)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_total", [(3, 1000), (2, 100), (3, 1536)])
+def test_sequence_parallel_protocol_with_empty_tail_ranks(world, n_total):
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_toy_worker, args=(world, port, n_total, ret), nprocs=world, join=True)
+    assert all(ret[r][0] for r in range(world)), dict(ret)
+    if n_total <= 512 * (world - 1):
+        assert any(ret[r][1] == 0 for r in range(world))      # the case under test: a rank without tokens
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("world,N,p", [(2, 2048, 2), (4, 4096, 2), (3, 3000, 2), (2, 1536, 1)])
 def test_sequence_parallel_kernels_emulated_ranks(world, N, p):

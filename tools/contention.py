@@ -3,7 +3,7 @@ import sys, os, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from fastmax_experiments_b200 import _lib
-lib = _lib.load()
+lib = _lib.load_dev()
 f = lib.fastmax_selftest_contention
 f.restype = ctypes.c_int
 f.argtypes = [ctypes.c_int] * 4 + [ctypes.c_uint, ctypes.c_void_p, ctypes.c_void_p]

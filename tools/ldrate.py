@@ -2,7 +2,7 @@ import sys, os, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from fastmax_experiments_b200 import _lib
-lib = _lib.load()
+lib = _lib.load_dev()
 lib.fastmax_selftest_ldrate.restype = ctypes.c_int
 lib.fastmax_selftest_ldrate.argtypes = [ctypes.c_int] * 4 + [ctypes.c_void_p, ctypes.c_void_p]
 out = torch.zeros(2, dtype=torch.int64, device="cuda")
