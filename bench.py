@@ -278,53 +278,115 @@ def run_reference_model(args) -> None:
 
 
 # ----------------------------------------------------------------------------------------------
-def run_sequence_parallel(args, rank: int, world: int, local: int) -> None:
-    """BASELINE.json config 5: p=2 causal fwd+bwd of ONE long sequence set (B=1, H=32, D=64, N=--seq)
-    split by token ranges over the ranks; one state all-gather per scan direction over NCCL."""
+def _sp_parity(q, k, v, do, o, g, dq, dk, dv, a0: int, world: int, rank: int, c: float) -> dict:
+    """In-run parity check of the sequence-parallel path over the real collective: for head (b=0, h=0) every rank
+    gathers the whole sequence of q, k, v, do and of the computed o, g, and checks sampled LOCAL rows of o, g, dq
+    and sampled local columns of dk, dv against the dense formula evaluated in fp64 with plain torch ops on its
+    GPU (the recipe of tests/test_gpu_parity.py::_sampled_rows_and_columns_check).  Returns the largest per-row
+    relative error of each tensor over all ranks."""
+    import torch.distributed as dist
+    n_loc = q.shape[2]
+
+    def gather(t):      # (n_loc, ...) of head (0, 0) -> (N, ...)
+        parts = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(parts, t.contiguous())
+        return torch.cat(parts, 0)
+
+    Q, K, V, DO, O = (gather(t[0, 0]).double() for t in (q, k, v, do, o))
+    G = gather(g[0, 0]).double()
+    N = Q.shape[0]
+    idx = torch.arange(N, device=q.device)
+    rows = torch.tensor(sorted({a0 + 1 if a0 == 0 else a0, a0 + 511, a0 + 512, a0 + n_loc // 2 + 77, a0 + n_loc - 1}),
+                        device=q.device)
+    cols = torch.tensor(sorted({a0, a0 + 511, a0 + 512, a0 + n_loc // 3 + 5, a0 + n_loc - 2}), device=q.device)
+
+    def worst(x, ref):
+        err = (x.double() - ref).abs().reshape(ref.shape[0], -1).max(-1).values
+        mag = ref.abs().reshape(ref.shape[0], -1).max(-1).values
+        return float((err / mag).max())
+
+    s = Q[rows] @ K.T / c
+    m = (idx[None, :] <= rows[:, None]).double()
+    w = (1 + s + 0.5 * s * s) * m
+    gr = w.sum(-1)
+    o_ref = (w @ V) / gr[:, None]
+    u = DO[rows] / gr[:, None]
+    dlt = (DO[rows] * o_ref).sum(-1) / gr
+    e = (1 + s) * (u @ V.T - dlt[:, None]) * m
+    res = {"o": worst(O[rows], o_ref), "g": worst(G[rows, None], gr[:, None]),
+           "dq": worst(dq[0, 0][rows - a0], e @ K / c)}
+    Uall = DO / G[:, None]
+    Dall = (DO * O).sum(-1) / G
+    st = K[cols] @ Q.T / c
+    mt = (idx[None, :] >= cols[:, None]).double()
+    wt = (1 + st + 0.5 * st * st) * mt
+    et = (1 + st) * (V[cols] @ Uall.T - Dall[None, :]) * mt
+    res["dv"] = worst(dv[0, 0][cols - a0], wt @ Uall)
+    res["dk"] = worst(dk[0, 0][cols - a0], et @ Q / c)
+    t = torch.tensor([res[n] for n in ("o", "g", "dq", "dk", "dv")], device=q.device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return {n: float(x) for n, x in zip(("o", "g", "dq", "dk", "dv"), t.tolist())}
+
+
+def measure_sequence_parallel(args, rank: int, world: int, dev, N: int, steps: int, warmup: int) -> dict:
+    """BASELINE.json config 5: p=2 causal fwd+bwd of ONE long sequence set (B=1, H=32, D=64, N tokens) split by
+    token ranges over the ranks; one state all-gather per scan direction over NCCL.  Timed like the headline
+    (barrier + synchronize on both sides, CUDA events, max over ranks), then checked in the same run against the
+    dense formula (`_sp_parity`).  The process group must exist."""
     import torch.distributed as dist
     from fastmax_experiments_b200 import _lib
     from fastmax_experiments_b200.sequence_parallel import fastmax_sp, partition
 
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-    os.environ.setdefault("MASTER_PORT", "29511")
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries exactly one JSON line
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
-    lib = _lib.load()
     B, H, D, p = 1, HL["H"], HL["D"], HL["p"]
-    N = args.seq if args.seq != HL["N"] else 131072
     a0, a1 = partition(N, world, rank)
     gen = torch.Generator(device=dev).manual_seed(4321 + rank)
     q, k, v = (torch.randn(B, H, a1 - a0, D, device=dev, generator=gen).to(torch.bfloat16).requires_grad_(True)
                for _ in range(3))
     do = torch.randn(B, H, a1 - a0, D, device=dev, generator=gen).to(torch.bfloat16)
+    keep = {}
 
     def step():
         for t in (q, k, v):
             t.grad = None
-        o = fastmax_sp(q, k, v, p=p)
+        o = fastmax_sp(q, k, v, p=p, token_offset=a0)
         o.backward(do)
+        keep["o"] = o
 
     def barrier():
         dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(dev.index)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
     e1.record()
     barrier()
     clocks = sampler.finish()
     t = torch.tensor([e0.elapsed_time(e1)], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
+    ms_step = float(t.item()) / steps
+    # the exchange alone: all-gather of one state record set per rank (what each scan direction moves)
+    lib = _lib.load()
+    rec = torch.empty(lib.fastmax_sp_state_bytes(B, H), dtype=torch.uint8, device=dev)
+    gathered = [torch.empty_like(rec) for _ in range(world)]
+    ag_ms = None
+    if world > 1:
+        for _ in range(2):
+            dist.all_gather(gathered, rec)
+        barrier()
+        e0.record()
+        for _ in range(5):
+            dist.all_gather(gathered, rec)
+        e1.record()
+        barrier()
+        ag_ms = e0.elapsed_time(e1) / 5
+    # per-kernel times of one more step
     _lib.profile_enable(True)
     step()
     torch.cuda.synchronize()
@@ -335,25 +397,69 @@ def run_sequence_parallel(args, rank: int, world: int, local: int) -> None:
         a = kern.setdefault(name, [0, 0.0])
         a[0] += 1
         a[1] += ms
+    # parity over the real collective
+    parity = None
+    if world > 1 and (a1 - a0) >= 1024 and N % world == 0:
+        with torch.no_grad():
+            # g is not returned by the autograd op: recompute this rank's forward through the raw entry points
+            from fastmax_experiments_b200.sequence_parallel import (exchange_states, sp_fwd, sp_local_state, sp_reduce)
+            red = lambda gathered, w, r, d: sp_reduce(gathered, w, r, d, B, H)
+            init = exchange_states(sp_local_state(k.detach(), v.detach(), p), None, 0, red)
+            o2, g2 = sp_fwd(q.detach(), k.detach(), v.detach(), init, a0, 1.0 / (8 * D ** 0.5), p)
+            parity = _sp_parity(q.detach(), k.detach(), v.detach(), do, o2, g2, q.grad, k.grad, v.grad, a0, world, rank,
+                                8 * D ** 0.5)
+            parity["tolerance"] = 2e-2
+            parity["ok"] = all(x <= 2e-2 for n, x in parity.items() if n in ("o", "g", "dq", "dk", "dv"))
+            parity["how"] = ("head (b=0,h=0): sampled local rows of o, g, dq and columns of dk, dv on every rank vs the "
+                             "dense formula in fp64 (torch ops on the gathered sequence); worst per-row relative error, "
+                             "max over ranks")
     f_fwd, f_bwd = flops_alg(D, p)
     peaks = load_peaks()
     ach = B * H * N * (f_fwd + f_bwd) / (ms_step * 1e-3) / 1e12
+    one = None      # best single-GPU rate of the same kernels on the same problem sizes (committed bench lines)
+    try:
+        one = json.load(open(os.path.join(ROOT, "profiles", "bench", "r2_sp_single_gpu.json")))
+    except Exception:
+        pass
+    value = B * N / (ms_step * 1e-3)
+    eff = None
+    if one and world > 1:
+        best1 = max(one.get("tokens_per_s", {}).values())
+        eff = {"vs_best_single_gpu_rate": round(value / (world * best1), 4), "single_gpu_tokens_per_s": one["tokens_per_s"],
+               "note": "strong scaling: value / (n_gpus * best single-GPU rate over N in {128k, 1M})"}
+    return {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"sequence-parallel fastmax p=2 causal fwd+bwd B={B} H={H} N={N} D={D} bf16, "
+                               f"tokens split over {world} rank(s), state all-gather over NCCL",
+                   "B": B, "H": H, "N": N, "D": D, "p": p, "causal": True, "local_tokens": a1 - a0,
+                   "l2": "inputs larger than L2"},
+        "clocks": clocks, "gpu_launches": len(recs) * steps,
+        "roofline": {"bound": "tensor", "achieved": round(ach, 3), "peak": peaks["tflops"] * world,
+                     "unit": "TFLOP/s", "frac": round(ach / (peaks["tflops"] * world), 5), "traffic": None,
+                     "scope": "whole fwd+bwd step over all ranks (algorithmic flops; the per-rank state "
+                              "reduce passes are redundant work and not counted)"},
+        "parity": parity, "efficiency": eff,
+        "exchange": {"all_gather_ms": ag_ms, "bytes_per_rank": int(rec.numel()), "per_step": 2,
+                     "redundant_flop_fraction": round(2 * (2 * D * D * (D + 1)) * (20 + 2) / 34 / (f_fwd + f_bwd), 4),
+                     "note": "one extra packed state-build pass over the local tokens per scan direction"},
+        "kernels": {n: {"launches": a[0], "ms": round(a[1], 4)} for n, a in sorted(kern.items(), key=lambda kv: -kv[1][1])},
+    }
+
+
+def run_sequence_parallel(args, rank: int, world: int, local: int) -> None:
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29511")
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries exactly one JSON line
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    N = args.seq if args.seq != HL["N"] else 131072
+    out = measure_sequence_parallel(args, rank, world, dev, N, args.steps, args.warmup)
     if rank == 0:
-        _emit(json.dumps({
-            "metric": METRIC, "value": B * N / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"sequence-parallel fastmax p=2 causal fwd+bwd B={B} H={H} N={N} D={D} bf16, "
-                                   f"tokens split over {world} rank(s), state all-gather over NCCL",
-                       "B": B, "H": H, "N": N, "D": D, "p": p, "causal": True, "local_tokens": a1 - a0,
-                       "l2": "inputs larger than L2"},
-            "clocks": clocks, "gpu_launches": len(recs) * args.steps,
-            "roofline": {"bound": "tensor", "achieved": round(ach, 3), "peak": peaks["tflops"] * world,
-                         "unit": "TFLOP/s", "frac": round(ach / (peaks["tflops"] * world), 5), "traffic": None,
-                         "scope": "whole fwd+bwd step over all ranks (algorithmic flops; the per-rank state "
-                                  "reduce passes are redundant work and not counted)"},
-            "kernels": {n: {"launches": a[0], "ms": round(a[1], 4)} for n, a in sorted(kern.items(), key=lambda kv: -kv[1][1])},
-        }))
+        _emit(json.dumps(out))
     dist.destroy_process_group()
 
 
@@ -374,6 +480,7 @@ def main() -> None:
     ap.add_argument("--model", default="pythia-14m", choices=sorted(MODEL_SEQ),
                     help="--workload model: which lit_gpt config (default sequence lengths: BASELINE.json configs)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-sp", action="store_true", help="N > 1: skip the sequence-parallel (config 5) leg")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -575,6 +682,13 @@ def main() -> None:
         rate, secs, kind = cpu_rate(512, D, repeats=3, threads=threads)
         out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": kind,
                                "sample": f"best of 3 ({secs:.2f} s each): " + _cpu_sample_text(kind, 512)}
+
+    # ---- N > 1: the sequence-parallel split of north_star (BASELINE.json config 5, N = 1M) in the same run ------
+    if world > 1 and not args.no_sp:
+        del q, k, v, do
+        torch.cuda.empty_cache()
+        sp = measure_sequence_parallel(args, rank, world, dev, 1 << 20, steps=max(2, min(args.steps, 3)), warmup=3)
+        out["sp"] = sp
 
     if rank == 0:
         _emit(json.dumps(out))

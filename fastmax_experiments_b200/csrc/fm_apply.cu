@@ -20,17 +20,24 @@
 //   forward o : X = Y = q, state S, MN-major        dq : X = q, Y = do/g, state S, K-major
 //   dv        : X = Y = k, state R, MN-major        dk : X = k, Y = v,    state R, K-major
 //
-// CTA = 2 token tiles of 128 rows, 19 warps:
+// CTA = 2 token tiles of 128 rows, 21 warps:
 //   * 16 generator warps = 2 tiles x 2 sets x 4 tensor-memory lane quadrants; thread = token row.  The unit
 //     of hand-over is a PAIR of slabs (K = 128, 64 columns of A): the sets take pairs alternately, so one
-//     pair costs a warp one buffer wait, two 32-column tcgen05.st, one wait::st and one arrive.  (Measured
+//     pair costs a warp one buffer wait, four 16-column tcgen05.st, one wait::st and one arrive.  (Measured
 //     with one warp per tile quadrant and a hand-over per slab: ~700 cycles per slab in the generator,
 //     against 256 cycles of MMA -- the generators, not the buffer depth, bounded the kernel.)
-//   * 2 MMA issuer warps, one per tile (converged warp, descriptors from the constant bank, tensor-memory
-//     addresses as immediates, see fm_sm100.cuh); A buffers: 3 per tile of 64 columns.
+//   * 4 MMA issuer warps = 2 tiles x 2 (even / odd pairs); converged warps, descriptors from the constant
+//     bank, tensor-memory addresses as immediates (fm_sm100.cuh).  An issuer's own sequence per pair (two
+//     barrier waits, fence, elect, commit) costs ~500 cycles before any MMA -- measured with everything else
+//     compiled out: 1.2 ms per launch -- and its MMA issue blocks while the pipe is busy, so with one issuer
+//     per tile the pipe idled during every hand-over; two per tile overlap them.  One commit per pair: the
+//     `done` barrier of a ring stage releases both the stage and the A buffers of that pair.
 //   * 1 TMA producer warp streaming slab pairs through a 6-stage ring (16 KiB per stage); symmetric uses
 //     fetch only the rows they need, one box per slab (four tensor maps with 64/48/32/16-row boxes).
 //     (Letting the issuer warps feed the ring coupled the tiles' MMA issue to each other's ring waits: 2x slower.)
+//   Every barrier is waited on by the same warps in every phase (a waiter that skips a phase is fooled by
+//   the parity of the older one): the barriers are indexed by ring stage (pair mod 6), and a stage always
+//   belongs to the same generator set and the same issuers.
 #include "fm_common.cuh"
 #include "fm_sm100.cuh"
 #include "fm_moments.cuh"
@@ -38,6 +45,18 @@
 FM_TIMING_DEFINE(apply)
 #ifndef FM_EXP
 #define FM_EXP 0      // developer experiments (wrong results): 1 no MMAs, 2 no operand stores, 4 no slab loads, 8 no products
+#endif
+
+#ifdef FM_TRACE
+// developer event trace of ONE CTA (blockIdx = (1, 0)): clock64 at the hand-over points of every slab pair
+static __device__ long long fm_trace_tab[8][40];
+extern "C" int fastmax_debug_trace_fetch_apply(long long* out) {
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(out, fm_trace_tab, sizeof(long long) * 8 * 40) == cudaSuccess ? 0 : -4;
+}
+#define FM_TR(ev, s) do { if (blockIdx.x == 1 && blockIdx.y == 0) fm_trace_tab[ev][s] = clock64(); } while (0)
+#else
+#define FM_TR(ev, s) ((void)0)
 #endif
 
 namespace fm {
@@ -52,14 +71,14 @@ constexpr int NSTAGE = 6;                   // ring stages (one slab pair each: 
 constexpr int NPAIR = 33;                   // 32 pairs of second-order slabs + slab 64 alone
 constexpr int ACOL = 64 * T;                // first A-buffer column
 constexpr int GEN_WARPS = 16;
-constexpr int THREADS = 19 * 32;
+constexpr int THREADS = 21 * 32;
 constexpr int RING_BYTES = NSTAGE * 16384;
 constexpr int STG_BYTES = T * 16384;        // bf16 output staging (TMA store source)
 constexpr int BAR_OFF = RING_BYTES + STG_BYTES;
 constexpr int SMEM = BAR_OFF + 1024 + 1024 /*align slack*/;
 // barrier indices
-constexpr int B_FULL = 0, B_EMPTY = NSTAGE, B_AREADY = 2 * NSTAGE, B_AFREE = B_AREADY + T * NBUF,
-              B_ACC = B_AFREE + T * NBUF, NBARS = B_ACC + T;
+constexpr int B_FULL = 0, B_DONE = NSTAGE, B_AREADY = 2 * NSTAGE /* [T][NSTAGE] */, B_ACC = B_AREADY + T * NSTAGE,
+              NBARS = B_ACC + T;
 static_assert(NBARS * 8 <= 512, "barrier block");
 static_assert(64 * T + 64 * T * NBUF <= 512, "tensor memory");
 }  // namespace gen
@@ -88,84 +107,91 @@ __device__ __forceinline__ void st_a(uint32_t taddr, const uint32_t* a) {
   else tmem_st8(taddr, a);
 }
 
-// A[row][8j+w] = xs(j) * Y[16(GX+j) + 2w, +1]: one slab of the generated operand (bf16 pairs)
-template <bool SYM, int GX>
-__device__ __forceinline__ void gen_products(const uint32_t (&Yp)[32], float xf, uint32_t (&a)[32]) {
-  constexpr int NK = 4 - GX;
+// k-steps [J0, J0 + NJ) of one slab of the generated operand: A[row][8j+w] = xs(j) * Y[16(GX+j) + 2w, +1]
+template <bool SYM, int GX, int J0, int NJ>
+__device__ __forceinline__ void gen_store(const uint32_t (&Yp)[32], float xf, uint32_t taddr) {
   const uint32_t xs1 = pack_bf16x2(xf, xf);
   const uint32_t xs2 = SYM ? pack_bf16x2(xf + xf, xf + xf) : xs1;   // blocks above the diagonal count twice
+  uint32_t a[8 * NJ];
 #pragma unroll
-  for (int j = 0; j < NK; ++j)
+  for (int j = 0; j < NJ; ++j)
 #pragma unroll
-    for (int w = 0; w < 8; ++w) a[8 * j + w] = mul_bf16x2(j == 0 ? xs1 : xs2, Yp[8 * (GX + j) + w]);
+    for (int w = 0; w < 8; ++w)
+      a[8 * j + w] = (FM_EXP & 8) ? Yp[8 * (GX + J0 + j) + w] : mul_bf16x2(J0 + j == 0 ? xs1 : xs2, Yp[8 * (GX + J0 + j) + w]);
+  if (FM_EXP & 2) return;
+  if constexpr (NJ == 2) tmem_st16(taddr + 8 * J0, a);
+  else tmem_st8(taddr + 8 * J0, a);
+}
+
+template <bool SYM, int GX>
+__device__ __forceinline__ void gen_slab(const uint32_t (&Yp)[32], float xf, uint32_t taddr) {
+  constexpr int NK = 4 - GX;
+  if constexpr (NK >= 2) gen_store<SYM, GX, 0, 2>(Yp, xf, taddr);
+  if constexpr (NK == 4) gen_store<SYM, GX, 2, 2>(Yp, xf, taddr);
+  if constexpr (NK == 3) gen_store<SYM, GX, 2, 1>(Yp, xf, taddr);
+  if constexpr (NK == 1) gen_store<SYM, GX, 0, 1>(Yp, xf, taddr);
 }
 
 // the slab pairs [S0, S0 + NS) of this warp set (every other pair): generate, store, hand over
 template <bool SYM, int GX>
 __device__ __forceinline__ void gen_phase(const uint32_t (&Yp)[32], const uint32_t* xrow, bool valid, float rho,
                                           uint32_t a_tile, uint64_t* bars, int t, int g, int lane) {
-  constexpr int NK = 4 - GX;
   constexpr int S0 = SYM ? 8 * GX : 0, NS = SYM ? 8 : 32;
   uint32_t xw_next = valid ? __ldg(xrow + S0 + g) : 0u;
 #pragma unroll 1
   for (int s = S0 + g; s < S0 + NS; s += 2) {
     const uint32_t xw = xw_next;
     xw_next = (valid && s + 2 < S0 + NS) ? __ldg(xrow + s + 2) : 0u;
-    const int buf = s % gen::NBUF, use = s / gen::NBUF;
-    const uint32_t abuf = a_tile + 64 * buf;
-    uint32_t a[32];
-    if (!(FM_EXP & 8)) gen_products<SYM, GX>(Yp, __uint_as_float(xw << 16) * rho, a);
-    else {
-#pragma unroll
-      for (int c = 0; c < 32; ++c) a[c] = Yp[c] ^ xw;
-    }
-    // the buffer was last read by the MMAs of pair s - NBUF
-    [[maybe_unused]] const long long w0 = FM_NOW();
-    if (use > 0) mbar_wait_warp(&bars[gen::B_AFREE + t * gen::NBUF + buf], (use - 1) & 1);
-    [[maybe_unused]] const long long w1 = FM_NOW();
+    const uint32_t abuf = a_tile + 64 * (s % gen::NBUF);
+    const bool tr = t == 0 && lane == 0 && (threadIdx.x >> 5 & 3) == 0;
+    if (tr) FM_TR(0, s);
+    // the buffer was last read by the MMAs of pair s - NBUF, whose completion is the `done` of that pair's stage
+    if (s >= gen::NBUF)
+      mbar_wait_warp(&bars[gen::B_DONE + (s - gen::NBUF) % gen::NSTAGE], ((s - gen::NBUF) / gen::NSTAGE) & 1);
+    if (tr) FM_TR(1, s);
     tc_fence_after();
-    if (!(FM_EXP & 2)) st_a<NK>(abuf, a);
-    if (!(FM_EXP & 8)) gen_products<SYM, GX>(Yp, __uint_as_float(xw & 0xffff0000u) * rho, a);
-    if (!(FM_EXP & 2)) st_a<NK>(abuf + 32, a), tmem_wait_st();
+    gen_slab<SYM, GX>(Yp, __uint_as_float(xw << 16) * rho, abuf);
+    gen_slab<SYM, GX>(Yp, __uint_as_float(xw & 0xffff0000u) * rho, abuf + 32);
+    tmem_wait_st();
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(&bars[gen::B_AREADY + t * gen::NBUF + buf]);
-#ifdef FM_TIMING
-    if (threadIdx.x == 0) FM_T(2, w1 - w0), FM_T(3, FM_NOW() - w1);
-#endif
+    if (lane == 0) mbar_arrive(&bars[gen::B_AREADY + t * gen::NSTAGE + s % gen::NSTAGE]);
+    if (tr) FM_TR(2, s);
   }
 }
 
-// MMA issuer of tile TT (a converged warp).  `live` = the tile has rows (a tile past the end of the sequence
-// only keeps the ring protocol going).
-template <bool SYM, int TT>
-__device__ __forceinline__ void issue_tile(const GenParams& P, uint64_t* bars, bool live, int lane) {
+// MMA issuer (TT, PAR): the pairs s = PAR (mod 2) of tile TT.  A converged warp; `live` = the tile has rows
+// (a tile past the end of the sequence only keeps the ring protocol going).
+template <bool SYM, int TT, int PAR>
+__device__ __forceinline__ void issue_pairs(const GenParams& P, uint64_t* bars, bool live, int lane) {
   constexpr uint32_t IDESC = make_idesc_bf16(128, 64, false, SYM);
   constexpr uint32_t BAR0 = FM_SMEM_BASE + gen::BAR_OFF;
 #pragma unroll 1
-  for (int s0 = 0; s0 < gen::NPAIR; s0 += gen::NSTAGE) {
+  for (int s0 = PAR; s0 < gen::NPAIR; s0 += gen::NSTAGE) {
 #pragma unroll
-    for (int u = 0; u < gen::NSTAGE; ++u) {           // u = ring stage (compile time), u % NBUF = A buffer
-      const int s = s0 + u;
+    for (int i = 0; i < 3; ++i) {                     // ring stage u = PAR + 2i (compile time), A buffer u % 3
+      const int u = PAR + 2 * i;
+      const int buf = u % gen::NBUF;
+      const int s = s0 + 2 * i;
       if (s < gen::NPAIR) {
-        constexpr int NB = gen::NBUF;
-        const int buf = u % NB;
         const int nk = (SYM && s < 32) ? 4 - (s >> 3) : 4;
         const bool last = s == gen::NPAIR - 1;
         if (lane == 0) {
-          [[maybe_unused]] const long long i1 = FM_NOW();
-          if (!(FM_EXP & 4)) mbar_wait(&bars[gen::B_FULL + u], (s / gen::NSTAGE) & 1, 2000 + s);
-          [[maybe_unused]] const long long i2 = FM_NOW();
-          if (live) mbar_wait(&bars[gen::B_AREADY + TT * NB + buf], (s / NB) & 1, 3000 + s);
-          else mbar_arrive(&bars[gen::B_EMPTY + u]);
-#ifdef FM_TIMING
-          if (TT == 0) FM_T(6, i2 - i1), FM_T(7, FM_NOW() - i2);
-#endif
+          uint64_t* fb = &bars[gen::B_FULL + u];
+          uint64_t* ab = &bars[gen::B_AREADY + TT * gen::NSTAGE + u];
+          const uint32_t ph = (s / gen::NSTAGE) & 1;
+          if (TT == 0) FM_TR(3, s);
+          // both barriers are usually complete: probe them together so the two probe latencies overlap
+          const bool ok_f = (FM_EXP & 4) ? true : mbar_try_wait(fb, ph);
+          const bool ok_a = live ? mbar_try_wait(ab, ph) : true;
+          if (!ok_f) mbar_wait(fb, ph, 2000 + s);
+          if (!ok_a) mbar_wait(ab, ph, 3000 + s);
+          if (!live) mbar_arrive(&bars[gen::B_DONE + u]);
+          if (TT == 0) FM_TR(4, s);
         }
         __syncwarp();
         if (live) {
           tc_fence_after();
-          [[maybe_unused]] const long long i3 = FM_NOW();
           if (elect_one()) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
@@ -173,23 +199,21 @@ __device__ __forceinline__ void issue_tile(const GenParams& P, uint64_t* bars, b
 #pragma unroll
               for (int j = 0; j < 4; ++j)
                 if (j < nk && !(FM_EXP & 1))
-                  umma_ts(64 * TT, gen::ACOL + 64 * (TT * NB + buf) + 32 * e + 8 * j, P.dB[u][e][j], IDESC,
-                          (uint32_t)((s | e | j) != 0));
+                  umma_ts(64 * TT, gen::ACOL + 64 * (TT * gen::NBUF + buf) + 32 * e + 8 * j, P.dB[u][e][j], IDESC, 1u);
             }
-            if (!last) {
-              umma_commit_addr(BAR0 + 8 * (gen::B_AFREE + TT * NB + buf));
-              umma_commit_addr(BAR0 + 8 * (gen::B_EMPTY + u));
-            } else {
-              umma_commit_addr(BAR0 + 8 * (gen::B_ACC + TT));
-            }
+            umma_commit_addr(BAR0 + 8 * (gen::B_DONE + u));
           }
           __syncwarp();
-#ifdef FM_TIMING
-          if (TT == 0 && lane == 0) FM_T(9, FM_NOW() - i3);
-#endif
+          if (TT == 0 && lane == 0) FM_TR(5, s);
         }
       }
     }
+  }
+  // the tile's accumulator is final when BOTH of its issuers' MMAs have completed
+  if (live) {
+    tc_fence_after();
+    if (elect_one()) umma_commit_addr(BAR0 + 8 * (gen::B_ACC + TT));
+    __syncwarp();
   }
 }
 
@@ -220,9 +244,9 @@ apply_gen_kernel(const __grid_constant__ CUtensorMap tmS64, const __grid_constan
     tmem_relinquish();
   }
   if (tid == 0) {
-    for (int i = 0; i < gen::NSTAGE; ++i) mbar_init(&bars[gen::B_FULL + i], 1), mbar_init(&bars[gen::B_EMPTY + i], gen::T);
-    for (int i = 0; i < gen::T * gen::NBUF; ++i) mbar_init(&bars[gen::B_AREADY + i], 4), mbar_init(&bars[gen::B_AFREE + i], 1);
-    for (int i = 0; i < gen::T; ++i) mbar_init(&bars[gen::B_ACC + i], 1);
+    for (int i = 0; i < gen::NSTAGE; ++i) mbar_init(&bars[gen::B_FULL + i], 1), mbar_init(&bars[gen::B_DONE + i], gen::T);
+    for (int i = 0; i < gen::T * gen::NSTAGE; ++i) mbar_init(&bars[gen::B_AREADY + i], 4);
+    for (int i = 0; i < gen::T; ++i) mbar_init(&bars[gen::B_ACC + i], 2);
     fence_barrier_init();
     tma_prefetch_desc(&tmS64);
     tma_prefetch_desc(&tmS16);
@@ -254,6 +278,18 @@ apply_gen_kernel(const __grid_constant__ CUtensorMap tmS64, const __grid_constan
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   assert_bases(tmem, smem);
+  // accumulators start at zero (every MMA accumulates: the tile's two issuers run independently); warp (t,g,q)
+  // clears columns [32g, 32g+32) of its lane quadrant of tile t
+  if (is_gen) {
+    uint32_t z[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) z[c] = 0u;
+    tmem_st32(tmem + ((uint32_t)(32 * q) << 16) + 64 * t + 32 * g, z);
+    tmem_wait_st();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
 
   if (is_gen) {
     // ---------------------------------------------------------------- generators + epilogue
@@ -264,7 +300,6 @@ apply_gen_kernel(const __grid_constant__ CUtensorMap tmS64, const __grid_constan
       part = reinterpret_cast<const float4*>(P.partial + ((size_t)bh * ((P.N + 127) / 128) + (size_t)(t0 / 128 + t)) *
                                                              PART_TILE_FLOATS) + (32 * q + lane);
     const uint32_t lane_addr = tmem + ((uint32_t)(32 * q) << 16);
-    [[maybe_unused]] const long long g0 = FM_NOW();
     if (has_state && tile_live) {
       const uint32_t a_tile = lane_addr + gen::ACOL + 64 * (t * gen::NBUF);
       const uint32_t* xrow = reinterpret_cast<const uint32_t*>(P.X + grow * 64);
@@ -282,23 +317,19 @@ apply_gen_kernel(const __grid_constant__ CUtensorMap tmS64, const __grid_constan
         asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
       }
       if (g == 0) {
-        // slab 64 alone (pair 32: buffer 32 % 3 = 2, use 10): the plain Y row (first-order term)
-        constexpr int buf = (gen::NPAIR - 1) % gen::NBUF, use = (gen::NPAIR - 1) / gen::NBUF;
-        mbar_wait_warp(&bars[gen::B_AFREE + t * gen::NBUF + buf], (use - 1) & 1);
+        // slab 64 alone (pair 32: stage 32 % 6 = 2, buffer 32 % 3 = 2): the plain Y row (first-order term)
+        constexpr int s = gen::NPAIR - 1;
+        mbar_wait_warp(&bars[gen::B_DONE + (s - gen::NBUF) % gen::NSTAGE], ((s - gen::NBUF) / gen::NSTAGE) & 1);
         tc_fence_after();
-        tmem_st32(a_tile + 64 * buf, Yp);
+        tmem_st32(a_tile + 64 * (s % gen::NBUF), Yp);
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars[gen::B_AREADY + t * gen::NBUF + buf]);
+        if (lane == 0) mbar_arrive(&bars[gen::B_AREADY + t * gen::NSTAGE + s % gen::NSTAGE]);
       }
       mbar_wait_warp(&bars[gen::B_ACC + t], 0);
       tc_fence_after();
-#ifdef FM_TIMING
-      if (tid == 0) FM_T(0, 1), FM_T(1, FM_NOW() - g0);
-#endif
     }
-    [[maybe_unused]] const long long g1 = FM_NOW();
     if (tile_live) {
       // epilogue: set g takes columns [32g, 32g + 32) of the warp's 32 rows
       const float scale = P.out_scale * inv_g;
@@ -337,23 +368,27 @@ apply_gen_kernel(const __grid_constant__ CUtensorMap tmS64, const __grid_constan
         bulk_wait_group_read0();
       }
     }
-#ifdef FM_TIMING
-    if (tid == 0 && has_state) FM_T(4, FM_NOW() - g1);
-#endif
-  } else if (warp < 18) {
-    // ---------------------------------------------------------------- MMA issuers (one per tile)
-    const int tt = warp - 16;
+  } else if (warp < 20) {
+    // ---------------------------------------------------------------- MMA issuers (tile, even / odd pairs)
+    const int tt = (warp - 16) >> 1, par = (warp - 16) & 1;
     if (has_state) {
       const bool live = t0 + 128 * tt < P.N;
-      if (tt == 0) issue_tile<SYM, 0>(P, bars, live, lane);
-      else issue_tile<SYM, 1>(P, bars, live, lane);
+      if (tt == 0) {
+        if (par == 0) issue_pairs<SYM, 0, 0>(P, bars, live, lane);
+        else issue_pairs<SYM, 0, 1>(P, bars, live, lane);
+      } else {
+        if (par == 0) issue_pairs<SYM, 1, 0>(P, bars, live, lane);
+        else issue_pairs<SYM, 1, 1>(P, bars, live, lane);
+      }
     }
   } else {
     // ---------------------------------------------------------------- TMA producer
     if (lane == 0 && has_state && !(FM_EXP & 4)) {
       for (int s = 0; s < gen::NPAIR; ++s) {
         const int st = s % gen::NSTAGE;
-        if (s >= gen::NSTAGE) mbar_wait(&bars[gen::B_EMPTY + st], ((s / gen::NSTAGE) - 1) & 1, 1000 + s);
+        FM_TR(6, s);
+        if (s >= gen::NSTAGE) mbar_wait(&bars[gen::B_DONE + st], ((s / gen::NSTAGE) - 1) & 1, 1000 + s);
+        FM_TR(7, s);
         uint8_t* dst = ring + st * 16384;
         uint64_t* fb = &bars[gen::B_FULL + st];
         if (s == gen::NPAIR - 1) {

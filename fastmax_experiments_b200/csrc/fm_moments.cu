@@ -167,6 +167,7 @@ build_kernel(const __grid_constant__ CUtensorMap tmXT, const __grid_constant__ C
   const int bh = blockIdx.y, cx = blockIdx.x;
   const bool special = cx == P.special_cx;
   const int ntile = special ? 1 : 4;
+  [[maybe_unused]] const long long cta_t0 = FM_NOW();
   const uint32_t stage_tx = special ? 3 * 8192 : 2 * 8192;
 
   if (warp == 20) {
@@ -328,6 +329,7 @@ build_kernel(const __grid_constant__ CUtensorMap tmXT, const __grid_constant__ C
             mbar_wait(&a_ready[kk * 2 + (j & 1)], (it >> 1) & 1);
 #ifdef FM_TIMING
             if (kk == 0 && cx == 0) FM_T(20, i1 - i0), FM_T(21, FM_NOW() - i1), FM_T(22, 1);
+            if (kk == 0 && special) FM_T(28, i1 - i0), FM_T(29, FM_NOW() - i1), FM_T(30, 1);
 #endif
           }
           __syncwarp();
@@ -392,7 +394,7 @@ build_kernel(const __grid_constant__ CUtensorMap tmXT, const __grid_constant__ C
       const int seg = !P.causal ? 0 : (P.reverse ? b / P.Lb - 1 : (b + 1) / P.Lb);
       const int rec_idx = P.causal ? bh * P.nseg + seg : bh;
       uint8_t* rec = P.state + (size_t)rec_idx * REC_BYTES;
-      if (storer || (P.packed && !special && lane == 0)) bulk_wait_group_read0();   // previous boundary's stores have left the staging tiles
+      if (storer) bulk_wait_group_read0();          // previous boundary's stores have left the staging tiles
       [[maybe_unused]] const long long s0 = FM_NOW();
       mbar_wait(acc_full, kq & 1);
       [[maybe_unused]] const long long s1 = FM_NOW();
@@ -434,12 +436,11 @@ build_kernel(const __grid_constant__ CUtensorMap tmXT, const __grid_constant__ C
             bulk_commit_group();
           }
         } else {
-          if (lane == 0) {
-            // unit u = 16 blk + xr  ->  rows [16 by, +16) of slab x = 16 gx + xr.  One storing lane per warp: 64
-            // bulk stores per boundary from a single thread took longer than the scan needs between boundaries.
-#pragma unroll 1
-            for (int u = q; u < 32; u += 4)
-              tma_store_3d(&tmS16, snap + u * 2048, 0, (16 * pgx[u >> 4] + (u & 15)) * 64 + 16 * pby[u >> 4], rec_idx);
+          if (storer) {
+            // block blk = staging units [16 blk, 16 blk + 16): rows [16 by, +16) of the 16 slabs x = 16 gx + xr --
+            // ONE bulk tensor store per block through the 4-D map (a store per 2 KiB unit, 64 per boundary, cost
+            // ~100 cycles each: the snapshot warps then needed longer than the scan takes between boundaries)
+            for (int blk = 0; blk < 2; ++blk) tma_store_4d(&tmS16, snap + blk * 32768, 0, 16 * pby[blk], 16 * pgx[blk], rec_idx);
           }
           // Mirror images of the off-diagonal blocks: atom (xr, yi, chunk c) of the staging moves from unit xr,
           // row yi to unit yi, row xr.  Lane l of an 8-lane phase takes xr = l (mod 8), yi = l + s (mod 8) with one
@@ -461,12 +462,10 @@ build_kernel(const __grid_constant__ CUtensorMap tmXT, const __grid_constant__ C
           }
           fence_proxy_async();
           named_barrier_sync(1, 128);
-          if (lane == 0) {
-            // unit u = 16 blk + yi  ->  rows [16 gx, +16) of slab y = 16 by + yi
-#pragma unroll 1
-            for (int u = q; u < 32; u += 4)
-              if (pgx[u >> 4] != pby[u >> 4])
-                tma_store_3d(&tmS16, mir + u * 2048, 0, (16 * pby[u >> 4] + (u & 15)) * 64 + 16 * pgx[u >> 4], rec_idx);
+          if (storer) {
+            // mirror of block blk: rows [16 gx, +16) of the 16 slabs y = 16 by + yi
+            for (int blk = 0; blk < 2; ++blk)
+              if (pgx[blk] != pby[blk]) tma_store_4d(&tmS16, mir + blk * 32768, 0, 16 * pgx[blk], 16 * pby[blk], rec_idx);
             bulk_commit_group();
           }
         }
@@ -510,13 +509,19 @@ build_kernel(const __grid_constant__ CUtensorMap tmXT, const __grid_constant__ C
             }
           }
         }
+#ifdef FM_TIMING
+        if (storer) FM_T(24, 1), FM_T(25, s1 - s0), FM_T(26, FM_NOW() - s1);
+#endif
       }
       ++kq;
     }
-    if (storer || (P.packed && !special && lane == 0)) bulk_wait_group_read0();   // shared memory must outlive the bulk stores' reads (not their global writes)
+    if (storer) bulk_wait_group_read0();            // shared memory must outlive the bulk stores' reads (not their global writes)
   }
   tc_fence_before();
   __syncthreads();
+#ifdef FM_TIMING
+  if (tid == 0) FM_T(special ? 33 : 32, 1), FM_T(special ? 35 : 34, FM_NOW() - cta_t0);
+#endif
   if (warp == 20) tmem_dealloc(tmem, 512);
 }
 
@@ -576,7 +581,8 @@ constexpr int A_THREADS = 19 * 32;                       // 16 epilogue warps, 2
 // column-split epilogue 2.9; issuing from the epilogue warpgroups 3.2; generated A operands in tensor
 // memory 3.2-5.2.
 __global__ void __launch_bounds__(A_THREADS, 1)
-apply_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmY, const ApplyParams P) {
+apply_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmY,
+             const __grid_constant__ CUtensorMap tmOut, const ApplyParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* res = smem;                       // [4 tiles][16 KiB]
@@ -739,17 +745,28 @@ apply_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CU
         if (lane == 0) mbar_arrive(&t_free[t]);
       }
     }
+    // The bf16 rows leave through shared memory: the tile's own resident Y tile is free once its last T tile
+    // has been read (all of its MMAs are complete), so the 128x64 output tile is staged there in the 128B-swizzled
+    // layout and one thread sends it with two bulk tensor stores (rows past N are clipped by the tensor map).
+    // (Storing from registers -- a 128-byte row per thread, 16 bytes per lane and instruction at a 128-byte
+    // stride -- was most of the ~7k-cycle tail of the CTA.)
     const float scale = P.out_scale * inv_g;
-    if (valid) {
-      uint4* dst = reinterpret_cast<uint4*>(P.out + grow * 64);
+    const int ob = t0 + 128 * t;
+    if (ob < P.N) {                                   // uniform over the tile's warpgroup
+      const int rloc = 32 * q + lane;
+      const uint32_t dst = smem_u32(res) + t * 16384 + rloc * 128;
 #pragma unroll
-      for (int c8 = 0; c8 < 8; ++c8) {
-        uint4 o;
-        o.x = pack_bf16x2(O[8 * c8 + 0] * scale, O[8 * c8 + 1] * scale);
-        o.y = pack_bf16x2(O[8 * c8 + 2] * scale, O[8 * c8 + 3] * scale);
-        o.z = pack_bf16x2(O[8 * c8 + 4] * scale, O[8 * c8 + 5] * scale);
-        o.w = pack_bf16x2(O[8 * c8 + 6] * scale, O[8 * c8 + 7] * scale);
-        dst[c8] = o;
+      for (int c8 = 0; c8 < 8; ++c8)
+        sts128(dst + ((uint32_t)(c8 ^ (rloc & 7)) << 4),
+               pack_bf16x2(O[8 * c8 + 0] * scale, O[8 * c8 + 1] * scale), pack_bf16x2(O[8 * c8 + 2] * scale, O[8 * c8 + 3] * scale),
+               pack_bf16x2(O[8 * c8 + 4] * scale, O[8 * c8 + 5] * scale), pack_bf16x2(O[8 * c8 + 6] * scale, O[8 * c8 + 7] * scale));
+      fence_proxy_async();
+      named_barrier_sync(1 + t, 128);
+      if (q == 0 && lane == 0) {
+        tma_store_3d(&tmOut, res + t * 16384, 0, ob, bh);
+        if (ob + 64 < P.N) tma_store_3d(&tmOut, res + t * 16384 + 8192, 0, ob + 64, bh);
+        bulk_commit_group();
+        bulk_wait_group_read0();
       }
     }
   }
@@ -879,7 +896,7 @@ static int launch_build(const Problem& pb, const MomLayout& m, const void* xt, c
   CUtensorMap tmXT, tmW, tmW2, tmS, tmS16;
   int rc;
   if ((rc = make_tmap_bf16_3d(&tmS, state, 64, NSLAB * 64, (uint64_t)m.BH * m.nrec, 128, REC_BYTES, 64, 64))) return rc;
-  if ((rc = make_tmap_bf16_3d(&tmS16, state, 64, NSLAB * 64, (uint64_t)m.BH * m.nrec, 128, REC_BYTES, 64, 16))) return rc;
+  if ((rc = make_tmap_state_4d(&tmS16, state, NSLAB, (uint64_t)m.BH * m.nrec, REC_BYTES, 16, 16))) return rc;
   if ((rc = make_tmap_bf16_3d(&tmXT, xt, 64, m.Npad, m.BH, 128, (uint64_t)m.Npad * 128, 64, 64))) return rc;
   if ((rc = make_tmap_bf16_3d(&tmW, w, 64, m.N, m.BH, 128, (uint64_t)m.N * 128, 64, 64))) return rc;
   if ((rc = make_tmap_bf16_3d(&tmW2, w2, 64, m.N, m.BH, 128, (uint64_t)m.N * 128, 64, 64))) return rc;
@@ -931,14 +948,15 @@ static int launch_apply(const Problem& pb, const MomLayout& m, const char* name,
     d.X = P.X, d.Y = Y, d.partial = P.partial, d.gden = P.gden, d.out = P.out, d.state = P.state;
     return launch_apply_gen(pb, m.BH, m.nrec, name, d, apply_variant());
   }
-  CUtensorMap tmS, tmY;
+  CUtensorMap tmS, tmY, tmOut;
   int rc;
   if ((rc = make_tmap_bf16_3d(&tmS, P.state, 64, NSLAB * 64, (uint64_t)m.BH * m.nrec, 128, REC_BYTES, 64, 64))) return rc;
   if ((rc = make_tmap_bf16_3d(&tmY, Y, 64, m.N, m.BH, 128, (uint64_t)m.N * 128, 64, 64))) return rc;
+  if ((rc = make_tmap_bf16_3d(&tmOut, P.out, 64, m.N, m.BH, 128, (uint64_t)m.N * 128, 64, 64))) return rc;
   P.N = m.N, P.L = m.L, P.nseg = m.nseg, P.causal = pb.causal, P.p = pb.p;
   FM_CUDA(cudaFuncSetAttribute(apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A_SMEM));
   dim3 grid((m.N + A_TOK - 1) / A_TOK, m.BH);
-  FM_LAUNCH(name, pb.stream, apply_kernel<<<grid, A_THREADS, A_SMEM, pb.stream>>>(tmS, tmY, P));
+  FM_LAUNCH(name, pb.stream, apply_kernel<<<grid, A_THREADS, A_SMEM, pb.stream>>>(tmS, tmY, tmOut, P));
   return FASTMAX_OK;
 }
 

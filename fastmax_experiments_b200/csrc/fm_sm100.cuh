@@ -123,6 +123,11 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* s
                ::"l"(m), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(m), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 // plain (1-D) bulk copy shared -> global; size a multiple of 16 bytes, both addresses 16-byte aligned
 __device__ __forceinline__ void bulk_store_1d(void* gdst, const void* ssrc, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes)
@@ -345,6 +350,8 @@ __device__ __forceinline__ uint32_t bcast_bf16(uint32_t x, int sel) {
 int make_tmap_bf16_3d(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint64_t batch,
                       uint64_t row_stride_bytes, uint64_t batch_stride_bytes, uint32_t box_cols,
                       uint32_t box_rows);
+int make_tmap_state_4d(CUtensorMap* map, const void* base, uint64_t nslab, uint64_t nrec, uint64_t rec_bytes,
+                       uint32_t box_rows, uint32_t box_slabs);
 // same for an fp32 tensor (box_cols * 4 bytes <= 128: one swizzle row)
 int make_tmap_f32_3d(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint64_t batch,
                       uint64_t row_stride_bytes, uint64_t batch_stride_bytes, uint32_t box_cols,

@@ -64,4 +64,27 @@ static int make_tmap_3d(CUtensorMap* map, CUtensorMapDataType dt, const void* ba
   return FASTMAX_OK;
 }
 
+// 4-D bf16 map over the state records viewed as (col 64, row 64, slab NSLAB, record): box = (64 cols x box_rows x
+// box_slabs x 1), 128B swizzle.  One bulk store then covers `box_rows` rows of `box_slabs` consecutive slabs.
+int make_tmap_state_4d(CUtensorMap* map, const void* base, uint64_t nslab, uint64_t nrec, uint64_t rec_bytes,
+                       uint32_t box_rows, uint32_t box_slabs) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    snprintf(status().cuda_err, sizeof(status().cuda_err), "cuTensorMapEncodeTiled entry point not found");
+    return FASTMAX_ERR_CUDA;
+  }
+  cuuint64_t dims[4] = {64, 64, nslab, nrec};
+  cuuint64_t strides[3] = {128, 64 * 128, rec_bytes};
+  cuuint32_t box[4] = {64, box_rows, box_slabs, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(status().cuda_err, sizeof(status().cuda_err), "cuTensorMapEncodeTiled (4-D state map) failed: %d", (int)r);
+    return FASTMAX_ERR_CUDA;
+  }
+  return FASTMAX_OK;
+}
+
 }  // namespace fm

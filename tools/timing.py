@@ -66,6 +66,11 @@ for name in ("moments", "intra", "apply"):
         print(f"   build, cx=0 CTAs, per boundary ({nb} boundaries): snapshot warps idle {t[17] // nb}, read-out + staging "
               f"{t[18] // nb}, stores / mirror {t[19] // nb}; issuer 0 per block ({t[22]} blocks): stalled on the snapshot "
               f"{t[20] / max(t[22], 1):.0f}, waiting for the generators {t[21] / max(t[22], 1):.0f}")
+        if t[24]:
+            print(f"   special CTAs: per boundary ({t[24]}): idle {t[25] // t[24]}, read-out + direct stores {t[26] // t[24]}; "
+                  f"issuer 0 per block: stalled on the snapshot {t[28] / max(t[30], 1):.0f}, waiting for the generators "
+                  f"{t[29] / max(t[30], 1):.0f}")
+        print(f"   whole-CTA cycles: regular {t[34] // max(t[32], 1)} ({t[32]} CTAs), special {t[35] // max(t[33], 1)} ({t[33]} CTAs)")
 if "--bwd" in sys.argv:
     fastmax_bwd_raw(q, k, v, o, g, do, True, 1.0 / 64, 2, _lib.ALGO_MOMENTS)
     for name in ("moments", "intra", "apply"):
