@@ -23,6 +23,7 @@ SYMBOLS = [
     "fastmax_saved_state_bytes", "fastmax_fwd_ex", "fastmax_bwd_ex",
     "fastmax_sp_state_bytes", "fastmax_sp_local_state_workspace_bytes", "fastmax_sp_local_state",
     "fastmax_sp_local_state_rev", "fastmax_sp_reduce", "fastmax_fwd_sp", "fastmax_bwd_sp",
+    "fastmax_decode_state_bytes", "fastmax_decode_init", "fastmax_decode_update", "fastmax_decode_attend",
 ]
 
 
@@ -109,6 +110,14 @@ def load() -> C.CDLL:
     lib.fastmax_fwd_sp.argtypes = [vp] * 6 + [ll] + [i32] * 5 + [f32, i32, vp, sz, vp]
     lib.fastmax_bwd_sp.restype = i32
     lib.fastmax_bwd_sp.argtypes = [vp] * 11 + [ll] + [i32] * 5 + [f32, i32, vp, sz, vp]
+    lib.fastmax_decode_state_bytes.restype = sz
+    lib.fastmax_decode_state_bytes.argtypes = [i32] * 4
+    lib.fastmax_decode_init.restype = i32
+    lib.fastmax_decode_init.argtypes = [vp] + [i32] * 4 + [vp]
+    lib.fastmax_decode_update.restype = i32
+    lib.fastmax_decode_update.argtypes = [vp] * 3 + [i32] * 6 + [vp]
+    lib.fastmax_decode_attend.restype = i32
+    lib.fastmax_decode_attend.argtypes = [vp] * 3 + [i32] * 5 + [f32, f32, i32, vp]
     lib.fastmax_profile_enable.restype = None
     lib.fastmax_profile_enable.argtypes = [i32]
     lib.fastmax_profile_fetch.restype = i32

@@ -218,6 +218,40 @@ int fastmax_bwd_ex(const void* q, const void* k, const void* v, const void* o, c
   return fm::moments_bwd(pb, q, k, v, o, g, d_o, dq, dk, dv, workspace);
 }
 
+// ---- recurrent inference state ---------------------------------------------------------------
+size_t fastmax_decode_state_bytes(int B, int H, int D, int p) {
+  if (B <= 0 || H <= 0 || D <= 0 || D > 128 || (p != 1 && p != 2)) return 0;
+  return fm::decode_state_bytes(B, H, D, p);
+}
+
+int fastmax_decode_init(void* state, int B, int H, int D, int p, void* stream) {
+  fm::status().launches = 0;
+  const size_t nb = fastmax_decode_state_bytes(B, H, D, p);
+  if (!state || !nb) return FASTMAX_ERR_BAD_ARG;
+  FM_CUDA(cudaMemsetAsync(state, 0, nb, (cudaStream_t)stream));
+  return FASTMAX_OK;
+}
+
+int fastmax_decode_update(void* state, const void* k, const void* v, int B, int H, int T, int D, int p, int dtype,
+                          void* stream) {
+  fm::status().launches = 0;
+  fm::status().cuda_err[0] = 0;
+  if (!state || !k || !v) return FASTMAX_ERR_BAD_ARG;
+  int rc = check_common(B, H, T, D, p, dtype);
+  if (rc) return rc;
+  return fm::decode_update(state, k, v, B, H, T, D, p, dtype, (cudaStream_t)stream);
+}
+
+int fastmax_decode_attend(const void* state, const void* q, void* o, int B, int H, int T, int D, int p, float inv_c,
+                          float count_term, int dtype, void* stream) {
+  fm::status().launches = 0;
+  fm::status().cuda_err[0] = 0;
+  if (!state || !q || !o) return FASTMAX_ERR_BAD_ARG;
+  int rc = check_common(B, H, T, D, p, dtype);
+  if (rc) return rc;
+  return fm::decode_attend(state, q, o, B, H, T, D, p, inv_c, count_term, dtype, (cudaStream_t)stream);
+}
+
 // ---- sequence parallelism ------------------------------------------------------------------
 static int check_sp(int B, int H, int N, int D, int p, int dtype) {
   int rc = check_common(B, H, N, D, p, dtype);

@@ -97,6 +97,11 @@ int intra_dkdv(const Problem& pb, int L, int Npad, const void* k, const void* v,
 //  outputs; the *_part arguments are then unused)
 namespace mom { struct ApplyDesc; }
 int launch_apply_gen(const Problem& pb, int BH, int nrec, const char* name, const mom::ApplyDesc& d, int variant);
+// recurrent inference state (fm_decode.cu)
+size_t decode_state_bytes(int B, int H, int D, int p);
+int decode_update(void* state, const void* k, const void* v, int B, int H, int T, int D, int p, int dtype, cudaStream_t stream);
+int decode_attend(const void* state, const void* q, void* o, int B, int H, int T, int D, int p, float inv_c,
+                  float count_term, int dtype, cudaStream_t stream);
 int moments_seg_len(int B, int H, int N, int p);
 size_t moments_state_bytes(int B, int H);
 size_t moments_saved_state_bytes(int B, int H, int N, int p, int causal);

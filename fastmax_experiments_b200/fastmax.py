@@ -38,6 +38,7 @@ __all__ = ["fastmax", "fastattention_einops", "FastmaxFunction", "fastmax_fwd_ra
 
 _DTYPES = {torch.float32: _lib.DTYPE_F32, torch.bfloat16: _lib.DTYPE_BF16}
 _TENSOR_PATH_D = 64      # head size of the tcgen05 kernels
+_RECT_STATE_MAX_Q = 64   # N_q != N_k with at most this many queries goes through the recurrent-state kernels
 
 
 def _check_inputs(q, k, v, rect_ok=False):
@@ -129,6 +130,14 @@ def rect_forward(q, k, v, inv_c: float, p: int, count: str = "q"):
     Nq, Nk, D = q.shape[2], k.shape[2], q.shape[3]
     F = torch.nn.functional
     q_, k_, v_ = q.contiguous(), k.contiguous(), v.contiguous()
+    if Nq <= _RECT_STATE_MAX_Q:
+        # decode / short prefill: reduce the cache to its moment state once (fp32) and evaluate only the real
+        # query rows against it, instead of padding q to N_k rows -- one normalisation, one rounding
+        from .decode import FastmaxState
+        st = FastmaxState(q.shape[0], q.shape[1], D, p=p, device=q.device, tensors_normalized=True)
+        st.inv_c = inv_c
+        st.update(k_, v_)
+        return st.attend(q_, count_term=float(Nq if count == "q" else Nk))
     if Nq < Nk:
         q_ = F.pad(q_, (0, 0, 0, Nk - Nq))
     else:

@@ -144,6 +144,22 @@ int fastmax_bwd_sp(const void* q, const void* k, const void* v, const void* o, c
                    long long token_offset, int B, int H, int N, int D, int p, float inv_c, int dtype,
                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- recurrent inference state (replaces the KV cache of generate/base.py:83-88, lit_gpt/model.py:427-430) ----
+ * The reference's generation path evaluates, for every new token, the NON-causal FastMax of the new queries
+ * over the whole zero-padded KV cache (model.py:478-487 with input_pos given).  The factorisation needs only
+ * the moment state of the keys seen so far: (1 + D + D^2)(D + 1) floats per (b,h) (D^2 term for p = 2 only),
+ * fastmax_decode_state_bytes() in total.  fastmax_decode_update adds T new key/value rows (B,H,T,D) to it;
+ * fastmax_decode_attend evaluates T query rows against it.  `count_term` is the count term of the normaliser:
+ * the reference uses the number of QUERY rows of the call (fastmax.py:269-271, quirk Q2), fastmax_hack.py:21
+ * (linearmax) the number of cache rows; pass whichever the caller reproduces.  fp32 state and accumulation,
+ * q/k/v/o in `dtype`, D <= 128. */
+size_t fastmax_decode_state_bytes(int B, int H, int D, int p);
+int fastmax_decode_init(void* state, int B, int H, int D, int p, void* stream);
+int fastmax_decode_update(void* state, const void* k, const void* v, int B, int H, int T, int D, int p, int dtype,
+                          void* stream);
+int fastmax_decode_attend(const void* state, const void* q, void* o, int B, int H, int T, int D, int p, float inv_c,
+                          float count_term, int dtype, void* stream);
+
 /* Optional per-launch timing for measurement harnesses (no reference counterpart).
  * While enabled, every kernel launch of the calling thread is bracketed by CUDA events on the
  * launching stream.  fastmax_profile_fetch waits for them and writes up to `cap` durations (ms)

@@ -424,3 +424,41 @@ def test_inference_shape_with_more_queries_than_keys():
         o16 = fm.fastmax(q.cuda(), k.cuda(), v.cuda(), mask=False, p=2)
     assert orc.rel_err(o32.double().cpu(), ref) <= 1e-4
     assert orc.rel_err(o16.double().cpu(), ref) <= 2e-2
+
+
+@pytest.mark.parametrize("name", golden_rect_names())
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_recurrent_state_matches_reference_over_the_kv_cache(name, dtype):
+    """FastmaxState (constant-size moment state instead of the KV cache): keys appended in three pieces, then the
+    queries of the fixture -- equals the reference's fastmax(q, k_cache, v_cache, mask=False), count term N_q."""
+    gd = load_golden_rect(name)
+    q, k, v = (gd[x].to("cuda", dtype) for x in ("q", "k", "v"))
+    B, H, Nk, D = k.shape
+    st = fm.FastmaxState(B, H, D, p=gd["p"])
+    cuts = [0, Nk // 3, Nk // 3 + 1, Nk]
+    for a, b in zip(cuts, cuts[1:]):
+        st.update(k[:, :, a:b], v[:, :, a:b])
+    assert st.n_keys == Nk
+    o = st.attend(q)
+    assert o.shape == q.shape and o.dtype == dtype
+    assert orc.rel_err(o.double().cpu(), gd["o"]) <= TOL[dtype]
+    # zero-padded cache rows (the reference's unfilled positions) change nothing
+    st.update(torch.zeros(B, H, 5, D, device="cuda", dtype=dtype), torch.zeros(B, H, 5, D, device="cuda", dtype=dtype))
+    assert orc.rel_err(st.attend(q).double().cpu(), gd["o"]) <= TOL[dtype]
+    st.reset()
+    st.update(k, v)
+    assert orc.rel_err(st.attend(q).double().cpu(), gd["o"]) <= TOL[dtype]
+
+
+def test_recurrent_state_decode_loop_matches_op_d128():
+    """Token-by-token decode at D = 128 (Llama-2-7B head size): every step equals the non-causal op over the keys so far."""
+    torch.manual_seed(8)
+    B, H, D, T = 1, 2, 128, 12
+    q, k, v = (torch.randn(B, H, T, D, device="cuda") for _ in range(3))
+    st = fm.FastmaxState(B, H, D, p=2)
+    for t in range(T):
+        st.update(k[:, :, t:t + 1], v[:, :, t:t + 1])
+        o = st.attend(q[:, :, t:t + 1])
+        ref, _ = orc.factorised_forward(q[:, :, t:t + 1].double().cpu(), k[:, :, :t + 1].double().cpu(),
+                                        v[:, :, :t + 1].double().cpu(), mask=False, p=2)
+        assert orc.rel_err(o.double().cpu(), ref) <= 1e-4, t
