@@ -34,6 +34,49 @@ void prof_end(cudaStream_t stream) {
 
 using fm::Problem;
 
+// The tcgen05 kernels build their shared-memory descriptors on the host for a fixed dynamic-shared-memory
+// base (fm_sm100.cuh: FM_SMEM_BASE) and trap if the device disagrees -- which would poison the CUDA context.
+// Probe the base once per process with a one-warp kernel instead: if this driver / tool (compute-sanitizer, a
+// debugger) reserves a different amount, the plan falls back to the CUDA-core kernels (AUTO) or reports
+// FASTMAX_ERR_UNSUPPORTED (explicit MOMENTS).  Without a device (planning on a build host) the answer is "yes".
+__global__ void probe_smem_base_kernel(unsigned* out) {
+  extern __shared__ uint8_t probe_smem[];
+  if (threadIdx.x == 0)
+    *out = static_cast<unsigned>(__cvta_generic_to_shared(
+        reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(probe_smem) + 1023) & ~uintptr_t(1023))));
+}
+
+static bool tensor_path_usable() {
+  static int cached = -1;
+  if (cached >= 0) return cached != 0;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return true;                               // no device: planning only (not cached: a device may appear later)
+  }
+  unsigned* d = nullptr;
+  unsigned h = 0;
+  cudaStream_t st = nullptr;
+  bool ok = cudaMalloc(&d, sizeof(unsigned)) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess;
+  if (ok) {
+    probe_smem_base_kernel<<<1, 32, 4096, st>>>(d);
+    ok = cudaMemcpyAsync(&h, d, sizeof(unsigned), cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+         cudaStreamSynchronize(st) == cudaSuccess;
+  }
+  if (st) cudaStreamDestroy(st);
+  if (d) cudaFree(d);
+  if (!ok) {
+    cudaGetLastError();
+    return true;                               // could not probe (e.g. stream capture in progress): keep the default
+  }
+  cached = h == fm::sm100_smem_base() ? 1 : 0;
+  if (!cached)
+    fprintf(stderr, "fastmax: dynamic shared memory starts at %u, not %u: tcgen05 path disabled, using the CUDA-core kernels\n",
+            h, fm::sm100_smem_base());
+  return cached != 0;
+}
+
 static int check_common(int B, int H, int N, int D, int p, int dtype) {
   if (B <= 0 || H <= 0 || N <= 0 || D <= 0) return FASTMAX_ERR_BAD_ARG;
   if (p != 1 && p != 2) return FASTMAX_ERR_BAD_ARG;  // reference raises ValueError (fastmax.py:428)
@@ -99,7 +142,7 @@ int fastmax_plan_make(fastmax_plan* plan, int B, int H, int N, int D, int p, int
   (void)causal;
   if (algo != FASTMAX_ALGO_AUTO && algo != FASTMAX_ALGO_EXACT && algo != FASTMAX_ALGO_MOMENTS)
     return FASTMAX_ERR_BAD_ARG;
-  const bool mom_ok = dtype == FASTMAX_DTYPE_BF16 && D == 64;
+  const bool mom_ok = dtype == FASTMAX_DTYPE_BF16 && D == 64 && tensor_path_usable();
   if (algo == FASTMAX_ALGO_MOMENTS && !mom_ok) return FASTMAX_ERR_UNSUPPORTED;
   // the tcgen05 path also covers short sequences (one segment = dense tensor-core tiles, no moment
   // states); below a couple of tiles the fp32 CUDA-core kernels are as fast and exact
@@ -256,7 +299,7 @@ int fastmax_decode_attend(const void* state, const void* q, void* o, int B, int 
 static int check_sp(int B, int H, int N, int D, int p, int dtype) {
   int rc = check_common(B, H, N, D, p, dtype);
   if (rc) return rc;
-  if (dtype != FASTMAX_DTYPE_BF16 || D != 64) return FASTMAX_ERR_UNSUPPORTED;
+  if (dtype != FASTMAX_DTYPE_BF16 || D != 64 || !tensor_path_usable()) return FASTMAX_ERR_UNSUPPORTED;
   return FASTMAX_OK;
 }
 

@@ -97,6 +97,7 @@ int intra_dkdv(const Problem& pb, int L, int Npad, const void* k, const void* v,
 //  outputs; the *_part arguments are then unused)
 namespace mom { struct ApplyDesc; }
 int launch_apply_gen(const Problem& pb, int BH, int nrec, const char* name, const mom::ApplyDesc& d, int variant);
+unsigned sm100_smem_base();     // FM_SMEM_BASE of fm_sm100.cuh (defined in fm_tmap.cu)
 // recurrent inference state (fm_decode.cu)
 size_t decode_state_bytes(int B, int H, int D, int p);
 int decode_update(void* state, const void* k, const void* v, int B, int H, int T, int D, int p, int dtype, cudaStream_t stream);

@@ -462,3 +462,36 @@ def test_recurrent_state_decode_loop_matches_op_d128():
         ref, _ = orc.factorised_forward(q[:, :, t:t + 1].double().cpu(), k[:, :, :t + 1].double().cpu(),
                                         v[:, :, :t + 1].double().cpu(), mask=False, p=2)
         assert orc.rel_err(o.double().cpu(), ref) <= 1e-4, t
+
+
+_VARIANT_SNIPPET = """
+import sys, torch
+sys.path.insert(0, {root!r})
+from fastmax_experiments_b200 import _lib
+from fastmax_experiments_b200.fastmax import fastmax_fwd_raw, fastmax_bwd_raw
+from oracle import fastmax_oracle as orc
+gen = torch.Generator().manual_seed(7)
+for (B, H, N, causal) in ((1, 2, 2560, True), (2, 1, 3000, True), (1, 2, 1100, False)):
+    q, k, v, do = (torch.randn(B, H, N, 64, generator=gen).to(torch.bfloat16) for _ in range(4))
+    ref = orc.dense_fwd_bwd(q.double(), k.double(), v.double(), do.double(), mask=causal, p=2)
+    qc, kc, vc, dc = (t.cuda() for t in (q, k, v, do))
+    o, g = fastmax_fwd_raw(qc, kc, vc, causal, 1.0 / orc.denominator_c(64), 2, _lib.ALGO_MOMENTS)
+    out = (o, g) + tuple(fastmax_bwd_raw(qc, kc, vc, o, g, dc, causal, 1.0 / orc.denominator_c(64), 2, _lib.ALGO_MOMENTS))
+    torch.cuda.synchronize()
+    for nm, x, r in zip(("o", "g", "dq", "dk", "dv"), out, ref):
+        err = orc.rel_err(x, r)
+        assert err <= 2e-2, (N, causal, nm, err)
+print("variant ok")
+"""
+
+
+@pytest.mark.parametrize("env", [{"FASTMAX_APPLY": "gen"}, {"FASTMAX_BUILD": "full"}], ids=["apply-gen", "build-full"])
+def test_kernel_variants_behind_developer_switches(env):
+    """The measured alternatives kept in the library (fm_apply.cu's generated-operand contraction; the round-1
+    unpacked build layout) stay parity-green: multi-segment causal and non-causal p=2 against the dense oracle,
+    in a fresh process (the switches are read once per process)."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", _VARIANT_SNIPPET.format(root=root)], env={**os.environ, **env},
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "variant ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
