@@ -22,7 +22,7 @@ cols = [c for c in KEEP if c in ix]
 w = csv.writer(sys.stdout)
 w.writerow(cols)
 for r in rows[2:]:
-    if len(r) < len(hdr) or "fm::" not in r[ix["Kernel Name"]]:      # only this library's kernels
+    if len(r) < len(hdr) or not any(k in r[ix["Kernel Name"]] for k in ("fm::", "apply_kernel", "build_kernel", "intra_kernel", "prep_bwd_kernel", "transpose_kernel")):      # only this library's kernels
         continue
     w.writerow([r[ix[c]] + ("" if c == "Kernel Name" or not units[ix[c]] else " " + units[ix[c]]) for c in cols])
 
@@ -31,7 +31,8 @@ if len(sys.argv) > 2:
     def gb(r, c):
         v, u = float(r[ix[c]]), units[ix[c]]
         return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[u]
-    fm_rows = [r for r in rows[2:] if len(r) >= len(hdr) and "fm::" in r[ix["Kernel Name"]]]
+    fm_rows = [r for r in rows[2:] if len(r) >= len(hdr) and any(k in r[ix["Kernel Name"]] for k in
+               ("fm::", "apply_kernel", "build_kernel", "intra_kernel", "prep_bwd_kernel", "transpose_kernel"))]
     tot = sum(gb(r, "dram__bytes_read.sum") + gb(r, "dram__bytes_write.sum") for r in fm_rows)
     json.dump({"launches": len(fm_rows), "dram_bytes_per_step": tot, "config": {"B": 8, "H": 32, "N": 16384, "kept_states": True},
                "source": "ncu --set full, one fwd+bwd step at the headline shape (tools/prof_run.py 8 32 16384 64 1 --bwd --keep)"},
