@@ -97,6 +97,11 @@ int intra_dkdv(const Problem& pb, int L, int Npad, const void* k, const void* v,
 //  outputs; the *_part arguments are then unused)
 namespace mom { struct ApplyDesc; }
 int launch_apply_gen(const Problem& pb, int BH, int nrec, const char* name, const mom::ApplyDesc& d, int variant);
+// first-order causal FastMax as one fused scan per (b,h) (fm_p1scan.cu)
+bool p1scan_usable(const Problem& pb);
+int p1scan_fwd(const Problem& pb, const void* q, const void* k, const void* v, void* o, float* g);
+int p1scan_bwd(const Problem& pb, int Npad, const void* q, const void* k, const void* v, const void* u, const float* dlt,
+               void* dq, void* dk, void* dv);
 unsigned sm100_smem_base();     // FM_SMEM_BASE of fm_sm100.cuh (defined in fm_tmap.cu)
 // recurrent inference state (fm_decode.cu)
 size_t decode_state_bytes(int B, int H, int D, int p);

@@ -778,6 +778,7 @@ apply_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CU
 // =============================================================================================
 // backward prep: u = do/g (bf16), dlt = (do.o)/g (fp32), qd = -dlt*q (bf16).  HBM-bound pass.
 // =============================================================================================
+template <bool QD>   // QD = false: only u and dlt (the first-order scan kernels do not use qd and q is not read)
 __global__ void __launch_bounds__(256) prep_bwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ o,
                                                         const bf16* __restrict__ d_o, const float* __restrict__ g,
                                                         bf16* __restrict__ u, float* __restrict__ dlt,
@@ -789,7 +790,7 @@ __global__ void __launch_bounds__(256) prep_bwd_kernel(const bf16* __restrict__ 
   const size_t off = (live ? row : 0) * 64 + 8 * c;
   const uint4 dv = __ldg(reinterpret_cast<const uint4*>(d_o + off));
   const uint4 ov = __ldg(reinterpret_cast<const uint4*>(o + off));
-  const uint4 qv = __ldg(reinterpret_cast<const uint4*>(q + off));
+  const uint4 qv = QD ? __ldg(reinterpret_cast<const uint4*>(q + off)) : make_uint4(0u, 0u, 0u, 0u);
   const float ig = 1.f / g[live ? row : 0];
   const uint32_t dw[4] = {dv.x, dv.y, dv.z, dv.w}, ow[4] = {ov.x, ov.y, ov.z, ov.w}, qw[4] = {qv.x, qv.y, qv.z, qv.w};
   float d[8], qf[8], s = 0.f;
@@ -810,7 +811,7 @@ __global__ void __launch_bounds__(256) prep_bwd_kernel(const bf16* __restrict__ 
   qo.x = pack_bf16x2(-dl * qf[0], -dl * qf[1]), qo.y = pack_bf16x2(-dl * qf[2], -dl * qf[3]);
   qo.z = pack_bf16x2(-dl * qf[4], -dl * qf[5]), qo.w = pack_bf16x2(-dl * qf[6], -dl * qf[7]);
   *reinterpret_cast<uint4*>(u + off) = uo;
-  *reinterpret_cast<uint4*>(qd + off) = qo;
+  if (QD) *reinterpret_cast<uint4*>(qd + off) = qo;
   if (c == 0) dlt[(row / N) * Npad + row % N] = dl;   // (BH, Npad) layout, pad stays zero
 }
 
@@ -871,6 +872,16 @@ int moments_seg_len(int B, int H, int N, int p) {
 
 size_t moments_workspace_bytes(int B, int H, int N, int p, int causal, bool bwd) {
   return mom_layout(B, H, N, moments_seg_len(B, H, N, p), causal, bwd).total;
+}
+
+// developer switch: FASTMAX_P1=chunked keeps first-order causal problems on the chunked scan (round-1 path)
+static bool p1_scan_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("FASTMAX_P1");
+    v = (e && !strcmp(e, "chunked")) ? 0 : 1;
+  }
+  return v != 0;
 }
 
 static int launch_transpose(const Problem& pb, const void* in, void* out, int Npad) {
@@ -966,6 +977,7 @@ int moments_fwd(const Problem& pb, const void* q, const void* k, const void* v, 
   uint8_t* w8 = (uint8_t*)ws;
   int rc;
   const float a = pb.inv_c;
+  if (p1_scan_enabled() && p1scan_usable(pb)) return p1scan_fwd(pb, q, k, v, o, g);
   uint8_t* state = pb.saved_states ? (uint8_t*)pb.saved_states : w8 + m.off_state;
   float* part = (float*)(w8 + m.off_part);
   // 1. K^T and the boundary states (forward direction)
@@ -1003,8 +1015,14 @@ int moments_bwd(const Problem& pb, const void* q, const void* k, const void* v, 
   const size_t rows = (size_t)m.BH * m.N;
   // 1. u = do/g, dlt = (do.o)/g, qd = -dlt*q
   FM_CUDA(cudaMemsetAsync(dlt, 0, (size_t)m.BH * m.Npad * 4, pb.stream));
+  if (p1_scan_enabled() && p1scan_usable(pb)) {
+    FM_LAUNCH("mom_prep_bwd", pb.stream,
+              prep_bwd_kernel<false><<<(unsigned)((rows + 31) / 32), 256, 0, pb.stream>>>(
+                  (const bf16*)q, (const bf16*)o, (const bf16*)d_o, g, u, dlt, qd, rows, m.N, m.Npad));
+    return p1scan_bwd(pb, m.Npad, q, k, v, u, dlt, dq, dk, dv);
+  }
   FM_LAUNCH("mom_prep_bwd", pb.stream,
-            prep_bwd_kernel<<<(unsigned)((rows + 31) / 32), 256, 0, pb.stream>>>(
+            prep_bwd_kernel<true><<<(unsigned)((rows + 31) / 32), 256, 0, pb.stream>>>(
                 (const bf16*)q, (const bf16*)o, (const bf16*)d_o, g, u, dlt, qd, rows, m.N, m.Npad));
   // 2. forward-direction states of (k, v) (recomputed, not saved) and reverse-direction states of (q, u)
   if (!pb.saved_states) {
@@ -1090,7 +1108,7 @@ int moments_local_state_rev(const Problem& pb_in, const void* q, const void* o, 
   const size_t rows = (size_t)m.BH * m.N;
   FM_CUDA(cudaMemsetAsync(dlt, 0, (size_t)m.BH * m.Npad * 4, pb.stream));
   FM_LAUNCH("mom_prep_bwd", pb.stream,
-            prep_bwd_kernel<<<(unsigned)((rows + 31) / 32), 256, 0, pb.stream>>>(
+            prep_bwd_kernel<true><<<(unsigned)((rows + 31) / 32), 256, 0, pb.stream>>>(
                 (const bf16*)q, (const bf16*)o, (const bf16*)d_o, g, u, dlt, qd, rows, m.N, m.Npad));
   int rc;
   if ((rc = launch_transpose(pb, q, w8, m.Npad))) return rc;

@@ -198,7 +198,7 @@ def _rows_ok(x, ref, tol=2e-2):
     return bool((err <= tol * ref_mag).all()), (err / ref_mag).tolist()
 
 
-def _sampled_rows_and_columns_check(q, k, v, do, o, g, dq, dk, dv, b, h, rows, cols, c, fwd=True):
+def _sampled_rows_and_columns_check(q, k, v, do, o, g, dq, dk, dv, b, h, rows, cols, c, fwd=True, p=2):
     """Sampled rows of o, g, dq and sampled columns of dk, dv of one (b,h) against the dense formula evaluated in
     fp64 on the host for those rows only.  Judged per row (gradient magnitudes fall like 1/i along the
     sequence).  Row 0 must be left out of `rows`: there dq = 0 exactly (u.v_0 = dlt), see the N = 1 seeded case."""
@@ -208,7 +208,8 @@ def _sampled_rows_and_columns_check(q, k, v, do, o, g, dq, dk, dv, b, h, rows, c
     # rows i: everything from keys j <= i
     s = Q[rows] @ K.T / c
     m = (idx[None, :] <= rows[:, None]).double()
-    w = (1 + s + 0.5 * s * s) * m
+    half = 0.5 if p == 2 else 0.0                            # f(s) = 1 + s (+ s^2/2), f'(s) = 1 (+ s)
+    w = (1 + s + half * s * s) * m
     gr = w.sum(-1)
     o_ref = (w @ V) / gr[:, None]
     if fwd:
@@ -216,7 +217,7 @@ def _sampled_rows_and_columns_check(q, k, v, do, o, g, dq, dk, dv, b, h, rows, c
         assert _rows_ok(O[rows], o_ref)[0], _rows_ok(O[rows], o_ref)
     u = DO[rows] / gr[:, None]
     dlt = (DO[rows] * o_ref).sum(-1) / gr
-    e = (1 + s) * (u @ V.T - dlt[:, None]) * m
+    e = (1 + 2 * half * s) * (u @ V.T - dlt[:, None]) * m
     ok = _rows_ok(dq[b, h].double().cpu()[rows], e @ K / c)
     assert ok[0], ("dq", b, h, ok)
     # columns j: everything from queries i >= j needs u_i, dlt_i of ALL later rows: use the kernel's own
@@ -225,8 +226,8 @@ def _sampled_rows_and_columns_check(q, k, v, do, o, g, dq, dk, dv, b, h, rows, c
     Dall = (DO * O).sum(-1) / G
     st = K[cols] @ Q.T / c                                   # (cols, N) scores s_ij for j in cols
     mt = (idx[None, :] >= cols[:, None]).double()
-    wt = (1 + st + 0.5 * st * st) * mt
-    et = (1 + st) * (V[cols] @ Uall.T - Dall[None, :]) * mt
+    wt = (1 + st + half * st * st) * mt
+    et = (1 + 2 * half * st) * (V[cols] @ Uall.T - Dall[None, :]) * mt
     ok = _rows_ok(dv[b, h].double().cpu()[cols], wt @ Uall)
     assert ok[0], ("dv", b, h, ok)
     ok = _rows_ok(dk[b, h].double().cpu()[cols], et @ Q / c)
@@ -266,6 +267,21 @@ def test_headline_shape_backward_sampled():
     cols = torch.tensor([0, 511, 512, 9000, 15871, 16382])
     for (b, h) in ((0, 0), (7, 31), (3, 17), (5, 1)):
         _sampled_rows_and_columns_check(q, k, v, do, o, g, dq, dk, dv, b, h, rows, cols, c)
+
+
+def test_headline_shape_first_order_sampled():
+    """p = 1 at the headline shape: 256 per-(b,h) scan CTAs, two per SM, with every operand load late under the
+    full memory load -- the case that exposes an MMA issued before its operand tile has landed."""
+    B, H, N, D, p = 8, 32, 16384, 64, 1
+    gen = torch.Generator(device="cuda").manual_seed(23)
+    q, k, v, do = (torch.randn(B, H, N, D, device="cuda", generator=gen).to(torch.bfloat16) for _ in range(4))
+    c = orc.denominator_c(D)
+    o, g = fastmax_fwd_raw(q, k, v, True, 1.0 / c, p)
+    dq, dk, dv = fastmax_bwd_raw(q, k, v, o, g, do, True, 1.0 / c, p)
+    rows = torch.tensor([37, 127, 128, 129, 511, 8191, 8192, 16383])
+    cols = torch.tensor([0, 127, 128, 9000, 16255, 16382])
+    for (b, h) in ((0, 0), (7, 31), (3, 17), (4, 20), (6, 9)):
+        _sampled_rows_and_columns_check(q, k, v, do, o, g, dq, dk, dv, b, h, rows, cols, c, p=p)
 
 
 def test_cuda_graph_capture_replays_the_step():
@@ -471,12 +487,13 @@ from fastmax_experiments_b200 import _lib
 from fastmax_experiments_b200.fastmax import fastmax_fwd_raw, fastmax_bwd_raw
 from oracle import fastmax_oracle as orc
 gen = torch.Generator().manual_seed(7)
+P = {p}
 for (B, H, N, causal) in ((1, 2, 2560, True), (2, 1, 3000, True), (1, 2, 1100, False)):
     q, k, v, do = (torch.randn(B, H, N, 64, generator=gen).to(torch.bfloat16) for _ in range(4))
-    ref = orc.dense_fwd_bwd(q.double(), k.double(), v.double(), do.double(), mask=causal, p=2)
+    ref = orc.dense_fwd_bwd(q.double(), k.double(), v.double(), do.double(), mask=causal, p=P)
     qc, kc, vc, dc = (t.cuda() for t in (q, k, v, do))
-    o, g = fastmax_fwd_raw(qc, kc, vc, causal, 1.0 / orc.denominator_c(64), 2, _lib.ALGO_MOMENTS)
-    out = (o, g) + tuple(fastmax_bwd_raw(qc, kc, vc, o, g, dc, causal, 1.0 / orc.denominator_c(64), 2, _lib.ALGO_MOMENTS))
+    o, g = fastmax_fwd_raw(qc, kc, vc, causal, 1.0 / orc.denominator_c(64), P, _lib.ALGO_MOMENTS)
+    out = (o, g) + tuple(fastmax_bwd_raw(qc, kc, vc, o, g, dc, causal, 1.0 / orc.denominator_c(64), P, _lib.ALGO_MOMENTS))
     torch.cuda.synchronize()
     for nm, x, r in zip(("o", "g", "dq", "dk", "dv"), out, ref):
         err = orc.rel_err(x, r)
@@ -485,13 +502,16 @@ print("variant ok")
 """
 
 
-@pytest.mark.parametrize("env", [{"FASTMAX_APPLY": "gen"}, {"FASTMAX_BUILD": "full"}], ids=["apply-gen", "build-full"])
-def test_kernel_variants_behind_developer_switches(env):
+@pytest.mark.parametrize("env,p", [({"FASTMAX_APPLY": "gen"}, 2), ({"FASTMAX_BUILD": "full"}, 2), ({"FASTMAX_P1": "chunked"}, 1)],
+                         ids=["apply-gen", "build-full", "p1-chunked"])
+def test_kernel_variants_behind_developer_switches(env, p):
     """The measured alternatives kept in the library (fm_apply.cu's generated-operand contraction; the round-1
-    unpacked build layout) stay parity-green: multi-segment causal and non-causal p=2 against the dense oracle,
-    in a fresh process (the switches are read once per process)."""
+    unpacked build layout; the chunked first-order path that the fused scan of fm_p1scan.cu replaced for whole
+    sequences and that sequence-parallel ranks and few-(b,h) long sequences still use) stay parity-green:
+    multi-segment causal and non-causal shapes against the dense oracle, in a fresh process (the switches are read
+    once per process)."""
     import os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, "-c", _VARIANT_SNIPPET.format(root=root)], env={**os.environ, **env},
+    r = subprocess.run([sys.executable, "-c", _VARIANT_SNIPPET.format(root=root, p=p)], env={**os.environ, **env},
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "variant ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
