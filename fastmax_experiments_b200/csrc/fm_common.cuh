@@ -102,6 +102,12 @@ bool p1scan_usable(const Problem& pb);
 int p1scan_fwd(const Problem& pb, const void* q, const void* k, const void* v, void* o, float* g);
 int p1scan_bwd(const Problem& pb, int Npad, const void* q, const void* k, const void* v, const void* u, const float* dlt,
                void* dq, void* dk, void* dv);
+// first-order non-causal FastMax as streaming reduce + apply passes (fm_p1full.cu); `region*`: p1full_state_bytes each
+bool p1full_usable(const Problem& pb);
+size_t p1full_state_bytes(int B, int H);
+int p1full_fwd(const Problem& pb, const void* q, const void* k, const void* v, void* o, float* g, void* region);
+int p1full_bwd(const Problem& pb, int Npad, const void* q, const void* k, const void* v, const void* u, const float* dlt,
+               void* dq, void* dk, void* dv, void* region_s, bool have_s, void* region_r);
 unsigned sm100_smem_base();     // FM_SMEM_BASE of fm_sm100.cuh (defined in fm_tmap.cu)
 // recurrent inference state (fm_decode.cu)
 size_t decode_state_bytes(int B, int H, int D, int p);

@@ -198,7 +198,7 @@ def _rows_ok(x, ref, tol=2e-2):
     return bool((err <= tol * ref_mag).all()), (err / ref_mag).tolist()
 
 
-def _sampled_rows_and_columns_check(q, k, v, do, o, g, dq, dk, dv, b, h, rows, cols, c, fwd=True, p=2):
+def _sampled_rows_and_columns_check(q, k, v, do, o, g, dq, dk, dv, b, h, rows, cols, c, fwd=True, p=2, causal=True):
     """Sampled rows of o, g, dq and sampled columns of dk, dv of one (b,h) against the dense formula evaluated in
     fp64 on the host for those rows only.  Judged per row (gradient magnitudes fall like 1/i along the
     sequence).  Row 0 must be left out of `rows`: there dq = 0 exactly (u.v_0 = dlt), see the N = 1 seeded case."""
@@ -207,7 +207,7 @@ def _sampled_rows_and_columns_check(q, k, v, do, o, g, dq, dk, dv, b, h, rows, c
     idx = torch.arange(N)
     # rows i: everything from keys j <= i
     s = Q[rows] @ K.T / c
-    m = (idx[None, :] <= rows[:, None]).double()
+    m = (idx[None, :] <= rows[:, None]).double() if causal else torch.ones(len(rows), N, dtype=torch.float64)
     half = 0.5 if p == 2 else 0.0                            # f(s) = 1 + s (+ s^2/2), f'(s) = 1 (+ s)
     w = (1 + s + half * s * s) * m
     gr = w.sum(-1)
@@ -225,7 +225,7 @@ def _sampled_rows_and_columns_check(q, k, v, do, o, g, dq, dk, dv, b, h, rows, c
     Uall = DO / G[:, None]
     Dall = (DO * O).sum(-1) / G
     st = K[cols] @ Q.T / c                                   # (cols, N) scores s_ij for j in cols
-    mt = (idx[None, :] >= cols[:, None]).double()
+    mt = (idx[None, :] >= cols[:, None]).double() if causal else torch.ones(len(cols), N, dtype=torch.float64)
     wt = (1 + st + half * st * st) * mt
     et = (1 + 2 * half * st) * (V[cols] @ Uall.T - Dall[None, :]) * mt
     ok = _rows_ok(dv[b, h].double().cpu()[cols], wt @ Uall)
@@ -282,6 +282,27 @@ def test_headline_shape_first_order_sampled():
     cols = torch.tensor([0, 127, 128, 9000, 16255, 16382])
     for (b, h) in ((0, 0), (7, 31), (3, 17), (4, 20), (6, 9)):
         _sampled_rows_and_columns_check(q, k, v, do, o, g, dq, dk, dv, b, h, rows, cols, c, p=p)
+
+
+@pytest.mark.parametrize("shape", [(8, 32, 16384), (1, 2, 20000), (1, 40, 1500)], ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("keep", [False, True], ids=["rebuild", "kept-state"])
+def test_first_order_full_streaming_passes(shape, keep):
+    """p = 1 without a mask (fm_p1full.cu: reduce + finalize + apply passes): the headline shape under full memory
+    load, a long sequence of few (b,h) (the reduce is split 8 ways, ragged last tile) and many short ones; with the
+    (k, v) state rebuilt in backward and kept from forward.  Sampled rows / columns against the dense formula."""
+    from fastmax_experiments_b200.fastmax import saved_state_bytes
+    B, H, N = shape
+    D, p = 64, 1
+    gen = torch.Generator(device="cuda").manual_seed(29 + N)
+    q, k, v, do = (torch.randn(B, H, N, D, device="cuda", generator=gen).to(torch.bfloat16) for _ in range(4))
+    c = orc.denominator_c(D)
+    saved = torch.empty(saved_state_bytes(q, False, p), dtype=torch.uint8, device="cuda") if keep else None
+    o, g = fastmax_fwd_raw(q, k, v, False, 1.0 / c, p, saved=saved)
+    dq, dk, dv = fastmax_bwd_raw(q, k, v, o, g, do, False, 1.0 / c, p, saved=saved)
+    rows = torch.tensor([0, 1, 127, 128, N // 2, N - 129, N - 1])
+    cols = torch.tensor([0, 63, 128, N // 3, N - 1])
+    for (b, h) in ((0, 0), (B - 1, H - 1), (B // 2, H // 2)):
+        _sampled_rows_and_columns_check(q, k, v, do, o, g, dq, dk, dv, b, h, rows, cols, c, p=p, causal=False)
 
 
 def test_cuda_graph_capture_replays_the_step():

@@ -3,11 +3,13 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspa
 from fastmax_experiments_b200 import _lib
 from fastmax_experiments_b200.fastmax import fastmax_fwd_raw, fastmax_bwd_raw
 B, H, N = 8, 32, 16384
+CAUSAL = os.environ.get('P1_CAUSAL', '1') == '1'
+PP = int(os.environ.get('P1_P', '1'))
 gen = torch.Generator(device="cuda").manual_seed(0)
 q, k, v, do = (torch.randn(B, H, N, 64, device="cuda", generator=gen).to(torch.bfloat16) for _ in range(4))
 def step():
-    o, g = fastmax_fwd_raw(q, k, v, True, 1 / 64, 1, _lib.ALGO_MOMENTS)
-    return fastmax_bwd_raw(q, k, v, o, g, do, True, 1 / 64, 1, _lib.ALGO_MOMENTS)
+    o, g = fastmax_fwd_raw(q, k, v, CAUSAL, 1 / 64, PP, _lib.ALGO_MOMENTS)
+    return fastmax_bwd_raw(q, k, v, o, g, do, CAUSAL, 1 / 64, PP, _lib.ALGO_MOMENTS)
 for _ in range(3): step()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
