@@ -480,6 +480,7 @@ def main() -> None:
     ap.add_argument("--model", default="pythia-14m", choices=sorted(MODEL_SEQ),
                     help="--workload model: which lit_gpt config (default sequence lengths: BASELINE.json configs)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-p1", action="store_true", help="skip the first-order (p=1) side measurement")
     ap.add_argument("--no-sp", action="store_true", help="N > 1: skip the sequence-parallel (config 5) leg")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -639,6 +640,39 @@ def main() -> None:
                    "sharding": "(b,h) units per rank, no collective"},
         "clocks": clocks, "gpu_launches": launches, "roofline": roofline, "kernels": kernels,
     }
+
+    # ---- first order (p = 1) on the same inputs: the HBM-bound side of the op (1544 B per unit) ----
+    if not args.no_p1:
+        fo = {}
+        for name, causal in (("causal", True), ("full", False)):
+            def step1():
+                o, g = fastmax_fwd_raw(q, k, v, causal, inv_c, 1, algo)
+                return fastmax_bwd_raw(q, k, v, o, g, do, causal, inv_c, 1, algo)
+            for _ in range(3):
+                step1()
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n1 = max(3, args.steps)
+            a0.record()
+            for _ in range(n1):
+                step1()
+            a1.record()
+            torch.cuda.synchronize()
+            ms1 = a0.elapsed_time(a1) / n1
+            gbs = U * (12 * D * 2 + 8) / (ms1 * 1e-3) / 1e9
+            _lib.profile_enable(True)
+            step1()
+            torch.cuda.synchronize()
+            k1 = {}
+            for nm, ms in _lib.profile_fetch():
+                k1[nm] = round(k1.get(nm, 0.0) + ms, 4)
+            _lib.profile_enable(False)
+            fo[name] = {"ms_per_step": round(ms1, 4), "tokens_per_s": round(B * N / (ms1 * 1e-3)),
+                        "roofline": {"bound": "hbm", "achieved": round(gbs, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                     "frac": round(gbs / peaks["hbm_gbs"], 4)},
+                        "kernels_ms": k1}
+        out["first_order"] = {"workload": f"fastmax p=1 fwd+bwd B={B} H={H} N={N} D={D} bf16 on this rank's inputs, "
+                                          "forward state not kept; algorithmic bytes 1544 B per (b,h,token)", **fo}
 
     # ---- e2e: host buffers in, host buffers out, copies inside the timed region ---------------
     if not args.no_e2e:

@@ -99,9 +99,14 @@ namespace mom { struct ApplyDesc; }
 int launch_apply_gen(const Problem& pb, int BH, int nrec, const char* name, const mom::ApplyDesc& d, int variant);
 // first-order causal FastMax as one fused scan per (b,h) (fm_p1scan.cu)
 bool p1scan_usable(const Problem& pb);
-int p1scan_fwd(const Problem& pb, const void* q, const void* k, const void* v, void* o, float* g);
+size_t p1scan_region_bytes(const Problem& pb);      // scratch per state region (0 unless sequences are cut into chunks)
+int p1scan_fwd(const Problem& pb, const void* q, const void* k, const void* v, void* o, float* g, void* region);
 int p1scan_bwd(const Problem& pb, int Npad, const void* q, const void* k, const void* v, const void* u, const float* dlt,
-               void* dq, void* dk, void* dv);
+               void* dq, void* dk, void* dv, void* region_s, void* region_r);
+int p1full_max_split();
+size_t p1full_prefix_bytes(int B, int H, int nsplit);
+int p1full_prefix_states(const Problem& pb, int Npad, const void* x, const void* w, const float* dlt, int nsplit,
+                         int tiles_per_split, int dir, void* region, const float** init);
 // first-order non-causal FastMax as streaming reduce + apply passes (fm_p1full.cu); `region*`: p1full_state_bytes each
 bool p1full_usable(const Problem& pb);
 size_t p1full_state_bytes(int B, int H);

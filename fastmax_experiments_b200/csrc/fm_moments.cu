@@ -977,8 +977,8 @@ int moments_fwd(const Problem& pb, const void* q, const void* k, const void* v, 
   uint8_t* w8 = (uint8_t*)ws;
   int rc;
   const float a = pb.inv_c;
-  if (p1_scan_enabled() && p1scan_usable(pb)) return p1scan_fwd(pb, q, k, v, o, g);
   uint8_t* state = pb.saved_states ? (uint8_t*)pb.saved_states : w8 + m.off_state;
+  if (p1_scan_enabled() && p1scan_usable(pb)) return p1scan_fwd(pb, q, k, v, o, g, w8 + m.off_state);
   if (p1_scan_enabled() && p1full_usable(pb)) return p1full_fwd(pb, q, k, v, o, g, state);
   float* part = (float*)(w8 + m.off_part);
   // 1. K^T and the boundary states (forward direction)
@@ -1020,7 +1020,7 @@ int moments_bwd(const Problem& pb, const void* q, const void* k, const void* v, 
     FM_LAUNCH("mom_prep_bwd", pb.stream,
               prep_bwd_kernel<false><<<(unsigned)((rows + 31) / 32), 256, 0, pb.stream>>>(
                   (const bf16*)q, (const bf16*)o, (const bf16*)d_o, g, u, dlt, qd, rows, m.N, m.Npad));
-    return p1scan_bwd(pb, m.Npad, q, k, v, u, dlt, dq, dk, dv);
+    return p1scan_bwd(pb, m.Npad, q, k, v, u, dlt, dq, dk, dv, w8 + m.off_state, R);
   }
   if (p1_scan_enabled() && p1full_usable(pb)) {
     FM_LAUNCH("mom_prep_bwd", pb.stream,

@@ -36,7 +36,7 @@ constexpr int PART_BYTES = PART_FLOATS * 4;
 // panel 1 = [64 y][64], column 64 in element 0), then fp32 row 64 [80], column 64 [64], column 65 [64]
 constexpr int FINAL_VEC = 16384;
 constexpr int FINAL_BYTES = 16384 + (80 + 64 + 64) * 4 + 192;   // 17408, a multiple of 256
-constexpr int MAX_SPLIT = 8;
+constexpr int MAX_SPLIT = 16;
 
 __device__ __forceinline__ void bulk_wait_group_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
@@ -210,6 +210,22 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__
   }
 }
 
+// exclusive prefix (dir 0) or suffix (dir 1) over the chunks of a (b,h): what a causal scan over chunk c starts from
+__global__ void __launch_bounds__(256) prefix_kernel(const float* __restrict__ partial, int nsplit, int dir,
+                                                     float* __restrict__ init) {
+  const int bh = blockIdx.x;
+  const float* src = partial + (size_t)bh * nsplit * PART_FLOATS;
+  float* dst = init + (size_t)bh * nsplit * PART_FLOATS;
+  for (int idx = threadIdx.x; idx < PART_FLOATS; idx += 256) {
+    float s = 0.f;
+    for (int j = 0; j < nsplit; ++j) {
+      const int c = dir ? nsplit - 1 - j : j;
+      dst[(size_t)c * PART_FLOATS + idx] = s;
+      s += src[(size_t)c * PART_FLOATS + idx];
+    }
+  }
+}
+
 // ============================================================================================ apply
 constexpr int A_STAGES = 3;
 constexpr int A_OFF_SB = 0;
@@ -375,6 +391,9 @@ applyfull_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 using namespace p1f;
 
+int p1full_max_split() { return MAX_SPLIT; }
+size_t p1full_prefix_bytes(int B, int H, int nsplit) { return (size_t)B * H * nsplit * PART_BYTES * 2; }
+
 static int reduce_geometry(const Problem& pb, int* nsplit, int* tiles_per_split) {
   const int BH = pb.B * pb.H, ntile = (pb.N + 127) / 128;
   int ns = (592 + BH - 1) / BH;                       // two CTAs per SM on 148 SMs, twice over
@@ -393,18 +412,45 @@ bool p1full_usable(const Problem& pb) {
          !pb.sp_init_fwd && !pb.sp_init_rev;
 }
 
+static int launch_reduce(const Problem& pb, const void* x, const void* w, const float* dlt, ReduceParams& P);
+
+// per-chunk states of (x, w [, dlt]) for a sequence cut into `nsplit` chunks of `tiles_per_split` tiles, and their
+// exclusive prefix (dir 0) / suffix (dir 1) -> *init: (BH, nsplit, PART_FLOATS) inside `region` (p1full_prefix_bytes)
+int p1full_prefix_states(const Problem& pb, int Npad, const void* x, const void* w, const float* dlt, int nsplit,
+                         int tiles_per_split, int dir, void* region, const float** init) {
+  const int BH = pb.B * pb.H;
+  ReduceParams P{};
+  P.N = pb.N, P.Npad = Npad, P.dlt = dlt, P.ntile = (pb.N + 127) / 128;
+  P.nsplit = nsplit, P.tiles_per_split = tiles_per_split;
+  P.partial = (float*)region;
+  float* out = P.partial + (size_t)BH * nsplit * PART_FLOATS;
+  int rc;
+  if ((rc = launch_reduce(pb, x, w, dlt, P))) return rc;
+  FM_LAUNCH("p1_prefix_states", pb.stream, prefix_kernel<<<BH, 256, 0, pb.stream>>>(P.partial, nsplit, dir, out));
+  *init = out;
+  return FASTMAX_OK;
+}
+
 // state of (x, w [, dlt]) -> final states at `region`
 int p1full_reduce(const Problem& pb, int Npad, const void* x, const void* w, const float* dlt, void* region) {
   const int BH = pb.B * pb.H;
-  CUtensorMap tX, tW;
-  int rc;
-  if ((rc = make_tmap_bf16_3d(&tX, x, 64, pb.N, BH, 128, (uint64_t)pb.N * 128, 64, 64))) return rc;
-  if ((rc = make_tmap_bf16_3d(&tW, w, 64, pb.N, BH, 128, (uint64_t)pb.N * 128, 64, 64))) return rc;
   ReduceParams P{};
   P.N = pb.N, P.Npad = Npad, P.dlt = dlt;
   P.ntile = reduce_geometry(pb, &P.nsplit, &P.tiles_per_split);
   uint8_t* fin = (uint8_t*)region;
   P.partial = (float*)(fin + (size_t)BH * FINAL_BYTES);
+  int rc;
+  if ((rc = launch_reduce(pb, x, w, dlt, P))) return rc;
+  FM_LAUNCH("p1_full_finalize", pb.stream, finalize_kernel<<<BH, 256, 0, pb.stream>>>(P.partial, P.nsplit, fin));
+  return FASTMAX_OK;
+}
+
+static int launch_reduce(const Problem& pb, const void* x, const void* w, const float* dlt, ReduceParams& P) {
+  const int BH = pb.B * pb.H;
+  CUtensorMap tX, tW;
+  int rc;
+  if ((rc = make_tmap_bf16_3d(&tX, x, 64, pb.N, BH, 128, (uint64_t)pb.N * 128, 64, 64))) return rc;
+  if ((rc = make_tmap_bf16_3d(&tW, w, 64, pb.N, BH, 128, (uint64_t)pb.N * 128, 64, 64))) return rc;
   const uint32_t base = sm100::FM_SMEM_BASE;
   for (int s = 0; s < R_STAGES; ++s)
     for (int kk = 0; kk < 8; ++kk) {
@@ -420,7 +466,6 @@ int p1full_reduce(const Problem& pb, int Npad, const void* x, const void* w, con
     FM_CUDA(cudaFuncSetAttribute(reduce_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, R_SMEM));
     FM_LAUNCH("p1_full_reduce", pb.stream, reduce_kernel<false><<<grid, THREADS, R_SMEM, pb.stream>>>(tX, tW, P));
   }
-  FM_LAUNCH("p1_full_finalize", pb.stream, finalize_kernel<<<BH, 256, 0, pb.stream>>>(P.partial, P.nsplit, fin));
   return FASTMAX_OK;
 }
 

@@ -78,6 +78,10 @@ constexpr int C_ST = 176;                // 128 x 80 state accumulator (rows 0..
 
 struct Params {
   int N, Npad, ntile;
+  // a sequence may be cut into `nchunk` ranges of `tiles_per_chunk` tiles, one CTA each (few (b,h), long sequences);
+  // a chunk then starts from `init`, the state of everything before (reverse modes: after) it
+  int nchunk, tiles_per_chunk;
+  const float* init;         // (BH, nchunk, 64*66 + 80) fp32 in the layout of fm_p1full.cu's partial states, or null
   float a;
   const float* dlt;          // (BH, Npad) fp32, zero padded (DQ, DV, DK)
   float* g;                  // (BH, N) (FWD)
@@ -129,7 +133,9 @@ scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   float* dcol = vcol_base + 128;                                        // [128] dlt of the tile's tokens (DK: per column)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int bh = blockIdx.x;
+  const int bh = blockIdx.x / P.nchunk, chunk = blockIdx.x % P.nchunk;
+  const int t_lo = chunk * P.tiles_per_chunk, t_hi = min(P.ntile, t_lo + P.tiles_per_chunk);   // this CTA's tiles
+  const int ntile = t_hi - t_lo;
 
   if (warp == 4) {
     tmem_alloc(tmem_slot, 256);
@@ -163,8 +169,8 @@ scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // ---------------------------------------------------------------- TMA producer
     if (lane == 0) {
       const size_t row0 = (size_t)bh * P.N;
-      for (int it = 0; it < P.ntile; ++it) {
-        const int t = REV ? P.ntile - 1 - it : it;
+      for (int it = 0; it < ntile; ++it) {
+        const int t = REV ? t_hi - 1 - it : t_lo + it;
         const int tok = t * 128;
         if (it > 0) mbar_wait(a_free, (it - 1) & 1, 200 + it);      // each operand is refilled as soon as it is dead
         mbar_arrive_expect_tx(full_s, 2 * 16384);
@@ -176,8 +182,8 @@ scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         for (int h = 0; h < 2; ++h) tma_load_3d(smem + OFF_B2 + h * 8192, &tmB2, full_v, 0, tok + 64 * h, bh);
         // pull the tile after next towards L2 while this one is being worked on
         const int it2 = it + FM_P1_PF;
-        if (FM_P1_PF > 0 && it2 < P.ntile) {
-          const int t2 = REV ? P.ntile - 1 - it2 : it2;
+        if (FM_P1_PF > 0 && it2 < ntile) {
+          const int t2 = REV ? t_hi - 1 - it2 : t_lo + it2;
           const size_t off = (row0 + (size_t)t2 * 128) * 64;
           const uint32_t nb = (uint32_t)min(128, P.N - t2 * 128) * 128u;       // whole 128-byte rows
           prefetch_l2(P.pA + off, nb), prefetch_l2(P.pB1 + off, nb), prefetch_l2(P.pB2 + off, nb);
@@ -192,7 +198,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // as well -- and on warp 0 that time sat on every tile's critical path.
     constexpr uint32_t ID_S = make_idesc_bf16(128, 64, false, false);
     constexpr uint32_t ID_UPD = make_idesc_bf16(128, 80, true, true);
-    for (int it = 0; it < P.ntile; ++it) {
+    for (int it = 0; it < ntile; ++it) {
       {
         // scores of half 0 of tile it, into columns [0, 64): for it > 0 as soon as the previous tile's second
         // polynomial has read its scores ([32, 96)) and its first P ([0, 32)) has been consumed
@@ -241,24 +247,57 @@ scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                                               : make_idesc_bf16(128, 64, false, false);
     constexpr uint32_t ID_PV = make_idesc_bf16(128, NACC, false, true);
     const float a = P.a;
-    // zero the state accumulator
+    // the state accumulator: zero, or the state of everything before (after) this chunk -- then also its bf16 copy
+    // and fp32 vectors, which the first tile reads
     {
-      uint32_t z[16];
+      const float* src = P.init ? P.init + ((size_t)bh * P.nchunk + chunk) * (64 * 66 + 80) : nullptr;
+      const float sc = (MODE == FWD || MODE == DV) ? a : 1.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 80; c0 += 16) {
+        uint32_t z[16];
 #pragma unroll
-      for (int c = 0; c < 16; ++c) z[c] = 0u;
+        for (int c = 0; c < 16; ++c) {
+          float x = 0.f;
+          if (src) {
+            if (r < 64) x = c0 + c < 66 ? src[r * 66 + c0 + c] : 0.f;
+            else if (r == 64) x = src[64 * 66 + c0 + c];
+          }
+          z[c] = __float_as_uint(x);
+        }
+        tmem_st16(lane_addr + C_ST + c0, z);
+        if (src && r < 64 && c0 < 64) {      // bf16 copy, rows y = 0..63: 16-byte chunks c0/8 and c0/8 + 1 of the swizzled row
+          const uint32_t dst = smem_u32(smem) + OFF_SB + r * 128;
 #pragma unroll
-      for (int c = 0; c < 80; c += 16) tmem_st16(lane_addr + C_ST + c, z);
+          for (int j = 0; j < 2; ++j)
+            sts128(dst + ((uint32_t)((c0 / 8 + j) ^ (r & 7)) << 4),
+                   pack_bf16x2(sc * __uint_as_float(z[8 * j]), sc * __uint_as_float(z[8 * j + 1])),
+                   pack_bf16x2(sc * __uint_as_float(z[8 * j + 2]), sc * __uint_as_float(z[8 * j + 3])),
+                   pack_bf16x2(sc * __uint_as_float(z[8 * j + 4]), sc * __uint_as_float(z[8 * j + 5])),
+                   pack_bf16x2(sc * __uint_as_float(z[8 * j + 6]), sc * __uint_as_float(z[8 * j + 7])));
+        }
+        if (src && r < 64 && c0 == 64) {
+          vcol_base[r] = __uint_as_float(z[REV ? 1 : 0]);
+          if (MODE == FWD)
+            *reinterpret_cast<uint16_t*>(smem + OFF_SB + 8192 + r * 128 + ((r & 7) << 4)) =
+                __bfloat16_as_ushort(__float2bfloat16_rn(sc * __uint_as_float(z[0])));
+        }
+        if (src && r == 64) {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) vrow_base[c0 + c] = __uint_as_float(z[c]);
+        }
+      }
       tmem_wait_st();
+      fence_proxy_async();
       tc_fence_before();
       named_barrier_sync(1, 128);
       tc_fence_after();
     }
-    for (int it = 0; it < P.ntile; ++it) {
+    for (int it = 0; it < ntile; ++it) {
       auto wait_mma = [&](int ev) {
         mbar_wait_warp(&mma[ev], it & 1);
         tc_fence_after();
       };
-      const int t = REV ? P.ntile - 1 - it : it;
+      const int t = REV ? t_hi - 1 - it : t_lo + it;
       const int i_tok = t * 128 + r;                         // this thread's token (row of A)
       const bool valid = i_tok < P.N;
       float dlt_row = 0.f;
@@ -454,7 +493,8 @@ using namespace p1;
 
 template <int MODE>
 static int launch_scan(const Problem& pb, int Npad, const void* A, const void* B1, const void* B2, void* out,
-                       const float* dlt, float* g, const char* name) {
+                       const float* dlt, float* g, const char* name, const float* init = nullptr, int nchunk = 1,
+                       int tiles_per_chunk = 0) {
   const int BH = pb.B * pb.H;
   CUtensorMap tA, tB1, tB2, tO;
   int rc;
@@ -465,6 +505,7 @@ static int launch_scan(const Problem& pb, int Npad, const void* A, const void* B
   Params P{};
   P.N = pb.N, P.Npad = Npad, P.ntile = (pb.N + 127) / 128, P.a = pb.inv_c, P.dlt = dlt, P.g = g;
   P.pA = (const bf16*)A, P.pB1 = (const bf16*)B1, P.pB2 = (const bf16*)B2;
+  P.init = init, P.nchunk = nchunk, P.tiles_per_chunk = nchunk > 1 ? tiles_per_chunk : P.ntile;
   const uint32_t base = sm100::FM_SMEM_BASE;
   // operand roles of the state update: X carries the first-order index (k or q), W the value-like tensor (v or u)
   const uint32_t offX = (MODE == FWD || MODE == DV) ? OFF_B1 : OFF_B2;
@@ -486,28 +527,56 @@ static int launch_scan(const Problem& pb, int Npad, const void* A, const void* B
   }
   auto kern = scan_kernel<MODE>;
   FM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-  FM_LAUNCH(name, pb.stream, kern<<<BH, THREADS, SMEM, pb.stream>>>(tA, tB1, tB2, tO, P));
+  FM_LAUNCH(name, pb.stream, kern<<<BH * nchunk, THREADS, SMEM, pb.stream>>>(tA, tB1, tB2, tO, P));
   return FASTMAX_OK;
 }
 
 bool p1scan_usable(const Problem& pb) {
-  // one CTA per (b,h) walks the sequence: with few (b,h) and a long sequence the chunked path's parallelism over
-  // segments wins, so it keeps those (and the sequence-parallel entries, which hand states between ranks)
+  // (the sequence-parallel entries, which hand states between ranks, stay on the chunked path)
   return pb.p == 1 && pb.causal && pb.D == 64 && pb.dtype == FASTMAX_DTYPE_BF16 && pb.N >= 256 &&
-         (pb.B * pb.H >= 16 || pb.N <= 8192) && !pb.sp_init_fwd && !pb.sp_init_rev;
+         !pb.sp_init_fwd && !pb.sp_init_rev;
 }
 
-int p1scan_fwd(const Problem& pb, const void* q, const void* k, const void* v, void* o, float* g) {
-  return launch_scan<FWD>(pb, (int)align_up(pb.N, 64), q, k, v, o, nullptr, g, "p1_scan_fwd");
+// One CTA per (b,h) walks the whole sequence when there are enough (b,h) to fill the GPU (two CTAs per SM).  With
+// fewer, each sequence is cut into chunks of at least 8 tiles: a streaming reduce pass (fm_p1full.cu) gives every
+// chunk's own state, a prefix kernel the state before (after) it, and the chunks scan in parallel from there.
+static int scan_chunks(const Problem& pb, int* tiles_per_chunk) {
+  const int BH = pb.B * pb.H, ntile = (pb.N + 127) / 128;
+  int nc = BH >= 148 ? 1 : std::min(std::min(296 / BH, p1full_max_split()), ntile / 8);
+  nc = std::max(nc, 1);
+  const int tpc = (ntile + nc - 1) / nc;
+  *tiles_per_chunk = tpc;
+  return (ntile + tpc - 1) / tpc;
+}
+
+size_t p1scan_region_bytes(const Problem& pb) {
+  int tpc;
+  const int nc = scan_chunks(pb, &tpc);
+  return nc > 1 ? p1full_prefix_bytes(pb.B, pb.H, nc) : 0;
+}
+
+// region: scratch of p1scan_region_bytes (chunked sequences only)
+int p1scan_fwd(const Problem& pb, const void* q, const void* k, const void* v, void* o, float* g, void* region) {
+  int tpc, rc;
+  const int nc = scan_chunks(pb, &tpc);
+  const float* init = nullptr;
+  if (nc > 1 && (rc = p1full_prefix_states(pb, 0, k, v, nullptr, nc, tpc, 0, region, &init))) return rc;
+  return launch_scan<FWD>(pb, (int)align_up(pb.N, 64), q, k, v, o, nullptr, g, "p1_scan_fwd", init, nc, tpc);
 }
 
 // u = do/g (bf16), dlt = (do.o)/g (fp32, (BH, Npad)) from the prep kernel
 int p1scan_bwd(const Problem& pb, int Npad, const void* q, const void* k, const void* v, const void* u, const float* dlt,
-               void* dq, void* dk, void* dv) {
-  int rc;
-  if ((rc = launch_scan<DQ>(pb, Npad, u, v, k, dq, dlt, nullptr, "p1_scan_dq"))) return rc;
-  if ((rc = launch_scan<DV>(pb, Npad, k, q, u, dv, dlt, nullptr, "p1_scan_dv"))) return rc;
-  return launch_scan<DK>(pb, Npad, v, u, q, dk, dlt, nullptr, "p1_scan_dk");
+               void* dq, void* dk, void* dv, void* region_s, void* region_r) {
+  int tpc, rc;
+  const int nc = scan_chunks(pb, &tpc);
+  const float *init_s = nullptr, *init_r = nullptr;
+  if (nc > 1) {
+    if ((rc = p1full_prefix_states(pb, Npad, k, v, nullptr, nc, tpc, 0, region_s, &init_s))) return rc;
+    if ((rc = p1full_prefix_states(pb, Npad, q, u, dlt, nc, tpc, 1, region_r, &init_r))) return rc;
+  }
+  if ((rc = launch_scan<DQ>(pb, Npad, u, v, k, dq, dlt, nullptr, "p1_scan_dq", init_s, nc, tpc))) return rc;
+  if ((rc = launch_scan<DV>(pb, Npad, k, q, u, dv, dlt, nullptr, "p1_scan_dv", init_r, nc, tpc))) return rc;
+  return launch_scan<DK>(pb, Npad, v, u, q, dk, dlt, nullptr, "p1_scan_dk", init_r, nc, tpc);
 }
 
 }  // namespace fm

@@ -284,6 +284,27 @@ def test_headline_shape_first_order_sampled():
         _sampled_rows_and_columns_check(q, k, v, do, o, g, dq, dk, dv, b, h, rows, cols, c, p=p)
 
 
+@pytest.mark.parametrize("shape", [(1, 2, 65536), (2, 3, 20001), (1, 40, 4096)], ids=lambda s: "x".join(map(str, s)))
+def test_first_order_causal_chunk_parallel_scan(shape):
+    """p = 1 causal with too few (b,h) to fill the GPU one sequence per CTA: each sequence is cut into up to 16 chunks
+    that scan in parallel from the state before (after) them -- per-chunk states from the streaming reduce pass plus
+    an exclusive prefix / suffix.  Sampled rows / columns around the chunk boundaries against the dense formula."""
+    B, H, N = shape
+    D, p = 64, 1
+    gen = torch.Generator(device="cuda").manual_seed(31 + N)
+    q, k, v, do = (torch.randn(B, H, N, D, device="cuda", generator=gen).to(torch.bfloat16) for _ in range(4))
+    c = orc.denominator_c(D)
+    o, g = fastmax_fwd_raw(q, k, v, True, 1.0 / c, p)
+    dq, dk, dv = fastmax_bwd_raw(q, k, v, o, g, do, True, 1.0 / c, p)
+    ntile = (N + 127) // 128
+    nc = max(1, min(296 // (B * H), 16, ntile // 8))
+    edge = 128 * ((ntile + nc - 1) // nc)                     # first chunk boundary (tokens)
+    rows = torch.tensor(sorted({37, 127, 128, edge - 1, edge, edge + 1, min(N - 1, 2 * edge), N // 2, N - 2, N - 1}))
+    cols = torch.tensor(sorted({0, 127, edge - 1, edge, min(N - 1, 2 * edge - 1), N // 3, N - 1}))
+    for (b, h) in ((0, 0), (B - 1, H - 1)):
+        _sampled_rows_and_columns_check(q, k, v, do, o, g, dq, dk, dv, b, h, rows, cols, c, p=p)
+
+
 @pytest.mark.parametrize("shape", [(8, 32, 16384), (1, 2, 20000), (1, 40, 1500)], ids=lambda s: "x".join(map(str, s)))
 @pytest.mark.parametrize("keep", [False, True], ids=["rebuild", "kept-state"])
 def test_first_order_full_streaming_passes(shape, keep):

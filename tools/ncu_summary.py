@@ -15,6 +15,8 @@ KEEP = [
     "lts__t_sector_hit_rate.pct", "sm__inst_executed.sum.per_cycle_elapsed", "sm__cycles_elapsed.max",
 ]
 import json
+FM_KERNELS = ("fm::", "apply_kernel", "build_kernel", "intra_kernel", "prep_bwd_kernel", "transpose_kernel", "scan_kernel",
+              "reduce_kernel", "applyfull_kernel", "finalize_kernel")
 rows = list(csv.reader(open(sys.argv[1])))
 hdr, units = rows[0], rows[1]
 ix = {h: i for i, h in enumerate(hdr)}
@@ -22,7 +24,7 @@ cols = [c for c in KEEP if c in ix]
 w = csv.writer(sys.stdout)
 w.writerow(cols)
 for r in rows[2:]:
-    if len(r) < len(hdr) or not any(k in r[ix["Kernel Name"]] for k in ("fm::", "apply_kernel", "build_kernel", "intra_kernel", "prep_bwd_kernel", "transpose_kernel")):      # only this library's kernels
+    if len(r) < len(hdr) or not any(k in r[ix["Kernel Name"]] for k in FM_KERNELS):      # only this library's kernels
         continue
     w.writerow([r[ix[c]] + ("" if c == "Kernel Name" or not units[ix[c]] else " " + units[ix[c]]) for c in cols])
 
@@ -32,7 +34,7 @@ if len(sys.argv) > 2:
         v, u = float(r[ix[c]]), units[ix[c]]
         return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[u]
     fm_rows = [r for r in rows[2:] if len(r) >= len(hdr) and any(k in r[ix["Kernel Name"]] for k in
-               ("fm::", "apply_kernel", "build_kernel", "intra_kernel", "prep_bwd_kernel", "transpose_kernel"))]
+               FM_KERNELS)]
     tot = sum(gb(r, "dram__bytes_read.sum") + gb(r, "dram__bytes_write.sum") for r in fm_rows)
     json.dump({"launches": len(fm_rows), "dram_bytes_per_step": tot, "config": {"B": 8, "H": 32, "N": 16384, "kept_states": True},
                "source": "ncu --set full, one fwd+bwd step at the headline shape (tools/prof_run.py 8 32 16384 64 1 --bwd --keep)"},
