@@ -181,17 +181,17 @@ reduce_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   if (warp == 4) tmem_dealloc(tmem, 128);
 }
 
-// sum of the partial states of a (b,h) -> bf16 operand panels + fp32 vectors
+// sum of the partial states of a (b,h) -> bf16 operand panels + fp32 vectors; FIN_SPLIT blocks per (b,h)
+constexpr int FIN_SPLIT = 8;
 __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__ partial, int nsplit,
                                                        uint8_t* __restrict__ final_state) {
-  const int bh = blockIdx.x;
+  const int bh = blockIdx.x / FIN_SPLIT, part = blockIdx.x % FIN_SPLIT;
   const float* src = partial + (size_t)bh * nsplit * PART_FLOATS;
   uint8_t* dst = final_state + (size_t)bh * FINAL_BYTES;
-  // panel 1 is read as columns 64..79 of the state: everything but column 64 is zero
-  for (int i = threadIdx.x; i < 8192 / 16; i += 256) reinterpret_cast<uint4*>(dst + 8192)[i] = make_uint4(0u, 0u, 0u, 0u);
-  __syncthreads();
   float* vec = reinterpret_cast<float*>(dst + FINAL_VEC);
-  for (int idx = threadIdx.x; idx < PART_FLOATS; idx += 256) {
+  constexpr int PER = (PART_FLOATS + FIN_SPLIT - 1) / FIN_SPLIT;
+  const int hi = min(PART_FLOATS, (part + 1) * PER);
+  for (int idx = part * PER + threadIdx.x; idx < hi; idx += 256) {
     float s = 0.f;
     for (int sp = 0; sp < nsplit; ++sp) s += src[(size_t)sp * PART_FLOATS + idx];
     if (idx < 64 * 66) {
@@ -199,7 +199,10 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__
       if (c < 64) {
         *reinterpret_cast<bf16*>(dst + y * 128 + (((c >> 3) ^ (y & 7)) << 4) + (c & 7) * 2) = __float2bfloat16_rn(s);
       } else if (c == 64) {
-        *reinterpret_cast<bf16*>(dst + 8192 + y * 128 + ((y & 7) << 4)) = __float2bfloat16_rn(s);
+        // panel 1 is read as columns 64..79 of the state: row y = [column 64, 0, 0, ...] (element 0 sits in chunk y & 7)
+        uint4* row = reinterpret_cast<uint4*>(dst + 8192 + y * 128);
+        for (int j = 0; j < 8; ++j)
+          row[j] = make_uint4(j == (y & 7) ? (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(s)) : 0u, 0u, 0u, 0u);
         vec[80 + y] = s;
       } else {
         vec[144 + y] = s;
@@ -441,7 +444,7 @@ int p1full_reduce(const Problem& pb, int Npad, const void* x, const void* w, con
   P.partial = (float*)(fin + (size_t)BH * FINAL_BYTES);
   int rc;
   if ((rc = launch_reduce(pb, x, w, dlt, P))) return rc;
-  FM_LAUNCH("p1_full_finalize", pb.stream, finalize_kernel<<<BH, 256, 0, pb.stream>>>(P.partial, P.nsplit, fin));
+  FM_LAUNCH("p1_full_finalize", pb.stream, finalize_kernel<<<BH * FIN_SPLIT, 256, 0, pb.stream>>>(P.partial, P.nsplit, fin));
   return FASTMAX_OK;
 }
 
