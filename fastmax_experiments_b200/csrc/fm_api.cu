@@ -1,6 +1,8 @@
 // fm_api.cu -- the C ABI of include/fastmax_b200.h: argument checks, planning, dispatch.
 #include "fm_common.cuh"
 
+#include <atomic>
+#include <mutex>
 #include <vector>
 #include <string>
 
@@ -15,20 +17,26 @@ struct ProfRecord {
   const char* name;
   cudaEvent_t a, b;
 };
-static thread_local bool g_prof_on = false;
-static thread_local std::vector<ProfRecord> g_prof;
+// process-wide (autograd runs backward on its own thread); a thread remembers the record it opened
+static std::atomic<bool> g_prof_on{false};
+static std::mutex g_prof_mu;
+static std::vector<ProfRecord> g_prof;
+static thread_local cudaEvent_t g_prof_open = nullptr;
 
 void prof_begin(const char* name, cudaStream_t stream) {
-  if (!g_prof_on) return;
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
   ProfRecord r{name, nullptr, nullptr};
   cudaEventCreate(&r.a);
   cudaEventCreate(&r.b);
   cudaEventRecord(r.a, stream);
+  g_prof_open = r.b;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
   g_prof.push_back(r);
 }
 void prof_end(cudaStream_t stream) {
-  if (!g_prof_on || g_prof.empty()) return;
-  cudaEventRecord(g_prof.back().b, stream);
+  if (!g_prof_open) return;
+  cudaEventRecord(g_prof_open, stream);
+  g_prof_open = nullptr;
 }
 }  // namespace fm
 
@@ -104,18 +112,20 @@ const char* fastmax_last_cuda_error(void) { return fm::status().cuda_err; }
 int fastmax_last_launch_count(void) { return fm::status().launches; }
 
 void fastmax_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(fm::g_prof_mu);
   for (auto& r : fm::g_prof) {
     cudaEventDestroy(r.a);
     cudaEventDestroy(r.b);
   }
   fm::g_prof.clear();
-  fm::g_prof_on = on != 0;
+  fm::g_prof_on.store(on != 0);
 }
 
 int fastmax_profile_fetch(char* names, size_t names_cap, float* ms, int cap) {
   int n = 0;
   size_t used = 0;
   if (names && names_cap) names[0] = 0;
+  std::lock_guard<std::mutex> lk(fm::g_prof_mu);
   for (auto& r : fm::g_prof) {
     if (n >= cap) break;
     if (cudaEventSynchronize(r.b) != cudaSuccess) return FASTMAX_ERR_CUDA;
@@ -162,6 +172,11 @@ int fastmax_plan_make(fastmax_plan* plan, int B, int H, int N, int D, int p, int
   plan->n_seg = 1;
   plan->fwd_workspace_bytes = 0;
   plan->bwd_workspace_bytes = 0;
+  {
+    // head size 128 in bf16: dense tcgen05 tiles (fm_dense128.cu); its backward needs u and dlt
+    Problem pb{B, H, N, D, p, causal ? 1 : 0, dtype, 1.f, nullptr};
+    if (fm::dense128_usable(pb) && tensor_path_usable()) plan->bwd_workspace_bytes = fm::dense128_bwd_workspace_bytes(B, H, N);
+  }
   return FASTMAX_OK;
 }
 
@@ -193,6 +208,7 @@ int fastmax_fwd(const void* q, const void* k, const void* v, void* o, float* g, 
     if (((uintptr_t)workspace & 255) != 0) return FASTMAX_ERR_WORKSPACE;
     return fm::moments_fwd(pb, q, k, v, o, g, workspace);
   }
+  if (fm::dense128_usable(pb) && tensor_path_usable()) return fm::dense128_fwd(pb, q, k, v, o, g);
   return fm::exact_fwd(pb, q, k, v, o, g);
 }
 
@@ -211,6 +227,10 @@ int fastmax_bwd(const void* q, const void* k, const void* v, const void* o, cons
   if (pl.algo == FASTMAX_ALGO_MOMENTS) {
     if (((uintptr_t)workspace & 255) != 0) return FASTMAX_ERR_WORKSPACE;
     return fm::moments_bwd(pb, q, k, v, o, g, d_o, dq, dk, dv, workspace);
+  }
+  if (fm::dense128_usable(pb) && tensor_path_usable()) {
+    if (((uintptr_t)workspace & 255) != 0) return FASTMAX_ERR_WORKSPACE;
+    return fm::dense128_bwd(pb, q, k, v, o, g, d_o, dq, dk, dv, workspace);
   }
   return fm::exact_bwd(pb, q, k, v, o, g, d_o, dq, dk, dv);
 }

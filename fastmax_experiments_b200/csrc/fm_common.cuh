@@ -113,6 +113,12 @@ size_t p1full_state_bytes(int B, int H);
 int p1full_fwd(const Problem& pb, const void* q, const void* k, const void* v, void* o, float* g, void* region);
 int p1full_bwd(const Problem& pb, int Npad, const void* q, const void* k, const void* v, const void* u, const float* dlt,
                void* dq, void* dk, void* dv, void* region_s, bool have_s, void* region_r);
+// head size 128 (bf16) as dense tcgen05 tiles (fm_dense128.cu)
+bool dense128_usable(const Problem& pb);
+int dense128_fwd(const Problem& pb, const void* q, const void* k, const void* v, void* o, float* g);
+size_t dense128_bwd_workspace_bytes(int B, int H, int N);     // u (bf16) and dlt (fp32)
+int dense128_bwd(const Problem& pb, const void* q, const void* k, const void* v, const void* o, const float* g,
+                 const void* d_o, void* dq, void* dk, void* dv, void* ws);
 unsigned sm100_smem_base();     // FM_SMEM_BASE of fm_sm100.cuh (defined in fm_tmap.cu)
 // recurrent inference state (fm_decode.cu)
 size_t decode_state_bytes(int B, int H, int D, int p);

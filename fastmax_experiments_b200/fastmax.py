@@ -21,9 +21,10 @@ Behavioural notes:
   only, with the reference's count term N_q in the normaliser (fastmax.py:269-271, quirk Q2).
 * Meta tensors pass through shape-only (the pretrain scripts' flop count runs the model on the meta
   device, where the reference's own host hop fails: quirk Q7).
-* bf16 heads narrower than 64 (Pythia: 32) are zero-padded to 64 so that they run on the tcgen05
-  path (D = 64 kernels): zero features change neither the scores nor the normaliser, and the padded
-  output / gradient columns are exactly zero and sliced off.  ``c`` still uses the caller's D.
+* bf16 heads narrower than 64 (Pythia: 32) are zero-padded to 64, heads between 64 and 128 (phi: 80, Llama-3.2: 96 ...)
+  to 128, so that they run on the tcgen05 kernels (D = 64 moment / scan kernels, D = 128 dense tiles): zero features
+  change neither the scores nor the normaliser, and the padded output / gradient columns are exactly zero and sliced
+  off.  ``c`` still uses the caller's D.
 """
 from __future__ import annotations
 
@@ -37,7 +38,19 @@ from . import _lib
 __all__ = ["fastmax", "fastattention_einops", "FastmaxFunction", "fastmax_fwd_raw", "fastmax_bwd_raw", "rect_forward"]
 
 _DTYPES = {torch.float32: _lib.DTYPE_F32, torch.bfloat16: _lib.DTYPE_BF16}
-_TENSOR_PATH_D = 64      # head size of the tcgen05 kernels
+_TENSOR_PATH_D = 64      # head size of the tcgen05 moment / scan kernels
+_DENSE_PATH_D = 128      # head size of the dense tcgen05 tiles (csrc/fm_dense128.cu)
+
+
+def _head_pad(dtype, D, N):
+    """Zero features to append so that a bf16 head runs on a tcgen05 kernel (0: none / not applicable)."""
+    if dtype != torch.bfloat16:
+        return 0
+    if D < _TENSOR_PATH_D and N >= 256:
+        return _TENSOR_PATH_D - D
+    if _TENSOR_PATH_D < D < _DENSE_PATH_D and N >= 128:
+        return _DENSE_PATH_D - D
+    return 0
 _RECT_STATE_MAX_Q = 64   # N_q != N_k with at most this many queries goes through the recurrent-state kernels
 
 
@@ -142,7 +155,7 @@ def rect_forward(q, k, v, inv_c: float, p: int, count: str = "q"):
         q_ = F.pad(q_, (0, 0, 0, Nk - Nq))
     else:
         k_, v_ = F.pad(k_, (0, 0, 0, Nq - Nk)), F.pad(v_, (0, 0, 0, Nq - Nk))
-    pad = _TENSOR_PATH_D - D if (q.dtype == torch.bfloat16 and D < _TENSOR_PATH_D and q_.shape[2] >= 256) else 0
+    pad = _head_pad(q.dtype, D, q_.shape[2])
     if pad:
         q_, k_, v_ = (F.pad(t, (0, pad)) for t in (q_, k_, v_))
     o, g = fastmax_fwd_raw(q_, k_, v_, False, inv_c, p)
@@ -187,7 +200,7 @@ class FastmaxFunction(torch.autograd.Function):
         if q.shape[2] != k.shape[2]:
             return _inference_rect(ctx, q, k, v, 1.0 / c, p)
         q_, k_, v_ = q.contiguous(), k.contiguous(), v.contiguous()
-        pad = _TENSOR_PATH_D - D if (q.dtype == torch.bfloat16 and D < _TENSOR_PATH_D and q.shape[2] >= 256) else 0
+        pad = _head_pad(q.dtype, D, q.shape[2])
         if pad:
             q_, k_, v_ = (torch.nn.functional.pad(t, (0, pad)) for t in (q_, k_, v_))
         saved = None

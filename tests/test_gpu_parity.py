@@ -326,6 +326,42 @@ def test_first_order_full_streaming_passes(shape, keep):
         _sampled_rows_and_columns_check(q, k, v, do, o, g, dq, dk, dv, b, h, rows, cols, c, p=p, causal=False)
 
 
+@pytest.mark.parametrize("shape", [(1, 2, 128, 128), (2, 2, 1000, 128), (1, 1, 2049, 128), (1, 2, 600, 96)],
+                         ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("p", [1, 2])
+@pytest.mark.parametrize("causal", [True, False], ids=["causal", "full"])
+def test_head_size_128_dense_tensor_tiles(shape, p, causal):
+    """Head size 128 in bf16 (Llama-2-7B, BASELINE.json config 4) runs as dense tcgen05 tiles (fm_dense128.cu): forward,
+    dq and dk/dv kernels against the dense oracle -- one tile, ragged tails, several tiles per row; a head of 96
+    goes through the public op zero-padded to 128."""
+    B, H, N, D = shape
+    gen = torch.Generator().manual_seed(300 + N + D + p)
+    q, k, v, do = (torch.randn(B, H, N, D, generator=gen).to(torch.bfloat16) for _ in range(4))
+    ref = orc.dense_fwd_bwd(q.double(), k.double(), v.double(), do.double(), mask=causal, p=p)
+    if D == 128:
+        c = orc.denominator_c(D)
+        out = _run_raw(*(t.cuda() for t in (q, k, v, do)), causal, 1.0 / c, p, _lib.ALGO_AUTO)
+        names = {n for n, _ in _profile_names(lambda: _run_raw(*(t.cuda() for t in (q, k, v, do)), causal, 1.0 / c, p, _lib.ALGO_AUTO))}
+        assert {"dense128_fwd", "dense128_dq", "dense128_dkdv"} <= names, names
+    else:
+        qq, kk, vv = (t.cuda().requires_grad_(True) for t in (q, k, v))
+        o = fm.fastmax(qq, kk, vv, mask=causal, p=p)
+        o.backward(do.cuda())
+        out = (o.detach(), ref[1], qq.grad, kk.grad, vv.grad)       # (g is internal to the op)
+    for nm, x, r in zip(("o", "g", "dq", "dk", "dv"), out, ref):
+        err = orc.rel_err(x, r)
+        assert err <= 2e-2, (shape, p, causal, nm, err)
+
+
+def _profile_names(fn):
+    _lib.profile_enable(True)
+    fn()
+    torch.cuda.synchronize()
+    recs = _lib.profile_fetch()
+    _lib.profile_enable(False)
+    return recs
+
+
 def test_cuda_graph_capture_replays_the_step():
     """The C ABI is stream-ordered and free of host synchronisation: a fwd+bwd step can be captured in a
     CUDA graph and replayed on new input values."""

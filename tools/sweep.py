@@ -50,3 +50,30 @@ for dtype, ns in ((torch.bfloat16, (1024, 2048, 4096, 16384, 65536)), (torch.flo
                       f"{'moments' if pl.algo == 2 else 'exact'} | {pl.seg_len} | {ms:.2f} | {B * N / ms / 1e3:.2f} | | |")
         del q, k, v, do
         torch.cuda.empty_cache()
+
+# head size 128 (BASELINE.json config 4: Llama-2-7B, 32 heads of 128): dense tcgen05 tiles, O(N^2)
+print()
+print("| N | B | H | D | p | mask | dtype | kernels | ms/step | M tokens/s |")
+print("|---|---|---|---|---|---|---|---|---|---|")
+for N, B in ((1024, 32), (4096, 8), (16384, 1)):
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    q, k, v, do = (torch.randn(B, H, N, 128, device="cuda", generator=gen).to(torch.bfloat16) for _ in range(4))
+    inv_c = 1.0 / (8 * 128 ** 0.5)
+    for p in (1, 2):
+        for causal in (True, False):
+            def step():
+                o, g = fastmax_fwd_raw(q, k, v, causal, inv_c, p, _lib.ALGO_AUTO)
+                return fastmax_bwd_raw(q, k, v, o, g, do, causal, inv_c, p, _lib.ALGO_AUTO)
+            for _ in range(2):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 3
+            print(f"| {N} | {B} | {H} | 128 | {p} | {'causal' if causal else 'full'} | bf16 | dense128 | {ms:.2f} | {B * N / ms / 1e3:.2f} |")
+    del q, k, v, do
+    torch.cuda.empty_cache()
