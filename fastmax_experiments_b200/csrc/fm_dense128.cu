@@ -14,7 +14,8 @@
 // fm_exact.cu (reference: fastmax.py:219-322 forward, :433-691 backward), O(N^2 D) work but on the tensor pipe: every
 // operand tile is two 64-column K-major panels (TMA, 128B swizzle), scores and accumulators live in tensor memory, the
 // polynomial result goes back to tensor memory as the bf16 A operand of the second MMA.  One CTA per SM (512 tensor-
-// memory columns): 4 compute warps (thread = score row), a TMA producer warp, an MMA issuer warp.
+// memory columns): 16 compute warps (four per scheduler, so the polynomial's dependent instruction chains overlap;
+// thread = one score row x 32 columns), a TMA producer warp, an MMA issuer warp.
 #include "fm_common.cuh"
 #include "fm_sm100.cuh"
 
@@ -23,7 +24,8 @@ namespace d128 {
 using namespace sm100;
 typedef __nv_bfloat16 bf16;
 
-constexpr int THREADS = 192;
+constexpr int NCW = 16;                     // compute warps: quadrant = warp & 3, 32-column block = warp >> 2
+constexpr int THREADS = (NCW + 2) * 32;     // + TMA producer warp + MMA issuer warp
 constexpr int TILE = 32768;                 // one 128-token x 128-feature operand tile: two 16 KiB panels
 constexpr int PANEL = 16384;
 
@@ -34,24 +36,43 @@ struct Params {
   float* g;                  // (BH, N) (forward)
 };
 
-__device__ __forceinline__ uint64_t kdesc(uint32_t saddr) { return make_smem_desc_const(saddr, 16, 1024, 2); }
-__device__ __forceinline__ uint64_t mndesc(uint32_t saddr, uint32_t lbo) { return make_smem_desc_const(saddr, lbo, 1024, 2); }
+// Shared-memory descriptors of every MMA operand, built on the host for the fixed layouts below and passed in the
+// constant bank: with immediate tensor-memory addresses (the CTA owns all 512 columns: base 0) one thread then issues
+// at the tensor pipe's rate (fm_sm100.cuh).
+struct Descs {
+  unsigned long long resK[2][8];      // resident tile 0 / 1, K-major, 8 k-steps of 16 features
+  unsigned long long strK[2][2][8];   // stage x streamed tile 0 / 1, K-major
+  unsigned long long strMN[2][2][8];  // the same tiles read MN-major (tokens = K), 8 k-steps of 16 tokens
+};
 
-// S[tmem] = A . B^T with A, B K-major 128 x 128 tiles (two panels each): 8 k-steps of 16
-__device__ __forceinline__ void mma_scores(uint32_t d_tmem, uint32_t a_saddr, uint32_t b_saddr) {
+// S[tmem DT] = res[RA] . str[ST][OB]^T
+template <uint32_t DT, int RA, int ST, int OB>
+__device__ __forceinline__ void mma_scores(const Descs& D) {
   constexpr uint32_t ID = make_idesc_bf16(128, 128, false, false);
 #pragma unroll
-  for (int kk = 0; kk < 8; ++kk)
-    umma_ss(d_tmem, kdesc(a_saddr + (kk >> 2) * PANEL) + (kk & 3) * 2, kdesc(b_saddr + (kk >> 2) * PANEL) + (kk & 3) * 2, ID,
-            kk > 0);
+  for (int kk = 0; kk < 8; ++kk) umma_ss(DT, D.resK[RA][kk], D.strK[ST][OB][kk], ID, kk > 0);
 }
-// acc[tmem] += P[tmem, bf16 128 x 128] . B with B = a 128-token tile read MN-major (tokens = K), N columns (128 or 144)
-template <int N>
-__device__ __forceinline__ void mma_accum(uint32_t d_tmem, uint32_t p_tmem, uint32_t b_saddr, uint32_t acc_first) {
+// acc[tmem DT] += P[tmem PT, bf16 128 x 128] . str[ST][OB] read MN-major, N columns (128, or 144 with the ones panel)
+template <int N, uint32_t DT, uint32_t PT, int ST, int OB>
+__device__ __forceinline__ void mma_accum(const Descs& D, uint32_t acc_first) {
   constexpr uint32_t ID = make_idesc_bf16(128, N, false, true);
 #pragma unroll
-  for (int kk = 0; kk < 8; ++kk)
-    umma_ts(d_tmem, p_tmem + 8 * kk, mndesc(b_saddr, PANEL) + kk * 128, ID, (acc_first || kk > 0) ? 1 : 0);
+  for (int kk = 0; kk < 8; ++kk) umma_ts(DT, PT + 8 * kk, D.strMN[ST][OB][kk], ID, (acc_first || kk > 0) ? 1 : 0);
+}
+
+static void fill_descs(Descs& D, uint32_t res0, uint32_t res1, uint32_t st0, uint32_t st_stride, uint32_t op1_off) {
+  const uint32_t base = sm100::FM_SMEM_BASE;
+  for (int kk = 0; kk < 8; ++kk) {
+    const uint32_t kp = (kk >> 2) * PANEL;
+    D.resK[0][kk] = sm100::desc_kmajor_sw128_const(base + res0 + kp) + (kk & 3) * 2;
+    D.resK[1][kk] = sm100::desc_kmajor_sw128_const(base + res1 + kp) + (kk & 3) * 2;
+    for (int st = 0; st < 2; ++st)
+      for (int op = 0; op < 2; ++op) {
+        const uint32_t t = base + st0 + st * st_stride + op * op1_off;
+        D.strK[st][op][kk] = sm100::desc_kmajor_sw128_const(t + kp) + (kk & 3) * 2;
+        D.strMN[st][op][kk] = sm100::desc_mnmajor_sw128_const(t, PANEL) + kk * 128;
+      }
+  }
 }
 
 __device__ __forceinline__ void load_tile(uint8_t* dst, const CUtensorMap* tm, uint64_t* bar, int tok, int bh) {
@@ -72,7 +93,8 @@ constexpr int F_SMEM = F_OFF_MISC + 1024 + 1024;
 template <int P>
 __global__ void __launch_bounds__(THREADS, 1)
 fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-           const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const Params prm) {
+           const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const Params prm,
+           const __grid_constant__ Descs D) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + F_OFF_MISC);
@@ -91,7 +113,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
   const int nj = prm.causal ? it + 1 : prm.ntile;
   const uint32_t sbase = smem_u32(smem);
 
-  if (warp == 4) {
+  if (warp == NCW) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
@@ -116,9 +138,10 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  assert_bases(tmem, smem);
   constexpr uint32_t C_ACC = 256;
 
-  if (warp == 4) {
+  if (warp == NCW) {
     if (lane == 0) {
       mbar_arrive_expect_tx(q_full, TILE);
       load_tile(smem, &tmQ, q_full, it * 128, bh);
@@ -133,7 +156,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
         load_tile(st + TILE, &tmV, &v_full[s], j * 128, bh);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == NCW + 1) {
     if (lane == 0) mbar_wait(q_full, 0, 300);
     __syncwarp();
     for (int j = 0; j <= nj; ++j) {
@@ -144,7 +167,8 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
         __syncwarp();
         tc_fence_after();
         if (elect_one()) {
-          mma_scores(tmem + 128 * s, sbase, sbase + F_OFF_ST + s * F_STAGE);
+          if (s == 0) mma_scores<0, 0, 0, 0>(D);
+          else mma_scores<128, 0, 1, 0>(D);
           umma_commit(&k_free[s]);
           umma_commit(&s_ready[s]);
         }
@@ -159,7 +183,8 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
         __syncwarp();
         tc_fence_after();
         if (elect_one()) {
-          mma_accum<144>(tmem + C_ACC, tmem + 128 * sp, sbase + F_OFF_ST + sp * F_STAGE + TILE, j > 1);
+          if (sp == 0) mma_accum<144, C_ACC, 0, 0, 1>(D, j > 1);
+          else mma_accum<144, C_ACC, 128, 1, 1>(D, j > 1);
           umma_commit(&v_free[sp]);
           if (j == nj) umma_commit(acc_done);
         }
@@ -167,9 +192,10 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
       }
     }
   } else {
-    const int r = tid;
+    const int q4 = warp & 3, cb = warp >> 2;
+    const int r = 32 * q4 + lane;
     const int i_tok = it * 128 + r;
-    const uint32_t lane_addr = tmem + ((uint32_t)(32 * warp) << 16);
+    const uint32_t lane_addr = tmem + ((uint32_t)(32 * q4) << 16);
     const float a = prm.a;
     for (int j = 0; j < nj; ++j) {
       const int s = j & 1;
@@ -177,11 +203,14 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
       tc_fence_after();
       const bool diag = prm.causal && j == it;
       const bool tail = (j + 1) * 128 > prm.N;
-#pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
+      {
+        const int c0 = 32 * cb;
         uint32_t v[32], pk[16];
         tmem_ld32(lane_addr + 128 * s + c0, v);
         tmem_wait_ld();
+        // the P of columns [c0, c0+32) goes to tensor-memory columns [c0/2, c0/2+16), which another warp of this
+        // quadrant may still be reading as scores: everyone has its scores in registers first
+        named_barrier_sync(1, 32 * NCW);
 #pragma unroll
         for (int c = 0; c < 32; c += 2) {
           float x0 = poly<P>(a * __uint_as_float(v[c])), x1 = poly<P>(a * __uint_as_float(v[c + 1]));
@@ -190,12 +219,11 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
           if (tail) x0 = j * 128 + col < prm.N ? x0 : 0.f, x1 = j * 128 + col + 1 < prm.N ? x1 : 0.f;
           pk[c >> 1] = pack_bf16x2(x0, x1);
         }
-        // the P of columns [c0, c0+32) goes to tensor-memory columns [c0/2, c0/2+16): behind the reads of this thread
         tmem_st16(lane_addr + 128 * s + (c0 >> 1), pk);
       }
       tmem_wait_st();
       tc_fence_before();
-      named_barrier_sync(1, 128);
+      named_barrier_sync(1, 32 * NCW);
       if (tid == 0) mbar_arrive(&p_ready[s]);
     }
     // epilogue: o = acc / den, g = den; rows leave through the Q tile's buffer (all score MMAs are complete)
@@ -206,9 +234,9 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
     tmem_wait_ld();
     const float den = __uint_as_float(w[0]);
     const float rden = 1.f / den;
-    if (i_tok < prm.N) prm.g[(size_t)bh * prm.N + i_tok] = den;
-#pragma unroll 1
-    for (int hh = 0; hh < 4; ++hh) {
+    if (cb == 0 && i_tok < prm.N) prm.g[(size_t)bh * prm.N + i_tok] = den;
+    {
+      const int hh = cb;
       uint32_t v[32];
       tmem_ld32(lane_addr + C_ACC + 32 * hh, v);
       tmem_wait_ld();
@@ -224,7 +252,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
       }
     }
     fence_proxy_async();
-    named_barrier_sync(1, 128);
+    named_barrier_sync(1, 32 * NCW);
     if (tid == 0) {
       tma_store_3d(&tmO, smem, 0, it * 128, bh);
       tma_store_3d(&tmO, smem + PANEL, 64, it * 128, bh);
@@ -234,7 +262,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, 512);
+  if (warp == NCW) tmem_dealloc(tmem, 512);
 }
 
 // ------------------------------------------------------------------------------------------------ backward: prep
@@ -269,7 +297,8 @@ template <int P>
 __global__ void __launch_bounds__(THREADS, 1)
 dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmU,
           const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
-          const __grid_constant__ CUtensorMap tmO, const Params prm) {
+          const __grid_constant__ CUtensorMap tmO, const Params prm,
+           const __grid_constant__ Descs D) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B_OFF_MISC);
@@ -286,7 +315,7 @@ dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
   const int nj = prm.causal ? it + 1 : prm.ntile;
   const uint32_t sbase = smem_u32(smem);
 
-  if (warp == 4) {
+  if (warp == NCW) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
@@ -299,9 +328,10 @@ dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  assert_bases(tmem, smem);
   constexpr uint32_t C_D = 128, C_ACC = 256;
 
-  if (warp == 4) {
+  if (warp == NCW) {
     if (lane == 0) {
       mbar_arrive_expect_tx(res_full, 2 * TILE);
       load_tile(smem, &tmQ, res_full, it * 128, bh);
@@ -315,18 +345,17 @@ dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
         load_tile(st + TILE, &tmV, &st_full[s], j * 128, bh);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == NCW + 1) {
     if (lane == 0) mbar_wait(res_full, 0, 300);
     __syncwarp();
     for (int j = 0; j < nj; ++j) {
       const int s = j & 1;
-      const uint32_t st = sbase + B_OFF_ST + s * B_STAGE;
       if (lane == 0) mbar_wait(&st_full[s], (j >> 1) & 1, 400 + j);
       __syncwarp();
       tc_fence_after();
       if (elect_one()) {
-        mma_scores(tmem, sbase, st);                      // S = Q K^T
-        mma_scores(tmem + C_D, sbase + TILE, st + TILE);  // D = U V^T
+        if (s == 0) mma_scores<0, 0, 0, 0>(D), mma_scores<C_D, 1, 0, 1>(D);     // S = Q K^T, D = U V^T
+        else mma_scores<0, 0, 1, 0>(D), mma_scores<C_D, 1, 1, 1>(D);
         umma_commit(sd_ready);
       }
       __syncwarp();
@@ -334,28 +363,31 @@ dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
       __syncwarp();
       tc_fence_after();
       if (elect_one()) {
-        mma_accum<128>(tmem + C_ACC, tmem, st, j > 0);    // dQ += E K
+        if (s == 0) mma_accum<128, C_ACC, 0, 0, 0>(D, j > 0);                    // dQ += E K
+        else mma_accum<128, C_ACC, 0, 1, 0>(D, j > 0);
         umma_commit(&st_free[s]);
         if (j == nj - 1) umma_commit(acc_done);
       }
       __syncwarp();
     }
   } else {
-    const int r = tid;
+    const int q4 = warp & 3, cb = warp >> 2;
+    const int r = 32 * q4 + lane;
     const int i_tok = it * 128 + r;
-    const uint32_t lane_addr = tmem + ((uint32_t)(32 * warp) << 16);
+    const uint32_t lane_addr = tmem + ((uint32_t)(32 * q4) << 16);
     const float a = prm.a;
     const float dl = i_tok < prm.N ? prm.dlt[(size_t)bh * prm.Npad + i_tok] : 0.f;
     for (int j = 0; j < nj; ++j) {
       mbar_wait_warp(sd_ready, j & 1);
       tc_fence_after();
       const bool diag = prm.causal && j == it;
-#pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
+      {
+        const int c0 = 32 * cb;
         uint32_t sv[32], dv[32], pk[16];
         tmem_ld32(lane_addr + c0, sv);
         tmem_ld32(lane_addr + C_D + c0, dv);
         tmem_wait_ld();
+        named_barrier_sync(1, 32 * NCW);       // (E overwrites score columns other warps of the quadrant read)
 #pragma unroll
         for (int c = 0; c < 32; c += 2) {
           float e0 = __uint_as_float(dv[c]) - dl, e1 = __uint_as_float(dv[c + 1]) - dl;
@@ -368,13 +400,13 @@ dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
       }
       tmem_wait_st();
       tc_fence_before();
-      named_barrier_sync(1, 128);
+      named_barrier_sync(1, 32 * NCW);
       if (tid == 0) mbar_arrive(p_ready);
     }
     mbar_wait_warp(acc_done, 0);
     tc_fence_after();
-#pragma unroll 1
-    for (int hh = 0; hh < 4; ++hh) {
+    {
+      const int hh = cb;
       uint32_t v[32];
       tmem_ld32(lane_addr + C_ACC + 32 * hh, v);
       tmem_wait_ld();
@@ -390,7 +422,7 @@ dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
       }
     }
     fence_proxy_async();
-    named_barrier_sync(1, 128);
+    named_barrier_sync(1, 32 * NCW);
     if (tid == 0) {
       tma_store_3d(&tmO, smem, 0, it * 128, bh);
       tma_store_3d(&tmO, smem + PANEL, 64, it * 128, bh);
@@ -400,7 +432,7 @@ dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, 512);
+  if (warp == NCW) tmem_dealloc(tmem, 512);
 }
 
 // ------------------------------------------------------------------------------------------------ backward: dk, dv
@@ -409,7 +441,8 @@ template <int P>
 __global__ void __launch_bounds__(THREADS, 1)
 dkdv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
             const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmU,
-            const __grid_constant__ CUtensorMap tmDK, const __grid_constant__ CUtensorMap tmDV, const Params prm) {
+            const __grid_constant__ CUtensorMap tmDK, const __grid_constant__ CUtensorMap tmDV, const Params prm,
+            const __grid_constant__ Descs D) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B_OFF_MISC);
@@ -428,7 +461,7 @@ dkdv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUt
   const int ni = prm.ntile - i0;
   const uint32_t sbase = smem_u32(smem);
 
-  if (warp == 4) {
+  if (warp == NCW) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
@@ -441,9 +474,10 @@ dkdv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUt
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  assert_bases(tmem, smem);
   constexpr uint32_t C_D = 128, C_DV = 256, C_DK = 384;
 
-  if (warp == 4) {
+  if (warp == NCW) {
     if (lane == 0) {
       mbar_arrive_expect_tx(res_full, 2 * TILE);
       load_tile(smem, &tmK, res_full, jt * 128, bh);
@@ -457,18 +491,17 @@ dkdv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUt
         load_tile(st + TILE, &tmU, &st_full[s], (i0 + n) * 128, bh);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == NCW + 1) {
     if (lane == 0) mbar_wait(res_full, 0, 300);
     __syncwarp();
     for (int n = 0; n < ni; ++n) {
       const int s = n & 1;
-      const uint32_t st = sbase + B_OFF_ST + s * B_STAGE;
       if (lane == 0) mbar_wait(&st_full[s], (n >> 1) & 1, 400 + n);
       __syncwarp();
       tc_fence_after();
       if (elect_one()) {
-        mma_scores(tmem, sbase, st);                      // S' = K Q^T
-        mma_scores(tmem + C_D, sbase + TILE, st + TILE);  // D' = V U^T
+        if (s == 0) mma_scores<0, 0, 0, 0>(D), mma_scores<C_D, 1, 0, 1>(D);     // S' = K Q^T, D' = V U^T
+        else mma_scores<0, 0, 1, 0>(D), mma_scores<C_D, 1, 1, 1>(D);
         umma_commit(sd_ready);
       }
       __syncwarp();
@@ -476,33 +509,34 @@ dkdv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUt
       __syncwarp();
       tc_fence_after();
       if (elect_one()) {
-        mma_accum<128>(tmem + C_DV, tmem, st + TILE, n > 0);        // dV += P' U
-        mma_accum<128>(tmem + C_DK, tmem + C_D, st, n > 0);         // dK += E' Q
+        if (s == 0) mma_accum<128, C_DV, 0, 0, 1>(D, n > 0), mma_accum<128, C_DK, C_D, 0, 0>(D, n > 0);   // dV += P' U, dK += E' Q
+        else mma_accum<128, C_DV, 0, 1, 1>(D, n > 0), mma_accum<128, C_DK, C_D, 1, 0>(D, n > 0);
         umma_commit(&st_free[s]);
         if (n == ni - 1) umma_commit(acc_done);
       }
       __syncwarp();
     }
   } else {
-    const int r = tid;
-    const uint32_t lane_addr = tmem + ((uint32_t)(32 * warp) << 16);
+    const int q4 = warp & 3, cb = warp >> 2;
+    const int r = 32 * q4 + lane;
+    const uint32_t lane_addr = tmem + ((uint32_t)(32 * q4) << 16);
     const float a = prm.a;
     for (int n = 0; n < ni; ++n) {
       const int i = i0 + n, s = n & 1;
       const int q_tok = i * 128 + r;
       // (the buffer of two iterations ago was last read before that iteration's P barrier)
-      dcol[128 * s + r] = q_tok < prm.N ? prm.dlt[(size_t)bh * prm.Npad + q_tok] : 0.f;
-      named_barrier_sync(1, 128);
+      if (cb == 0) dcol[128 * s + r] = q_tok < prm.N ? prm.dlt[(size_t)bh * prm.Npad + q_tok] : 0.f;
       mbar_wait_warp(sd_ready, n & 1);
       tc_fence_after();
       const bool diag = prm.causal && i == jt;
       const float* dc = dcol + 128 * s;
-#pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
+      {
+        const int c0 = 32 * cb;
         uint32_t sv[32], dv[32], pp[16], pe[16];
         tmem_ld32(lane_addr + c0, sv);
         tmem_ld32(lane_addr + C_D + c0, dv);
         tmem_wait_ld();
+        named_barrier_sync(1, 32 * NCW);       // scores in registers everywhere, dlt of the q tokens visible
 #pragma unroll
         for (int c = 0; c < 32; c += 2) {
           const int col = c0 + c;
@@ -522,7 +556,7 @@ dkdv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUt
       }
       tmem_wait_st();
       tc_fence_before();
-      named_barrier_sync(1, 128);
+      named_barrier_sync(1, 32 * NCW);
       if (tid == 0) mbar_arrive(p_ready);
     }
     mbar_wait_warp(acc_done, 0);
@@ -530,8 +564,8 @@ dkdv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUt
 #pragma unroll 1
     for (int which = 0; which < 2; ++which) {             // dV into the K tile's buffer, dK into the V tile's
       const float sc = which == 0 ? 1.f : a;
-#pragma unroll 1
-      for (int hh = 0; hh < 4; ++hh) {
+      {
+        const int hh = cb;
         uint32_t v[32];
         tmem_ld32(lane_addr + (which == 0 ? C_DV : C_DK) + 32 * hh, v);
         tmem_wait_ld();
@@ -560,7 +594,7 @@ dkdv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUt
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, 512);
+  if (warp == NCW) tmem_dealloc(tmem, 512);
 }
 
 }  // namespace d128
@@ -585,12 +619,14 @@ int dense128_fwd(const Problem& pb, const void* q, const void* k, const void* v,
   Params P{};
   P.N = pb.N, P.ntile = (pb.N + 127) / 128, P.p = pb.p, P.causal = pb.causal, P.a = pb.inv_c, P.g = g;
   dim3 grid(P.ntile, BH);
+  Descs D{};
+  fill_descs(D, 0, 0, F_OFF_ST, F_STAGE, TILE);          // resident Q; stages [K | V | ones]
   if (pb.p == 2) {
     FM_CUDA(cudaFuncSetAttribute(fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM));
-    FM_LAUNCH("dense128_fwd", pb.stream, fwd_kernel<2><<<grid, THREADS, F_SMEM, pb.stream>>>(tQ, tK, tV, tO, P));
+    FM_LAUNCH("dense128_fwd", pb.stream, fwd_kernel<2><<<grid, THREADS, F_SMEM, pb.stream>>>(tQ, tK, tV, tO, P, D));
   } else {
     FM_CUDA(cudaFuncSetAttribute(fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM));
-    FM_LAUNCH("dense128_fwd", pb.stream, fwd_kernel<1><<<grid, THREADS, F_SMEM, pb.stream>>>(tQ, tK, tV, tO, P));
+    FM_LAUNCH("dense128_fwd", pb.stream, fwd_kernel<1><<<grid, THREADS, F_SMEM, pb.stream>>>(tQ, tK, tV, tO, P, D));
   }
   return FASTMAX_OK;
 }
@@ -618,16 +654,18 @@ int dense128_bwd(const Problem& pb, const void* q, const void* k, const void* v,
   Params P{};
   P.N = pb.N, P.Npad = Npad, P.ntile = (pb.N + 127) / 128, P.p = pb.p, P.causal = pb.causal, P.a = pb.inv_c, P.dlt = dlt;
   dim3 grid(P.ntile, BH);
+  Descs D{};
+  fill_descs(D, 0, TILE, B_OFF_ST, B_STAGE, TILE);       // resident [Q | U] resp. [K | V]; stages [K | V] resp. [Q | U]
   if (pb.p == 2) {
     FM_CUDA(cudaFuncSetAttribute(dq_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
     FM_CUDA(cudaFuncSetAttribute(dkdv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
-    FM_LAUNCH("dense128_dq", pb.stream, dq_kernel<2><<<grid, THREADS, B_SMEM, pb.stream>>>(tQ, tU, tK, tV, tDQ, P));
-    FM_LAUNCH("dense128_dkdv", pb.stream, dkdv_kernel<2><<<grid, THREADS, B_SMEM, pb.stream>>>(tK, tV, tQ, tU, tDK, tDV, P));
+    FM_LAUNCH("dense128_dq", pb.stream, dq_kernel<2><<<grid, THREADS, B_SMEM, pb.stream>>>(tQ, tU, tK, tV, tDQ, P, D));
+    FM_LAUNCH("dense128_dkdv", pb.stream, dkdv_kernel<2><<<grid, THREADS, B_SMEM, pb.stream>>>(tK, tV, tQ, tU, tDK, tDV, P, D));
   } else {
     FM_CUDA(cudaFuncSetAttribute(dq_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
     FM_CUDA(cudaFuncSetAttribute(dkdv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
-    FM_LAUNCH("dense128_dq", pb.stream, dq_kernel<1><<<grid, THREADS, B_SMEM, pb.stream>>>(tQ, tU, tK, tV, tDQ, P));
-    FM_LAUNCH("dense128_dkdv", pb.stream, dkdv_kernel<1><<<grid, THREADS, B_SMEM, pb.stream>>>(tK, tV, tQ, tU, tDK, tDV, P));
+    FM_LAUNCH("dense128_dq", pb.stream, dq_kernel<1><<<grid, THREADS, B_SMEM, pb.stream>>>(tQ, tU, tK, tV, tDQ, P, D));
+    FM_LAUNCH("dense128_dkdv", pb.stream, dkdv_kernel<1><<<grid, THREADS, B_SMEM, pb.stream>>>(tK, tV, tQ, tU, tDK, tDV, P, D));
   }
   return FASTMAX_OK;
 }
