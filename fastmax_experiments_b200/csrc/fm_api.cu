@@ -176,6 +176,11 @@ int fastmax_plan_make(fastmax_plan* plan, int B, int H, int N, int D, int p, int
     // head size 128 in bf16: dense tcgen05 tiles (fm_dense128.cu); its backward needs u and dlt
     Problem pb{B, H, N, D, p, causal ? 1 : 0, dtype, 1.f, nullptr};
     if (fm::dense128_usable(pb) && tensor_path_usable()) plan->bwd_workspace_bytes = fm::dense128_bwd_workspace_bytes(B, H, N);
+    // fp32, head size <= 64: the same tiles on [hi | lo] bf16 pairs (AUTO only: EXACT keeps the fp32 CUDA-core kernels)
+    if (algo == FASTMAX_ALGO_AUTO && fm::dense_split_usable(pb) && tensor_path_usable()) {
+      plan->fwd_workspace_bytes = fm::dense_split_fwd_workspace_bytes(B, H, N);
+      plan->bwd_workspace_bytes = fm::dense_split_bwd_workspace_bytes(B, H, N);
+    }
   }
   return FASTMAX_OK;
 }
@@ -209,6 +214,10 @@ int fastmax_fwd(const void* q, const void* k, const void* v, void* o, float* g, 
     return fm::moments_fwd(pb, q, k, v, o, g, workspace);
   }
   if (fm::dense128_usable(pb) && tensor_path_usable()) return fm::dense128_fwd(pb, q, k, v, o, g);
+  if (algo == FASTMAX_ALGO_AUTO && fm::dense_split_usable(pb) && tensor_path_usable()) {
+    if (((uintptr_t)workspace & 255) != 0) return FASTMAX_ERR_WORKSPACE;
+    return fm::dense_split_fwd(pb, q, k, v, o, g, workspace);
+  }
   return fm::exact_fwd(pb, q, k, v, o, g);
 }
 
@@ -231,6 +240,10 @@ int fastmax_bwd(const void* q, const void* k, const void* v, const void* o, cons
   if (fm::dense128_usable(pb) && tensor_path_usable()) {
     if (((uintptr_t)workspace & 255) != 0) return FASTMAX_ERR_WORKSPACE;
     return fm::dense128_bwd(pb, q, k, v, o, g, d_o, dq, dk, dv, workspace);
+  }
+  if (algo == FASTMAX_ALGO_AUTO && fm::dense_split_usable(pb) && tensor_path_usable()) {
+    if (((uintptr_t)workspace & 255) != 0) return FASTMAX_ERR_WORKSPACE;
+    return fm::dense_split_bwd(pb, q, k, v, o, g, d_o, dq, dk, dv, workspace);
   }
   return fm::exact_bwd(pb, q, k, v, o, g, d_o, dq, dk, dv);
 }

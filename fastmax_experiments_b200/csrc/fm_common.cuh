@@ -117,6 +117,13 @@ int p1full_bwd(const Problem& pb, int Npad, const void* q, const void* k, const 
 bool dense128_usable(const Problem& pb);
 int dense128_fwd(const Problem& pb, const void* q, const void* k, const void* v, void* o, float* g);
 size_t dense128_bwd_workspace_bytes(int B, int H, int N);     // u (bf16) and dlt (fp32)
+// fp32 inputs of head size <= 64 through the same kernels as [hi | lo] bf16 pairs (three-term products)
+bool dense_split_usable(const Problem& pb);
+size_t dense_split_fwd_workspace_bytes(int B, int H, int N);
+size_t dense_split_bwd_workspace_bytes(int B, int H, int N);
+int dense_split_fwd(const Problem& pb, const void* q, const void* k, const void* v, void* o, float* g, void* ws);
+int dense_split_bwd(const Problem& pb, const void* q, const void* k, const void* v, const void* o, const float* g,
+                    const void* d_o, void* dq, void* dk, void* dv, void* ws);
 int dense128_bwd(const Problem& pb, const void* q, const void* k, const void* v, const void* o, const float* g,
                  const void* d_o, void* dq, void* dk, void* dv, void* ws);
 unsigned sm100_smem_base();     // FM_SMEM_BASE of fm_sm100.cuh (defined in fm_tmap.cu)

@@ -16,6 +16,12 @@
 // polynomial result goes back to tensor memory as the bf16 A operand of the second MMA.  One CTA per SM (512 tensor-
 // memory columns): 16 compute warps (four per scheduler, so the polynomial's dependent instruction chains overlap;
 // thread = one score row x 32 columns), a TMA producer warp, an MMA issuer warp.
+//
+// SPLIT = true runs fp32 problems of head size <= 64 through the same kernels at fp32-level accuracy: every fp32 operand x
+// is stored as the bf16 pair [hi | lo] (hi = bf16(x), lo = bf16(x - hi): 16 mantissa bits) -- exactly the two-panel tile of
+// a 128-wide head -- and each product A.B is taken as hi.hi + hi.lo + lo.hi on the tensor pipe with fp32 accumulation
+// (three MMA groups instead of two).  The polynomial results P / E are split the same way when they go back to tensor
+// memory, the normaliser is summed in fp32 on CUDA cores, outputs are written as fp32.
 #include "fm_common.cuh"
 #include "fm_sm100.cuh"
 
@@ -34,6 +40,8 @@ struct Params {
   float a;
   const float* dlt;          // (BH, Npad) fp32
   float* g;                  // (BH, N) (forward)
+  float *out0, *out1;        // SPLIT: fp32 outputs (BH, N, Dout): o | dq | dv, dk
+  int Dout;
 };
 
 // Shared-memory descriptors of every MMA operand, built on the host for the fixed layouts below and passed in the
@@ -45,19 +53,59 @@ struct Descs {
   unsigned long long strMN[2][2][8];  // the same tiles read MN-major (tokens = K), 8 k-steps of 16 tokens
 };
 
-// S[tmem DT] = res[RA] . str[ST][OB]^T
-template <uint32_t DT, int RA, int ST, int OB>
+// S[tmem DT] = res[RA] . str[ST][OB]^T.  SPLIT: panels are [hi | lo] of a 64-wide operand: hi.hi + hi.lo + lo.hi
+template <bool SPLIT, uint32_t DT, int RA, int ST, int OB>
 __device__ __forceinline__ void mma_scores(const Descs& D) {
   constexpr uint32_t ID = make_idesc_bf16(128, 128, false, false);
+  if constexpr (!SPLIT) {
 #pragma unroll
-  for (int kk = 0; kk < 8; ++kk) umma_ss(DT, D.resK[RA][kk], D.strK[ST][OB][kk], ID, kk > 0);
+    for (int kk = 0; kk < 8; ++kk) umma_ss(DT, D.resK[RA][kk], D.strK[ST][OB][kk], ID, kk > 0);
+  } else {
+#pragma unroll
+    for (int t = 0; t < 12; ++t) {
+      const int ka = (t < 8 ? 0 : 4) + (t & 3), kb = (t >= 4 && t < 8 ? 4 : 0) + (t & 3);
+      umma_ss(DT, D.resK[RA][ka], D.strK[ST][OB][kb], ID, t > 0);
+    }
+  }
 }
-// acc[tmem DT] += P[tmem PT, bf16 128 x 128] . str[ST][OB] read MN-major, N columns (128, or 144 with the ones panel)
-template <int N, uint32_t DT, uint32_t PT, int ST, int OB>
+// acc[tmem DT] += P[tmem PT, bf16 128 x 128] . str[ST][OB] read MN-major, N columns (128, or 144 with the ones panel).
+// SPLIT: acc[:, 0:128) += P_hi . [B_hi | B_lo], acc[:, 0:64) += P_lo . B_hi (P_lo in tensor-memory columns PT + 64 ...)
+template <bool SPLIT, int N, uint32_t DT, uint32_t PT, int ST, int OB>
 __device__ __forceinline__ void mma_accum(const Descs& D, uint32_t acc_first) {
-  constexpr uint32_t ID = make_idesc_bf16(128, N, false, true);
+  constexpr uint32_t ID = make_idesc_bf16(128, SPLIT ? 128 : N, false, true);
 #pragma unroll
   for (int kk = 0; kk < 8; ++kk) umma_ts(DT, PT + 8 * kk, D.strMN[ST][OB][kk], ID, (acc_first || kk > 0) ? 1 : 0);
+  if constexpr (SPLIT) {
+    constexpr uint32_t ID64 = make_idesc_bf16(128, 64, false, true);
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) umma_ts(DT, PT + 64 + 8 * kk, D.strMN[ST][OB][kk], ID64, 1);
+  }
+}
+
+// x -> bf16 pair (hi, lo)
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+  hi = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+  lo = pack_bf16x2(x0 - __bfloat162float(h0), x1 - __bfloat162float(h1));
+}
+
+// fp32 rows of a SPLIT epilogue: columns [32 cb2, +32) of (accA + accB) * scale -> out[(bh N + tok) Dout + ...]
+__device__ __forceinline__ void store_rows_f32(float* out, size_t row, int Dout, int cb2, const uint32_t* va,
+                                               const uint32_t* vb, float scale) {
+  float* dst = out + row * Dout + 32 * cb2;
+  if (Dout == 64) {
+#pragma unroll
+    for (int c = 0; c < 32; c += 4)
+      *reinterpret_cast<float4*>(dst + c) =
+          make_float4((__uint_as_float(va[c]) + __uint_as_float(vb[c])) * scale,
+                      (__uint_as_float(va[c + 1]) + __uint_as_float(vb[c + 1])) * scale,
+                      (__uint_as_float(va[c + 2]) + __uint_as_float(vb[c + 2])) * scale,
+                      (__uint_as_float(va[c + 3]) + __uint_as_float(vb[c + 3])) * scale);
+  } else {
+#pragma unroll
+    for (int c = 0; c < 32; ++c)
+      if (32 * cb2 + c < Dout) dst[c] = (__uint_as_float(va[c]) + __uint_as_float(vb[c])) * scale;
+  }
 }
 
 static void fill_descs(Descs& D, uint32_t res0, uint32_t res1, uint32_t st0, uint32_t st_stride, uint32_t op1_off) {
@@ -88,9 +136,9 @@ __device__ __forceinline__ float poly(float x) { return P == 2 ? fmaf(fmaf(0.5f,
 constexpr int F_STAGE = 2 * TILE + PANEL;
 constexpr int F_OFF_ST = TILE;
 constexpr int F_OFF_MISC = F_OFF_ST + 2 * F_STAGE;
-constexpr int F_SMEM = F_OFF_MISC + 1024 + 1024;
+constexpr int F_SMEM = F_OFF_MISC + 4096 + 1024;
 
-template <int P>
+template <int P, bool SPLIT>
 __global__ void __launch_bounds__(THREADS, 1)
 fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
            const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const Params prm,
@@ -107,6 +155,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
   uint64_t* p_ready = bars + 11;   // [2] bf16 P written back
   uint64_t* acc_done = bars + 13;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  float* rs_sm = reinterpret_cast<float*>(smem + F_OFF_MISC + 128);   // [4][128] row sums per column block (SPLIT)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int bh = blockIdx.y;
   const int it = prm.ntile - 1 - blockIdx.x;            // long rows first
@@ -167,8 +216,8 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
         __syncwarp();
         tc_fence_after();
         if (elect_one()) {
-          if (s == 0) mma_scores<0, 0, 0, 0>(D);
-          else mma_scores<128, 0, 1, 0>(D);
+          if (s == 0) mma_scores<SPLIT, 0, 0, 0, 0>(D);
+          else mma_scores<SPLIT, 128, 0, 1, 0>(D);
           umma_commit(&k_free[s]);
           umma_commit(&s_ready[s]);
         }
@@ -183,8 +232,8 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
         __syncwarp();
         tc_fence_after();
         if (elect_one()) {
-          if (sp == 0) mma_accum<144, C_ACC, 0, 0, 1>(D, j > 1);
-          else mma_accum<144, C_ACC, 128, 1, 1>(D, j > 1);
+          if (sp == 0) mma_accum<SPLIT, 144, C_ACC, 0, 0, 1>(D, j > 1);
+          else mma_accum<SPLIT, 144, C_ACC, 128, 1, 1>(D, j > 1);
           umma_commit(&v_free[sp]);
           if (j == nj) umma_commit(acc_done);
         }
@@ -197,6 +246,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
     const int i_tok = it * 128 + r;
     const uint32_t lane_addr = tmem + ((uint32_t)(32 * q4) << 16);
     const float a = prm.a;
+    float rsum = 0.f;
     for (int j = 0; j < nj; ++j) {
       const int s = j & 1;
       mbar_wait_warp(&s_ready[s], (j >> 1) & 1);
@@ -205,7 +255,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
       const bool tail = (j + 1) * 128 > prm.N;
       {
         const int c0 = 32 * cb;
-        uint32_t v[32], pk[16];
+        uint32_t v[32], pk[16], pl[16];
         tmem_ld32(lane_addr + 128 * s + c0, v);
         tmem_wait_ld();
         // the P of columns [c0, c0+32) goes to tensor-memory columns [c0/2, c0/2+16), which another warp of this
@@ -217,9 +267,15 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
           const int col = c0 + c;
           if (diag) x0 = col <= r ? x0 : 0.f, x1 = col + 1 <= r ? x1 : 0.f;
           if (tail) x0 = j * 128 + col < prm.N ? x0 : 0.f, x1 = j * 128 + col + 1 < prm.N ? x1 : 0.f;
-          pk[c >> 1] = pack_bf16x2(x0, x1);
+          if constexpr (SPLIT) {
+            rsum += x0 + x1;
+            split2(x0, x1, pk[c >> 1], pl[c >> 1]);
+          } else {
+            pk[c >> 1] = pack_bf16x2(x0, x1);
+          }
         }
         tmem_st16(lane_addr + 128 * s + (c0 >> 1), pk);
+        if constexpr (SPLIT) tmem_st16(lane_addr + 128 * s + 64 + (c0 >> 1), pl);
       }
       tmem_wait_st();
       tc_fence_before();
@@ -229,13 +285,28 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
     // epilogue: o = acc / den, g = den; rows leave through the Q tile's buffer (all score MMAs are complete)
     mbar_wait_warp(acc_done, 0);
     tc_fence_after();
-    uint32_t w[8];
-    tmem_ld8(lane_addr + C_ACC + 128, w);
-    tmem_wait_ld();
-    const float den = __uint_as_float(w[0]);
+    float den;
+    if constexpr (SPLIT) {
+      rs_sm[128 * cb + r] = rsum;
+      named_barrier_sync(1, 32 * NCW);
+      den = rs_sm[r] + rs_sm[128 + r] + rs_sm[256 + r] + rs_sm[384 + r];
+    } else {
+      uint32_t w[8];
+      tmem_ld8(lane_addr + C_ACC + 128, w);
+      tmem_wait_ld();
+      den = __uint_as_float(w[0]);
+    }
     const float rden = 1.f / den;
     if (cb == 0 && i_tok < prm.N) prm.g[(size_t)bh * prm.N + i_tok] = den;
-    {
+    if constexpr (SPLIT) {
+      if (cb < 2) {
+        uint32_t va[32], vb[32];
+        tmem_ld32(lane_addr + C_ACC + 32 * cb, va);
+        tmem_ld32(lane_addr + C_ACC + 64 + 32 * cb, vb);
+        tmem_wait_ld();
+        if (i_tok < prm.N) store_rows_f32(prm.out0, (size_t)bh * prm.N + i_tok, prm.Dout, cb, va, vb, rden);
+      }
+    } else {
       const int hh = cb;
       uint32_t v[32];
       tmem_ld32(lane_addr + C_ACC + 32 * hh, v);
@@ -253,7 +324,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
     }
     fence_proxy_async();
     named_barrier_sync(1, 32 * NCW);
-    if (tid == 0) {
+    if (!SPLIT && tid == 0) {
       tma_store_3d(&tmO, smem, 0, it * 128, bh);
       tma_store_3d(&tmO, smem + PANEL, 64, it * 128, bh);
       bulk_commit_group();
@@ -263,6 +334,35 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
   tc_fence_before();
   __syncthreads();
   if (warp == NCW) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------ fp32 -> [hi | lo]
+// (rows, D <= 64) fp32 -> (rows, 128) bf16: columns [0, 64) = hi, [64, 128) = lo, zero beyond D; one warp per row
+__global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ x, bf16* __restrict__ out, size_t rows,
+                                                    int D, const float* __restrict__ g) {
+  const size_t row = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float rg = g ? 1.f / __ldg(g + row) : 1.f;
+  const float x0 = 2 * lane < D ? __ldg(x + row * D + 2 * lane) * rg : 0.f;
+  const float x1 = 2 * lane + 1 < D ? __ldg(x + row * D + 2 * lane + 1) * rg : 0.f;
+  uint32_t hi, lo;
+  split2(x0, x1, hi, lo);
+  reinterpret_cast<uint32_t*>(out + row * 128)[lane] = hi;
+  reinterpret_cast<uint32_t*>(out + row * 128 + 64)[lane] = lo;
+}
+// dlt = (do . o) / g for fp32 rows
+__global__ void __launch_bounds__(256) dlt_f32_kernel(const float* __restrict__ o, const float* __restrict__ d_o,
+                                                      const float* __restrict__ g, float* __restrict__ dlt, size_t rows,
+                                                      int D, int N, int Npad) {
+  const size_t row = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float dot = 0.f;
+  for (int c = lane; c < D; c += 32) dot += __ldg(o + row * D + c) * __ldg(d_o + row * D + c);
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, m);
+  if (lane == 0) dlt[(row / N) * Npad + row % N] = dot / __ldg(g + row);
 }
 
 // ------------------------------------------------------------------------------------------------ backward: prep
@@ -293,7 +393,7 @@ constexpr int B_STAGE = 2 * TILE;
 constexpr int B_OFF_MISC = B_OFF_ST + 2 * B_STAGE;
 constexpr int B_SMEM = B_OFF_MISC + 2048 + 1024;
 
-template <int P>
+template <int P, bool SPLIT>
 __global__ void __launch_bounds__(THREADS, 1)
 dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmU,
           const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
@@ -354,8 +454,8 @@ dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
       __syncwarp();
       tc_fence_after();
       if (elect_one()) {
-        if (s == 0) mma_scores<0, 0, 0, 0>(D), mma_scores<C_D, 1, 0, 1>(D);     // S = Q K^T, D = U V^T
-        else mma_scores<0, 0, 1, 0>(D), mma_scores<C_D, 1, 1, 1>(D);
+        if (s == 0) mma_scores<SPLIT, 0, 0, 0, 0>(D), mma_scores<SPLIT, C_D, 1, 0, 1>(D);     // S = Q K^T, D = U V^T
+        else mma_scores<SPLIT, 0, 0, 1, 0>(D), mma_scores<SPLIT, C_D, 1, 1, 1>(D);
         umma_commit(sd_ready);
       }
       __syncwarp();
@@ -363,8 +463,8 @@ dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
       __syncwarp();
       tc_fence_after();
       if (elect_one()) {
-        if (s == 0) mma_accum<128, C_ACC, 0, 0, 0>(D, j > 0);                    // dQ += E K
-        else mma_accum<128, C_ACC, 0, 1, 0>(D, j > 0);
+        if (s == 0) mma_accum<SPLIT, 128, C_ACC, 0, 0, 0>(D, j > 0);             // dQ += E K
+        else mma_accum<SPLIT, 128, C_ACC, 0, 1, 0>(D, j > 0);
         umma_commit(&st_free[s]);
         if (j == nj - 1) umma_commit(acc_done);
       }
@@ -383,7 +483,7 @@ dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
       const bool diag = prm.causal && j == it;
       {
         const int c0 = 32 * cb;
-        uint32_t sv[32], dv[32], pk[16];
+        uint32_t sv[32], dv[32], pk[16], pl[SPLIT ? 16 : 1];
         tmem_ld32(lane_addr + c0, sv);
         tmem_ld32(lane_addr + C_D + c0, dv);
         tmem_wait_ld();
@@ -394,9 +494,11 @@ dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
           if (P == 2) e0 *= fmaf(a, __uint_as_float(sv[c]), 1.f), e1 *= fmaf(a, __uint_as_float(sv[c + 1]), 1.f);
           const int col = c0 + c;
           if (diag) e0 = col <= r ? e0 : 0.f, e1 = col + 1 <= r ? e1 : 0.f;
-          pk[c >> 1] = pack_bf16x2(e0, e1);
+          if constexpr (SPLIT) split2(e0, e1, pk[c >> 1], pl[c >> 1]);
+          else pk[c >> 1] = pack_bf16x2(e0, e1);
         }
         tmem_st16(lane_addr + (c0 >> 1), pk);
+        if constexpr (SPLIT) tmem_st16(lane_addr + 64 + (c0 >> 1), pl);
       }
       tmem_wait_st();
       tc_fence_before();
@@ -405,7 +507,15 @@ dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
     }
     mbar_wait_warp(acc_done, 0);
     tc_fence_after();
-    {
+    if constexpr (SPLIT) {
+      if (cb < 2) {
+        uint32_t va[32], vb[32];
+        tmem_ld32(lane_addr + C_ACC + 32 * cb, va);
+        tmem_ld32(lane_addr + C_ACC + 64 + 32 * cb, vb);
+        tmem_wait_ld();
+        if (i_tok < prm.N) store_rows_f32(prm.out0, (size_t)bh * prm.N + i_tok, prm.Dout, cb, va, vb, a);
+      }
+    } else {
       const int hh = cb;
       uint32_t v[32];
       tmem_ld32(lane_addr + C_ACC + 32 * hh, v);
@@ -423,7 +533,7 @@ dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
     }
     fence_proxy_async();
     named_barrier_sync(1, 32 * NCW);
-    if (tid == 0) {
+    if (!SPLIT && tid == 0) {
       tma_store_3d(&tmO, smem, 0, it * 128, bh);
       tma_store_3d(&tmO, smem + PANEL, 64, it * 128, bh);
       bulk_commit_group();
@@ -437,7 +547,7 @@ dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
 
 // ------------------------------------------------------------------------------------------------ backward: dk, dv
 // shared memory: K tile | V tile | 2 stages x [Q tile | U tile] | misc (dlt of the stage's q tokens)
-template <int P>
+template <int P, bool SPLIT>
 __global__ void __launch_bounds__(THREADS, 1)
 dkdv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
             const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmU,
@@ -500,8 +610,8 @@ dkdv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUt
       __syncwarp();
       tc_fence_after();
       if (elect_one()) {
-        if (s == 0) mma_scores<0, 0, 0, 0>(D), mma_scores<C_D, 1, 0, 1>(D);     // S' = K Q^T, D' = V U^T
-        else mma_scores<0, 0, 1, 0>(D), mma_scores<C_D, 1, 1, 1>(D);
+        if (s == 0) mma_scores<SPLIT, 0, 0, 0, 0>(D), mma_scores<SPLIT, C_D, 1, 0, 1>(D);     // S' = K Q^T, D' = V U^T
+        else mma_scores<SPLIT, 0, 0, 1, 0>(D), mma_scores<SPLIT, C_D, 1, 1, 1>(D);
         umma_commit(sd_ready);
       }
       __syncwarp();
@@ -509,8 +619,8 @@ dkdv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUt
       __syncwarp();
       tc_fence_after();
       if (elect_one()) {
-        if (s == 0) mma_accum<128, C_DV, 0, 0, 1>(D, n > 0), mma_accum<128, C_DK, C_D, 0, 0>(D, n > 0);   // dV += P' U, dK += E' Q
-        else mma_accum<128, C_DV, 0, 1, 1>(D, n > 0), mma_accum<128, C_DK, C_D, 1, 0>(D, n > 0);
+        if (s == 0) mma_accum<SPLIT, 128, C_DV, 0, 0, 1>(D, n > 0), mma_accum<SPLIT, 128, C_DK, C_D, 0, 0>(D, n > 0);   // dV += P' U, dK += E' Q
+        else mma_accum<SPLIT, 128, C_DV, 0, 1, 1>(D, n > 0), mma_accum<SPLIT, 128, C_DK, C_D, 1, 0>(D, n > 0);
         umma_commit(&st_free[s]);
         if (n == ni - 1) umma_commit(acc_done);
       }
@@ -533,6 +643,7 @@ dkdv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUt
       {
         const int c0 = 32 * cb;
         uint32_t sv[32], dv[32], pp[16], pe[16];
+        uint32_t lp[SPLIT ? 16 : 1], le[SPLIT ? 16 : 1];
         tmem_ld32(lane_addr + c0, sv);
         tmem_ld32(lane_addr + C_D + c0, dv);
         tmem_wait_ld();
@@ -548,11 +659,20 @@ dkdv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUt
             const bool k0 = col >= r, k1 = col + 1 >= r;
             p0 = k0 ? p0 : 0.f, p1 = k1 ? p1 : 0.f, e0 = k0 ? e0 : 0.f, e1 = k1 ? e1 : 0.f;
           }
-          pp[c >> 1] = pack_bf16x2(p0, p1);
-          pe[c >> 1] = pack_bf16x2(e0, e1);
+          if constexpr (SPLIT) {
+            split2(p0, p1, pp[c >> 1], lp[c >> 1]);
+            split2(e0, e1, pe[c >> 1], le[c >> 1]);
+          } else {
+            pp[c >> 1] = pack_bf16x2(p0, p1);
+            pe[c >> 1] = pack_bf16x2(e0, e1);
+          }
         }
         tmem_st16(lane_addr + (c0 >> 1), pp);
         tmem_st16(lane_addr + C_D + (c0 >> 1), pe);
+        if constexpr (SPLIT) {
+          tmem_st16(lane_addr + 64 + (c0 >> 1), lp);
+          tmem_st16(lane_addr + C_D + 64 + (c0 >> 1), le);
+        }
       }
       tmem_wait_st();
       tc_fence_before();
@@ -564,7 +684,17 @@ dkdv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUt
 #pragma unroll 1
     for (int which = 0; which < 2; ++which) {             // dV into the K tile's buffer, dK into the V tile's
       const float sc = which == 0 ? 1.f : a;
-      {
+      if constexpr (SPLIT) {
+        const int kv_tok = jt * 128 + r;
+        if (cb < 2) {
+          uint32_t va[32], vb[32];
+          tmem_ld32(lane_addr + (which == 0 ? C_DV : C_DK) + 32 * cb, va);
+          tmem_ld32(lane_addr + (which == 0 ? C_DV : C_DK) + 64 + 32 * cb, vb);
+          tmem_wait_ld();
+          if (kv_tok < prm.N)
+            store_rows_f32(which == 0 ? prm.out0 : prm.out1, (size_t)bh * prm.N + kv_tok, prm.Dout, cb, va, vb, sc);
+        }
+      } else {
         const int hh = cb;
         uint32_t v[32];
         tmem_ld32(lane_addr + (which == 0 ? C_DV : C_DK) + 32 * hh, v);
@@ -582,8 +712,8 @@ dkdv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUt
       }
     }
     fence_proxy_async();
-    named_barrier_sync(1, 128);
-    if (tid == 0) {
+    named_barrier_sync(1, 32 * NCW);
+    if (!SPLIT && tid == 0) {
       tma_store_3d(&tmDV, smem, 0, jt * 128, bh);
       tma_store_3d(&tmDV, smem + PANEL, 64, jt * 128, bh);
       tma_store_3d(&tmDK, smem + TILE, 0, jt * 128, bh);
@@ -608,31 +738,97 @@ static int tmap128(CUtensorMap* tm, const void* p, int N, int BH) {
 bool dense128_usable(const Problem& pb) {
   return pb.D == 128 && pb.dtype == FASTMAX_DTYPE_BF16 && pb.N >= 128 && !pb.sp_init_fwd && !pb.sp_init_rev;
 }
+// fp32, head size <= 64: the same kernels on [hi | lo] bf16 pairs
+bool dense_split_usable(const Problem& pb) {
+  return pb.D <= 64 && pb.dtype == FASTMAX_DTYPE_F32 && pb.N >= 128 && !pb.sp_init_fwd && !pb.sp_init_rev;
+}
 
-int dense128_fwd(const Problem& pb, const void* q, const void* k, const void* v, void* o, float* g) {
+static size_t split_tensor_bytes(int B, int H, int N) { return align_up((size_t)B * H * N * 256, 1024); }
+size_t dense_split_fwd_workspace_bytes(int B, int H, int N) { return 3 * split_tensor_bytes(B, H, N); }
+size_t dense_split_bwd_workspace_bytes(int B, int H, int N) {
+  return 4 * split_tensor_bytes(B, H, N) + align_up((size_t)B * H * align_up(N, 64) * 4, 1024);
+}
+size_t dense128_bwd_workspace_bytes(int B, int H, int N) {
+  return align_up((size_t)B * H * N * 256, 1024) + align_up((size_t)B * H * align_up(N, 64) * 4, 1024);
+}
+
+template <bool SPLIT>
+static int launch_fwd(const Problem& pb, const void* q, const void* k, const void* v, void* o, float* g) {
   const int BH = pb.B * pb.H;
   CUtensorMap tQ, tK, tV, tO;
   int rc;
-  if ((rc = tmap128(&tQ, q, pb.N, BH)) || (rc = tmap128(&tK, k, pb.N, BH)) || (rc = tmap128(&tV, v, pb.N, BH)) ||
-      (rc = tmap128(&tO, o, pb.N, BH)))
-    return rc;
+  if ((rc = tmap128(&tQ, q, pb.N, BH)) || (rc = tmap128(&tK, k, pb.N, BH)) || (rc = tmap128(&tV, v, pb.N, BH))) return rc;
+  if ((rc = tmap128(&tO, SPLIT ? q : o, pb.N, BH))) return rc;          // (SPLIT writes fp32 rows itself)
   Params P{};
   P.N = pb.N, P.ntile = (pb.N + 127) / 128, P.p = pb.p, P.causal = pb.causal, P.a = pb.inv_c, P.g = g;
+  P.out0 = SPLIT ? (float*)o : nullptr, P.Dout = pb.D;
   dim3 grid(P.ntile, BH);
   Descs D{};
   fill_descs(D, 0, 0, F_OFF_ST, F_STAGE, TILE);          // resident Q; stages [K | V | ones]
+  const char* name = SPLIT ? "dense_split_fwd" : "dense128_fwd";
   if (pb.p == 2) {
-    FM_CUDA(cudaFuncSetAttribute(fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM));
-    FM_LAUNCH("dense128_fwd", pb.stream, fwd_kernel<2><<<grid, THREADS, F_SMEM, pb.stream>>>(tQ, tK, tV, tO, P, D));
+    FM_CUDA(cudaFuncSetAttribute(fwd_kernel<2, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM));
+    FM_LAUNCH(name, pb.stream, (fwd_kernel<2, SPLIT><<<grid, THREADS, F_SMEM, pb.stream>>>(tQ, tK, tV, tO, P, D)));
   } else {
-    FM_CUDA(cudaFuncSetAttribute(fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM));
-    FM_LAUNCH("dense128_fwd", pb.stream, fwd_kernel<1><<<grid, THREADS, F_SMEM, pb.stream>>>(tQ, tK, tV, tO, P, D));
+    FM_CUDA(cudaFuncSetAttribute(fwd_kernel<1, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM));
+    FM_LAUNCH(name, pb.stream, (fwd_kernel<1, SPLIT><<<grid, THREADS, F_SMEM, pb.stream>>>(tQ, tK, tV, tO, P, D)));
   }
   return FASTMAX_OK;
 }
 
-size_t dense128_bwd_workspace_bytes(int B, int H, int N) {
-  return align_up((size_t)B * H * N * 256, 1024) + align_up((size_t)B * H * align_up(N, 64) * 4, 1024);
+int dense128_fwd(const Problem& pb, const void* q, const void* k, const void* v, void* o, float* g) {
+  return launch_fwd<false>(pb, q, k, v, o, g);
+}
+
+static int launch_split(const Problem& pb, const void* x, void* out, const float* g, const char* name) {
+  const size_t rows = (size_t)pb.B * pb.H * pb.N;
+  FM_LAUNCH(name, pb.stream,
+            split_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, pb.stream>>>((const float*)x, (bf16*)out, rows, pb.D, g));
+  return FASTMAX_OK;
+}
+
+int dense_split_fwd(const Problem& pb, const void* q, const void* k, const void* v, void* o, float* g, void* ws) {
+  const size_t tb = split_tensor_bytes(pb.B, pb.H, pb.N);
+  uint8_t* w8 = (uint8_t*)ws;
+  int rc;
+  if ((rc = launch_split(pb, q, w8, nullptr, "dense_split_q")) || (rc = launch_split(pb, k, w8 + tb, nullptr, "dense_split_k")) ||
+      (rc = launch_split(pb, v, w8 + 2 * tb, nullptr, "dense_split_v")))
+    return rc;
+  return launch_fwd<true>(pb, w8, w8 + tb, w8 + 2 * tb, o, g);
+}
+
+template <bool SPLIT>
+static int launch_bwd(const Problem& pb, int Npad, const void* q, const void* k, const void* v, const void* u,
+                      const float* dlt, void* dq, void* dk, void* dv) {
+  const int BH = pb.B * pb.H;
+  CUtensorMap tQ, tK, tV, tU, tDQ, tDK, tDV;
+  int rc;
+  if ((rc = tmap128(&tQ, q, pb.N, BH)) || (rc = tmap128(&tK, k, pb.N, BH)) || (rc = tmap128(&tV, v, pb.N, BH)) ||
+      (rc = tmap128(&tU, u, pb.N, BH)) || (rc = tmap128(&tDQ, SPLIT ? q : dq, pb.N, BH)) ||
+      (rc = tmap128(&tDK, SPLIT ? q : dk, pb.N, BH)) || (rc = tmap128(&tDV, SPLIT ? q : dv, pb.N, BH)))
+    return rc;
+  Params P{};
+  P.N = pb.N, P.Npad = Npad, P.ntile = (pb.N + 127) / 128, P.p = pb.p, P.causal = pb.causal, P.a = pb.inv_c, P.dlt = dlt;
+  P.Dout = pb.D;
+  Params Pq = P, Pkv = P;
+  if (SPLIT) Pq.out0 = (float*)dq, Pkv.out0 = (float*)dv, Pkv.out1 = (float*)dk;
+  dim3 grid(P.ntile, BH);
+  Descs D{};
+  fill_descs(D, 0, TILE, B_OFF_ST, B_STAGE, TILE);       // resident [Q | U] resp. [K | V]; stages [K | V] resp. [Q | U]
+  const char* n1 = SPLIT ? "dense_split_dq" : "dense128_dq";
+  const char* n2 = SPLIT ? "dense_split_dkdv" : "dense128_dkdv";
+  if (pb.p == 2) {
+    FM_CUDA(cudaFuncSetAttribute(dq_kernel<2, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
+    FM_CUDA(cudaFuncSetAttribute(dkdv_kernel<2, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
+    FM_LAUNCH(n1, pb.stream, (dq_kernel<2, SPLIT><<<grid, THREADS, B_SMEM, pb.stream>>>(tQ, tU, tK, tV, tDQ, Pq, D)));
+    FM_LAUNCH(n2, pb.stream, (dkdv_kernel<2, SPLIT><<<grid, THREADS, B_SMEM, pb.stream>>>(tK, tV, tQ, tU, tDK, tDV, Pkv, D)));
+  } else {
+    FM_CUDA(cudaFuncSetAttribute(dq_kernel<1, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
+    FM_CUDA(cudaFuncSetAttribute(dkdv_kernel<1, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
+    FM_LAUNCH(n1, pb.stream, (dq_kernel<1, SPLIT><<<grid, THREADS, B_SMEM, pb.stream>>>(tQ, tU, tK, tV, tDQ, Pq, D)));
+    FM_LAUNCH(n2, pb.stream, (dkdv_kernel<1, SPLIT><<<grid, THREADS, B_SMEM, pb.stream>>>(tK, tV, tQ, tU, tDK, tDV, Pkv, D)));
+  }
+  return FASTMAX_OK;
 }
 
 int dense128_bwd(const Problem& pb, const void* q, const void* k, const void* v, const void* o, const float* g,
@@ -645,29 +841,26 @@ int dense128_bwd(const Problem& pb, const void* q, const void* k, const void* v,
   FM_LAUNCH("dense128_prep", pb.stream,
             prep_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, pb.stream>>>((const bf16*)o, (const bf16*)d_o, g, u, dlt, rows,
                                                                            pb.N, Npad));
-  CUtensorMap tQ, tK, tV, tU, tDQ, tDK, tDV;
+  return launch_bwd<false>(pb, Npad, q, k, v, u, dlt, dq, dk, dv);
+}
+
+int dense_split_bwd(const Problem& pb, const void* q, const void* k, const void* v, const void* o, const float* g,
+                    const void* d_o, void* dq, void* dk, void* dv, void* ws) {
+  const int BH = pb.B * pb.H, Npad = (int)align_up(pb.N, 64);
+  const size_t tb = split_tensor_bytes(pb.B, pb.H, pb.N);
+  uint8_t* w8 = (uint8_t*)ws;
+  float* dlt = (float*)(w8 + 4 * tb);
+  const size_t rows = (size_t)BH * pb.N;
   int rc;
-  if ((rc = tmap128(&tQ, q, pb.N, BH)) || (rc = tmap128(&tK, k, pb.N, BH)) || (rc = tmap128(&tV, v, pb.N, BH)) ||
-      (rc = tmap128(&tU, u, pb.N, BH)) || (rc = tmap128(&tDQ, dq, pb.N, BH)) || (rc = tmap128(&tDK, dk, pb.N, BH)) ||
-      (rc = tmap128(&tDV, dv, pb.N, BH)))
+  FM_CUDA(cudaMemsetAsync(dlt, 0, (size_t)BH * Npad * 4, pb.stream));
+  FM_LAUNCH("dense_split_dlt", pb.stream,
+            dlt_f32_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, pb.stream>>>((const float*)o, (const float*)d_o, g, dlt, rows,
+                                                                              pb.D, pb.N, Npad));
+  if ((rc = launch_split(pb, q, w8, nullptr, "dense_split_q")) || (rc = launch_split(pb, k, w8 + tb, nullptr, "dense_split_k")) ||
+      (rc = launch_split(pb, v, w8 + 2 * tb, nullptr, "dense_split_v")) ||
+      (rc = launch_split(pb, d_o, w8 + 3 * tb, g, "dense_split_u")))
     return rc;
-  Params P{};
-  P.N = pb.N, P.Npad = Npad, P.ntile = (pb.N + 127) / 128, P.p = pb.p, P.causal = pb.causal, P.a = pb.inv_c, P.dlt = dlt;
-  dim3 grid(P.ntile, BH);
-  Descs D{};
-  fill_descs(D, 0, TILE, B_OFF_ST, B_STAGE, TILE);       // resident [Q | U] resp. [K | V]; stages [K | V] resp. [Q | U]
-  if (pb.p == 2) {
-    FM_CUDA(cudaFuncSetAttribute(dq_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
-    FM_CUDA(cudaFuncSetAttribute(dkdv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
-    FM_LAUNCH("dense128_dq", pb.stream, dq_kernel<2><<<grid, THREADS, B_SMEM, pb.stream>>>(tQ, tU, tK, tV, tDQ, P, D));
-    FM_LAUNCH("dense128_dkdv", pb.stream, dkdv_kernel<2><<<grid, THREADS, B_SMEM, pb.stream>>>(tK, tV, tQ, tU, tDK, tDV, P, D));
-  } else {
-    FM_CUDA(cudaFuncSetAttribute(dq_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
-    FM_CUDA(cudaFuncSetAttribute(dkdv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
-    FM_LAUNCH("dense128_dq", pb.stream, dq_kernel<1><<<grid, THREADS, B_SMEM, pb.stream>>>(tQ, tU, tK, tV, tDQ, P, D));
-    FM_LAUNCH("dense128_dkdv", pb.stream, dkdv_kernel<1><<<grid, THREADS, B_SMEM, pb.stream>>>(tK, tV, tQ, tU, tDK, tDV, P, D));
-  }
-  return FASTMAX_OK;
+  return launch_bwd<true>(pb, Npad, w8, w8 + tb, w8 + 2 * tb, w8 + 3 * tb, dlt, dq, dk, dv);
 }
 
 }  // namespace fm

@@ -353,6 +353,28 @@ def test_head_size_128_dense_tensor_tiles(shape, p, causal):
         assert err <= 2e-2, (shape, p, causal, nm, err)
 
 
+@pytest.mark.parametrize("shape", [(1, 2, 128, 64), (2, 2, 1000, 64), (1, 1, 2049, 64), (1, 2, 600, 32), (1, 1, 333, 48)],
+                         ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("p", [1, 2])
+@pytest.mark.parametrize("causal", [True, False], ids=["causal", "full"])
+def test_fp32_inputs_run_as_split_precision_tensor_tiles(shape, p, causal):
+    """fp32 problems (head size <= 64, N >= 128) run on the tensor pipe with every fp32 operand as a [hi | lo] bf16 pair
+    and three-term products (fm_dense128.cu, SPLIT): the fp32 parity bar of SURVEY 8c (1e-4) must hold for every
+    output, and the kernels that ran must be the tcgen05 ones."""
+    B, H, N, D = shape
+    gen = torch.Generator().manual_seed(500 + N + D + p)
+    q, k, v, do = (torch.randn(B, H, N, D, generator=gen) for _ in range(4))
+    ref = orc.dense_fwd_bwd(q.double(), k.double(), v.double(), do.double(), mask=causal, p=p)
+    c = orc.denominator_c(D)
+    args = tuple(t.cuda() for t in (q, k, v, do)) + (causal, 1.0 / c, p, _lib.ALGO_AUTO)
+    out = _run_raw(*args)
+    names = {n for n, _ in _profile_names(lambda: _run_raw(*args))}
+    assert {"dense_split_fwd", "dense_split_dq", "dense_split_dkdv"} <= names, names
+    for nm, x, r in zip(("o", "g", "dq", "dk", "dv"), out, ref):
+        err = orc.rel_err(x, r)
+        assert err <= 1e-4, (shape, p, causal, nm, err)
+
+
 def _profile_names(fn):
     _lib.profile_enable(True)
     fn()

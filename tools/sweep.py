@@ -1,5 +1,5 @@
 """Op sweep of BASELINE.json configs[1] on one GPU: B*N = 128k tokens, H=32, D=64, N = 1k..64k, p = 1 and 2,
-causal / non-causal, bf16 (tcgen05 path) and fp32 (CUDA-core path, short N only: it is O(N^2)).
+causal / non-causal, bf16 (tcgen05 moment / scan paths) and fp32 (dense tcgen05 tiles on split bf16 pairs: O(N^2)).
 Prints a markdown table: ms per fwd+bwd, tokens/s, and for p=1 the algorithmic HBM rate
 (1544 B/unit bf16) against the measured copy bandwidth in MEASURED_PEAKS.json."""
 import json, os, sys
@@ -13,7 +13,7 @@ peaks = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_P
 hbm = peaks["hbm_gbs"]
 print(f"| N | B | p | mask | dtype | algo | seg | ms/step | M tokens/s | alg. GB/s (p=1) | of {hbm:.0f} GB/s |")
 print("|---|---|---|---|---|---|---|---|---|---|---|")
-for dtype, ns in ((torch.bfloat16, (1024, 2048, 4096, 16384, 65536)), (torch.float32, (1024, 2048))):
+for dtype, ns in ((torch.bfloat16, (1024, 2048, 4096, 16384, 65536)), (torch.float32, (1024, 2048, 4096, 16384))):
     for N in ns:
         B = max(1, min(64, 131072 // N))
         gen = torch.Generator(device="cuda").manual_seed(0)
@@ -41,13 +41,15 @@ for dtype, ns in ((torch.bfloat16, (1024, 2048, 4096, 16384, 65536)), (torch.flo
                 torch.cuda.synchronize()
                 ms = e0.elapsed_time(e1) / reps
                 units = B * H * N
+                # (fp32 with N >= 128 under ALGO_AUTO: dense tcgen05 tiles on [hi | lo] bf16 pairs, fm_dense128.cu)
+                algo_name = 'moments' if pl.algo == 2 else ('dense split' if dtype == torch.float32 and N >= 128 else 'exact')
                 es = 2 if dtype == torch.bfloat16 else 4
                 gbs = units * (12 * D * es + 8) / (ms * 1e-3) / 1e9
                 print(f"| {N} | {B} | {p} | {'causal' if causal else 'full'} | {'bf16' if es == 2 else 'fp32'} | "
-                      f"{'moments' if pl.algo == 2 else 'exact'} | {pl.seg_len} | {ms:.2f} | {B * N / ms / 1e3:.2f} | "
+                      f"{algo_name} | {pl.seg_len} | {ms:.2f} | {B * N / ms / 1e3:.2f} | "
                       f"{gbs:.0f} | {100 * gbs / hbm:.1f} % |" if p == 1 else
                       f"| {N} | {B} | {p} | {'causal' if causal else 'full'} | {'bf16' if es == 2 else 'fp32'} | "
-                      f"{'moments' if pl.algo == 2 else 'exact'} | {pl.seg_len} | {ms:.2f} | {B * N / ms / 1e3:.2f} | | |")
+                      f"{algo_name} | {pl.seg_len} | {ms:.2f} | {B * N / ms / 1e3:.2f} | | |")
         del q, k, v, do
         torch.cuda.empty_cache()
 
