@@ -24,6 +24,18 @@
 // memory, the normaliser is summed in fp32 on CUDA cores, outputs are written as fp32.
 #include "fm_common.cuh"
 #include "fm_sm100.cuh"
+#include <type_traits>
+
+#ifdef FM_TRACE
+// developer build: event times of CTA (0,0) of the forward kernel, [event][tile]
+static __device__ long long fm_trace_d128[8][64];
+extern "C" int fastmax_debug_trace_fetch_d128(long long* out) {
+  return cudaMemcpyFromSymbol(out, fm_trace_d128, sizeof(fm_trace_d128)) == cudaSuccess ? 0 : -4;
+}
+#define FM_TRD(ev, j) do { if (blockIdx.x == 0 && blockIdx.y == 0 && (j) < 64) fm_trace_d128[ev][j] = clock64(); } while (0)
+#else
+#define FM_TRD(ev, j) ((void)0)
+#endif
 
 namespace fm {
 namespace d128 {
@@ -128,8 +140,11 @@ __device__ __forceinline__ void load_tile(uint8_t* dst, const CUtensorMap* tm, u
   tma_load_3d(dst + PANEL, tm, bar, 64, tok, bh);
 }
 
+// f(a s) straight from the raw score: 1 + a s (+ (a^2 / 2) s^2), one or two FMAs (c1 = a, c2 = a^2 / 2)
 template <int P>
-__device__ __forceinline__ float poly(float x) { return P == 2 ? fmaf(fmaf(0.5f, x, 1.f), x, 1.f) : 1.f + x; }
+__device__ __forceinline__ float poly(float s, float c1, float c2) {
+  return P == 2 ? fmaf(fmaf(c2, s, c1), s, 1.f) : fmaf(c1, s, 1.f);
+}
 
 // ------------------------------------------------------------------------------------------------ forward
 // shared memory: Q tile | 2 stages x [K tile | V tile | ones panel] | misc
@@ -212,7 +227,10 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
       const int s = j & 1;
       if (j < nj) {
         // scores of tile j into buffer s (its previous content, P of tile j-2, was consumed by an MMA issued earlier)
-        if (lane == 0) mbar_wait(&k_full[s], (j >> 1) & 1, 400 + j);
+        if (lane == 0) {
+          mbar_wait(&k_full[s], (j >> 1) & 1, 400 + j);
+          FM_TRD(0, j);
+        }
         __syncwarp();
         tc_fence_after();
         if (elect_one()) {
@@ -220,6 +238,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
           else mma_scores<SPLIT, 128, 0, 1, 0>(D);
           umma_commit(&k_free[s]);
           umma_commit(&s_ready[s]);
+          FM_TRD(1, j);
         }
         __syncwarp();
       }
@@ -228,6 +247,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
         if (lane == 0) {
           mbar_wait(&v_full[sp], ((j - 1) >> 1) & 1, 500 + j);
           mbar_wait(&p_ready[sp], ((j - 1) >> 1) & 1, 600 + j);
+          FM_TRD(2, j - 1);
         }
         __syncwarp();
         tc_fence_after();
@@ -236,6 +256,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
           else mma_accum<SPLIT, 144, C_ACC, 128, 1, 1>(D, j > 1);
           umma_commit(&v_free[sp]);
           if (j == nj) umma_commit(acc_done);
+          FM_TRD(3, j - 1);
         }
         __syncwarp();
       }
@@ -245,12 +266,13 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
     const int r = 32 * q4 + lane;
     const int i_tok = it * 128 + r;
     const uint32_t lane_addr = tmem + ((uint32_t)(32 * q4) << 16);
-    const float a = prm.a;
+    const float a = prm.a, c2 = 0.5f * a * a;
     float rsum = 0.f;
     for (int j = 0; j < nj; ++j) {
       const int s = j & 1;
       mbar_wait_warp(&s_ready[s], (j >> 1) & 1);
       tc_fence_after();
+      if (tid == 0) FM_TRD(4, j);
       const bool diag = prm.causal && j == it;
       const bool tail = (j + 1) * 128 > prm.N;
       {
@@ -261,19 +283,26 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
         // the P of columns [c0, c0+32) goes to tensor-memory columns [c0/2, c0/2+16), which another warp of this
         // quadrant may still be reading as scores: everyone has its scores in registers first
         named_barrier_sync(1, 32 * NCW);
+        if (tid == 0) FM_TRD(5, j);
+        // (interior tiles take the loop without the mask selects: the polynomial is ~1300 issue cycles per tile pair
+        //  and scheduler otherwise, more than the pair's MMAs)
+        auto body = [&](auto masked) {
+          constexpr bool M = decltype(masked)::value;
+          const int lim = M ? min(diag ? r : 127, prm.N - 1 - j * 128) : 0;     // last column this row keeps
 #pragma unroll
-        for (int c = 0; c < 32; c += 2) {
-          float x0 = poly<P>(a * __uint_as_float(v[c])), x1 = poly<P>(a * __uint_as_float(v[c + 1]));
-          const int col = c0 + c;
-          if (diag) x0 = col <= r ? x0 : 0.f, x1 = col + 1 <= r ? x1 : 0.f;
-          if (tail) x0 = j * 128 + col < prm.N ? x0 : 0.f, x1 = j * 128 + col + 1 < prm.N ? x1 : 0.f;
-          if constexpr (SPLIT) {
-            rsum += x0 + x1;
-            split2(x0, x1, pk[c >> 1], pl[c >> 1]);
-          } else {
-            pk[c >> 1] = pack_bf16x2(x0, x1);
+          for (int c = 0; c < 32; c += 2) {
+            float x0 = poly<P>(__uint_as_float(v[c]), a, c2), x1 = poly<P>(__uint_as_float(v[c + 1]), a, c2);
+            if (M) x0 = c0 + c <= lim ? x0 : 0.f, x1 = c0 + c + 1 <= lim ? x1 : 0.f;
+            if constexpr (SPLIT) {
+              rsum += x0 + x1;
+              split2(x0, x1, pk[c >> 1], pl[c >> 1]);
+            } else {
+              pk[c >> 1] = pack_bf16x2(x0, x1);
+            }
           }
-        }
+        };
+        if (diag || tail) body(std::true_type{});
+        else body(std::false_type{});
         tmem_st16(lane_addr + 128 * s + (c0 >> 1), pk);
         if constexpr (SPLIT) tmem_st16(lane_addr + 128 * s + 64 + (c0 >> 1), pl);
       }
@@ -281,6 +310,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
       tc_fence_before();
       named_barrier_sync(1, 32 * NCW);
       if (tid == 0) mbar_arrive(&p_ready[s]);
+      if (tid == 0) FM_TRD(6, j);
     }
     // epilogue: o = acc / den, g = den; rows leave through the Q tile's buffer (all score MMAs are complete)
     mbar_wait_warp(acc_done, 0);
@@ -488,15 +518,19 @@ dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
         tmem_ld32(lane_addr + C_D + c0, dv);
         tmem_wait_ld();
         named_barrier_sync(1, 32 * NCW);       // (E overwrites score columns other warps of the quadrant read)
+        auto body = [&](auto masked) {
+          constexpr bool M = decltype(masked)::value;
 #pragma unroll
-        for (int c = 0; c < 32; c += 2) {
-          float e0 = __uint_as_float(dv[c]) - dl, e1 = __uint_as_float(dv[c + 1]) - dl;
-          if (P == 2) e0 *= fmaf(a, __uint_as_float(sv[c]), 1.f), e1 *= fmaf(a, __uint_as_float(sv[c + 1]), 1.f);
-          const int col = c0 + c;
-          if (diag) e0 = col <= r ? e0 : 0.f, e1 = col + 1 <= r ? e1 : 0.f;
-          if constexpr (SPLIT) split2(e0, e1, pk[c >> 1], pl[c >> 1]);
-          else pk[c >> 1] = pack_bf16x2(e0, e1);
-        }
+          for (int c = 0; c < 32; c += 2) {
+            float e0 = __uint_as_float(dv[c]) - dl, e1 = __uint_as_float(dv[c + 1]) - dl;
+            if (P == 2) e0 *= fmaf(a, __uint_as_float(sv[c]), 1.f), e1 *= fmaf(a, __uint_as_float(sv[c + 1]), 1.f);
+            if (M) e0 = c0 + c <= r ? e0 : 0.f, e1 = c0 + c + 1 <= r ? e1 : 0.f;
+            if constexpr (SPLIT) split2(e0, e1, pk[c >> 1], pl[c >> 1]);
+            else pk[c >> 1] = pack_bf16x2(e0, e1);
+          }
+        };
+        if (diag) body(std::true_type{});
+        else body(std::false_type{});
         tmem_st16(lane_addr + (c0 >> 1), pk);
         if constexpr (SPLIT) tmem_st16(lane_addr + 64 + (c0 >> 1), pl);
       }
@@ -630,7 +664,7 @@ dkdv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUt
     const int q4 = warp & 3, cb = warp >> 2;
     const int r = 32 * q4 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)(32 * q4) << 16);
-    const float a = prm.a;
+    const float a = prm.a, c2 = 0.5f * a * a;
     for (int n = 0; n < ni; ++n) {
       const int i = i0 + n, s = n & 1;
       const int q_tok = i * 128 + r;
@@ -648,25 +682,31 @@ dkdv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUt
         tmem_ld32(lane_addr + C_D + c0, dv);
         tmem_wait_ld();
         named_barrier_sync(1, 32 * NCW);       // scores in registers everywhere, dlt of the q tokens visible
+        auto body = [&](auto masked) {
+          constexpr bool M = decltype(masked)::value;
 #pragma unroll
-        for (int c = 0; c < 32; c += 2) {
-          const int col = c0 + c;
-          const float x0 = a * __uint_as_float(sv[c]), x1 = a * __uint_as_float(sv[c + 1]);
-          float p0 = poly<P>(x0), p1 = poly<P>(x1);
-          float e0 = __uint_as_float(dv[c]) - dc[col], e1 = __uint_as_float(dv[c + 1]) - dc[col + 1];
-          if (P == 2) e0 *= 1.f + x0, e1 *= 1.f + x1;
-          if (diag) {
-            const bool k0 = col >= r, k1 = col + 1 >= r;
-            p0 = k0 ? p0 : 0.f, p1 = k1 ? p1 : 0.f, e0 = k0 ? e0 : 0.f, e1 = k1 ? e1 : 0.f;
+          for (int c = 0; c < 32; c += 2) {
+            const int col = c0 + c;
+            const float s0 = __uint_as_float(sv[c]), s1 = __uint_as_float(sv[c + 1]);
+            float p0 = poly<P>(s0, a, c2), p1 = poly<P>(s1, a, c2);
+            const float2 dd = *reinterpret_cast<const float2*>(dc + col);
+            float e0 = __uint_as_float(dv[c]) - dd.x, e1 = __uint_as_float(dv[c + 1]) - dd.y;
+            if (P == 2) e0 *= fmaf(a, s0, 1.f), e1 *= fmaf(a, s1, 1.f);
+            if (M) {
+              const bool k0 = col >= r, k1 = col + 1 >= r;
+              p0 = k0 ? p0 : 0.f, p1 = k1 ? p1 : 0.f, e0 = k0 ? e0 : 0.f, e1 = k1 ? e1 : 0.f;
+            }
+            if constexpr (SPLIT) {
+              split2(p0, p1, pp[c >> 1], lp[c >> 1]);
+              split2(e0, e1, pe[c >> 1], le[c >> 1]);
+            } else {
+              pp[c >> 1] = pack_bf16x2(p0, p1);
+              pe[c >> 1] = pack_bf16x2(e0, e1);
+            }
           }
-          if constexpr (SPLIT) {
-            split2(p0, p1, pp[c >> 1], lp[c >> 1]);
-            split2(e0, e1, pe[c >> 1], le[c >> 1]);
-          } else {
-            pp[c >> 1] = pack_bf16x2(p0, p1);
-            pe[c >> 1] = pack_bf16x2(e0, e1);
-          }
-        }
+        };
+        if (diag) body(std::true_type{});
+        else body(std::false_type{});
         tmem_st16(lane_addr + (c0 >> 1), pp);
         tmem_st16(lane_addr + C_D + (c0 >> 1), pe);
         if constexpr (SPLIT) {

@@ -21,6 +21,9 @@ Behavioural notes:
   only, with the reference's count term N_q in the normaliser (fastmax.py:269-271, quirk Q2).
 * Meta tensors pass through shape-only (the pretrain scripts' flop count runs the model on the meta
   device, where the reference's own host hop fails: quirk Q7).
+* fp32 inputs of head size <= 64 with N >= 128 run on the tensor pipe in split precision (every fp32 operand as a
+  [hi | lo] bf16 pair, three-term products, fp32 accumulation: ~1e-5 against the fp64 formula; csrc/fm_dense128.cu);
+  other fp32 shapes use the fp32 CUDA-core kernels (~1e-6).
 * bf16 heads narrower than 64 (Pythia: 32) are zero-padded to 64, heads between 64 and 128 (phi: 80, Llama-3.2: 96 ...)
   to 128, so that they run on the tcgen05 kernels (D = 64 moment / scan kernels, D = 128 dense tiles): zero features
   change neither the scores nor the normaliser, and the padded output / gradient columns are exactly zero and sliced
