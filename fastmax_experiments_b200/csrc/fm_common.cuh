@@ -95,6 +95,10 @@ int intra_dkdv(const Problem& pb, int L, int Npad, const void* k, const void* v,
                void* dv_final = nullptr);
 // (p = 1 with *_final given: the kernels also apply the first-order state term and write the final bf16
 //  outputs; the *_part arguments are then unused)
+// second-generation intra-segment kernels for p = 2 causal (fm_seg.cu): same contract as intra_fwd
+bool seg_fwd_usable(const Problem& pb, int L);
+int seg_fwd(const Problem& pb, int L, const void* q, const void* k, const void* v, float* o_part, float* g,
+            const uint8_t* state);
 namespace mom { struct ApplyDesc; }
 int launch_apply_gen(const Problem& pb, int BH, int nrec, const char* name, const mom::ApplyDesc& d, int variant);
 // first-order causal FastMax as one fused scan per (b,h) (fm_p1scan.cu)

@@ -884,6 +884,16 @@ static bool p1_scan_enabled() {
   return v != 0;
 }
 
+// developer switch: FASTMAX_INTRA=v1 keeps the first-generation intra-segment kernels of fm_intra.cu for p = 2 causal
+static bool seg_kernels_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("FASTMAX_INTRA");
+    v = (e && !strcmp(e, "v1")) ? 0 : 1;
+  }
+  return v != 0;
+}
+
 static int launch_transpose(const Problem& pb, const void* in, void* out, int Npad) {
   dim3 grid(Npad / 64, pb.B * pb.H);
   FM_LAUNCH("mom_transpose", pb.stream,
@@ -989,7 +999,11 @@ int moments_fwd(const Problem& pb, const void* q, const void* k, const void* v, 
   // only that MMA runs (no intra-segment part, no partial)
   if (pb.p == 1)   // first order: the intra kernel applies the (single-slab) state term itself and writes o
     return intra_fwd(pb, m.L, m.Npad, q, k, v, nullptr, g, state, o);
-  if ((rc = intra_fwd(pb, m.L, m.Npad, q, k, v, pb.causal ? part : nullptr, g, state))) return rc;
+  if (seg_kernels_enabled() && seg_fwd_usable(pb, m.L)) {
+    if ((rc = seg_fwd(pb, m.L, q, k, v, part, g, state))) return rc;
+  } else if ((rc = intra_fwd(pb, m.L, m.Npad, q, k, v, pb.causal ? part : nullptr, g, state))) {
+    return rc;
+  }
   // 3. inter-segment part + normalisation
   ApplyParams ap{};
   ap.mode = APPLY_FWD, ap.state_reverse = 0, ap.b_kmajor = 0, ap.edge_state = pb.sp_init_fwd != nullptr;

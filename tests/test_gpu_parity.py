@@ -602,11 +602,12 @@ print("variant ok")
 """
 
 
-@pytest.mark.parametrize("env,p", [({"FASTMAX_APPLY": "gen"}, 2), ({"FASTMAX_BUILD": "full"}, 2), ({"FASTMAX_P1": "chunked"}, 1)],
-                         ids=["apply-gen", "build-full", "p1-chunked"])
+@pytest.mark.parametrize("env,p", [({"FASTMAX_APPLY": "gen"}, 2), ({"FASTMAX_BUILD": "full"}, 2), ({"FASTMAX_P1": "chunked"}, 1),
+                                    ({"FASTMAX_INTRA": "v1"}, 2)],
+                         ids=["apply-gen", "build-full", "p1-chunked", "intra-v1"])
 def test_kernel_variants_behind_developer_switches(env, p):
     """The measured alternatives kept in the library (fm_apply.cu's generated-operand contraction; the round-1
-    unpacked build layout; the chunked first-order path that the fused scan of fm_p1scan.cu replaced for whole
+    unpacked build layout; the first-generation forward intra-segment kernel that fm_seg.cu replaced; the chunked first-order path that the fused scan of fm_p1scan.cu replaced for whole
     sequences and that sequence-parallel ranks and few-(b,h) long sequences still use) stay parity-green:
     multi-segment causal and non-causal shapes against the dense oracle, in a fresh process (the switches are read
     once per process)."""
