@@ -24,6 +24,8 @@ SYMBOLS = [
     "fastmax_sp_state_bytes", "fastmax_sp_local_state_workspace_bytes", "fastmax_sp_local_state",
     "fastmax_sp_local_state_rev", "fastmax_sp_reduce", "fastmax_fwd_sp", "fastmax_bwd_sp",
     "fastmax_decode_state_bytes", "fastmax_decode_init", "fastmax_decode_update", "fastmax_decode_attend",
+    "fastmax_gqa_workspace_bytes", "fastmax_gqa_saved_state_bytes", "fastmax_fwd_gqa", "fastmax_bwd_gqa",
+    "fastmax_qkv_prologue", "fastmax_qkv_prologue_bwd",
 ]
 
 
@@ -42,7 +44,7 @@ class FastmaxError(RuntimeError):
 
 _lib = None
 _dev = None
-ABI_VERSION = 3          # FASTMAX_B200_ABI_VERSION of include/fastmax_b200.h these argtypes were written for
+ABI_VERSION = 4          # FASTMAX_B200_ABI_VERSION of include/fastmax_b200.h these argtypes were written for
 
 
 def load_dev() -> C.CDLL:
@@ -118,6 +120,18 @@ def load() -> C.CDLL:
     lib.fastmax_decode_update.argtypes = [vp] * 3 + [i32] * 6 + [vp]
     lib.fastmax_decode_attend.restype = i32
     lib.fastmax_decode_attend.argtypes = [vp] * 3 + [i32] * 5 + [f32, f32, i32, vp]
+    lib.fastmax_gqa_workspace_bytes.restype = sz
+    lib.fastmax_gqa_workspace_bytes.argtypes = [i32] * 9
+    lib.fastmax_gqa_saved_state_bytes.restype = sz
+    lib.fastmax_gqa_saved_state_bytes.argtypes = [i32] * 8
+    lib.fastmax_fwd_gqa.restype = i32
+    lib.fastmax_fwd_gqa.argtypes = [vp] * 6 + [i32] * 7 + [f32, i32, vp, sz, vp]
+    lib.fastmax_bwd_gqa.restype = i32
+    lib.fastmax_bwd_gqa.argtypes = [vp] * 10 + [i32] * 7 + [f32, i32, vp, sz, vp]
+    lib.fastmax_qkv_prologue.restype = i32
+    lib.fastmax_qkv_prologue.argtypes = [vp] * 6 + [i32] * 8 + [vp]
+    lib.fastmax_qkv_prologue_bwd.restype = i32
+    lib.fastmax_qkv_prologue_bwd.argtypes = [vp] * 6 + [i32] * 8 + [vp]
     lib.fastmax_profile_enable.restype = None
     lib.fastmax_profile_enable.argtypes = [i32]
     lib.fastmax_profile_fetch.restype = i32

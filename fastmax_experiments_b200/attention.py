@@ -55,15 +55,22 @@ def _method_fastmax_cuda(self, q, k, v):                  # bound as CausalSelfA
     return fastmax(q, k, v, p=2, mask=True)
 
 
-def patch_causal_self_attention(cls) -> type:
-    """Rebind ``cls.fastmax`` / ``cls.fastmax_cuda`` (a ``lit_gpt.model.CausalSelfAttention``-like
-    class) to the CUDA path.  Returns ``cls`` for chaining."""
+def patch_causal_self_attention(cls, fused: bool = False) -> type:
+    """Rebind ``cls.fastmax`` / ``cls.fastmax_cuda`` / ``cls.linearmax`` (a ``lit_gpt.model.CausalSelfAttention``-like
+    class) to the CUDA path.  ``fused=True`` also replaces ``cls.forward`` for the FastMax training path by
+    ``gqa.fused_attention_forward`` (one-pass q/k/v prologue, k and v not expanded over the query groups:
+    SURVEY.md section 8f-1); the class's own forward stays reachable as ``cls._reference_forward`` and still serves
+    every other ``attn_alg`` and the KV-cache path.  Returns ``cls`` for chaining."""
     for name in ("forward",):
         if not hasattr(cls, name):
             raise TypeError(f"{cls!r} does not look like lit_gpt.model.CausalSelfAttention")
     cls.fastmax = _method_fastmax
     cls.fastmax_cuda = _method_fastmax_cuda
     cls.linearmax = _method_linearmax
+    if fused and not hasattr(cls, "_reference_forward"):
+        from .gqa import fused_attention_forward
+        cls._reference_forward = cls.forward
+        cls.forward = fused_attention_forward
     return cls
 
 

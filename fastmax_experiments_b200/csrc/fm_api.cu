@@ -294,6 +294,89 @@ int fastmax_bwd_ex(const void* q, const void* k, const void* v, const void* o, c
   return fm::moments_bwd(pb, q, k, v, o, g, d_o, dq, dk, dv, workspace);
 }
 
+// ---- grouped-query attention -------------------------------------------------------------------
+static int gqa_check(int B, int H, int Hkv, int N, int D, int p, int causal, int dtype, fastmax_plan* pl) {
+  if (Hkv <= 0 || H % Hkv != 0) return FASTMAX_ERR_BAD_ARG;
+  int rc = fastmax_plan_make(pl, B, H, N, D, p, causal, dtype, FASTMAX_ALGO_MOMENTS);
+  if (rc) return rc;
+  if (p != 2) return FASTMAX_ERR_UNSUPPORTED;   // first order runs on the scan kernels, which are not group-aware
+  return FASTMAX_OK;
+}
+
+size_t fastmax_gqa_workspace_bytes(int B, int H, int Hkv, int N, int D, int p, int causal, int dtype, int backward) {
+  fastmax_plan pl;
+  if (gqa_check(B, H, Hkv, N, D, p, causal, dtype, &pl)) return 0;
+  return fm::moments_workspace_bytes(B, H, N, p, causal, backward != 0, Hkv);
+}
+
+size_t fastmax_gqa_saved_state_bytes(int B, int H, int Hkv, int N, int D, int p, int causal, int dtype) {
+  fastmax_plan pl;
+  if (gqa_check(B, H, Hkv, N, D, p, causal, dtype, &pl)) return 0;
+  return fm::moments_saved_state_bytes(B, H, N, p, causal, Hkv);
+}
+
+int fastmax_fwd_gqa(const void* q, const void* k, const void* v, void* o, float* g, void* saved_states, int B, int H,
+                    int Hkv, int N, int D, int p, int causal, float inv_c, int dtype, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+  fm::status().launches = 0;
+  fm::status().cuda_err[0] = 0;
+  if (!q || !k || !v || !o || !g) return FASTMAX_ERR_BAD_ARG;
+  fastmax_plan pl;
+  int rc = gqa_check(B, H, Hkv, N, D, p, causal, dtype, &pl);
+  if (rc) return rc;
+  if (fm::moments_workspace_bytes(B, H, N, p, causal, false, Hkv) > workspace_bytes || !workspace ||
+      ((uintptr_t)workspace & 255))
+    return FASTMAX_ERR_WORKSPACE;
+  Problem pb{B, H, N, D, p, causal ? 1 : 0, dtype, inv_c, (cudaStream_t)stream};
+  pb.saved_states = saved_states;
+  pb.Hkv = Hkv;
+  return fm::moments_fwd(pb, q, k, v, o, g, workspace);
+}
+
+int fastmax_bwd_gqa(const void* q, const void* k, const void* v, const void* o, const float* g, const void* d_o,
+                    void* dq, void* dk, void* dv, const void* saved_states, int B, int H, int Hkv, int N, int D, int p,
+                    int causal, float inv_c, int dtype, void* workspace, size_t workspace_bytes, void* stream) {
+  fm::status().launches = 0;
+  fm::status().cuda_err[0] = 0;
+  if (!q || !k || !v || !o || !g || !d_o || !dq || !dk || !dv) return FASTMAX_ERR_BAD_ARG;
+  fastmax_plan pl;
+  int rc = gqa_check(B, H, Hkv, N, D, p, causal, dtype, &pl);
+  if (rc) return rc;
+  if (fm::moments_workspace_bytes(B, H, N, p, causal, true, Hkv) > workspace_bytes || !workspace ||
+      ((uintptr_t)workspace & 255))
+    return FASTMAX_ERR_WORKSPACE;
+  Problem pb{B, H, N, D, p, causal ? 1 : 0, dtype, inv_c, (cudaStream_t)stream};
+  pb.saved_states = const_cast<void*>(saved_states);
+  pb.Hkv = Hkv;
+  return fm::moments_bwd(pb, q, k, v, o, g, d_o, dq, dk, dv, workspace);
+}
+
+int fastmax_qkv_prologue(const void* qkv, const void* cos, const void* sin, void* q, void* k, void* v, int B, int T,
+                         int n_query_groups, int q_per_kv, int head_size, int rope_n_elem, int dtype, int dtype_cos_sin,
+                         void* stream) {
+  fm::status().launches = 0;
+  fm::status().cuda_err[0] = 0;
+  if (!qkv || !q || !k || !v || (rope_n_elem > 0 && (!cos || !sin))) return FASTMAX_ERR_BAD_ARG;
+  if ((dtype != FASTMAX_DTYPE_BF16 && dtype != FASTMAX_DTYPE_F32) ||
+      (dtype_cos_sin != FASTMAX_DTYPE_BF16 && dtype_cos_sin != FASTMAX_DTYPE_F32))
+    return FASTMAX_ERR_BAD_ARG;
+  return fm::qkv_prologue(qkv, cos, sin, q, k, v, B, T, n_query_groups, q_per_kv, head_size, rope_n_elem, dtype,
+                          dtype_cos_sin, 0, (cudaStream_t)stream);
+}
+
+int fastmax_qkv_prologue_bwd(const void* dq, const void* dk, const void* dv, const void* cos, const void* sin, void* dqkv,
+                             int B, int T, int n_query_groups, int q_per_kv, int head_size, int rope_n_elem, int dtype,
+                             int dtype_cos_sin, void* stream) {
+  fm::status().launches = 0;
+  fm::status().cuda_err[0] = 0;
+  if (!dqkv || !dq || !dk || !dv || (rope_n_elem > 0 && (!cos || !sin))) return FASTMAX_ERR_BAD_ARG;
+  if ((dtype != FASTMAX_DTYPE_BF16 && dtype != FASTMAX_DTYPE_F32) ||
+      (dtype_cos_sin != FASTMAX_DTYPE_BF16 && dtype_cos_sin != FASTMAX_DTYPE_F32))
+    return FASTMAX_ERR_BAD_ARG;
+  return fm::qkv_prologue(dqkv, cos, sin, const_cast<void*>(dq), const_cast<void*>(dk), const_cast<void*>(dv), B, T,
+                          n_query_groups, q_per_kv, head_size, rope_n_elem, dtype, dtype_cos_sin, 1, (cudaStream_t)stream);
+}
+
 // ---- recurrent inference state ---------------------------------------------------------------
 size_t fastmax_decode_state_bytes(int B, int H, int D, int p) {
   if (B <= 0 || H <= 0 || D <= 0 || D > 128 || (p != 1 && p != 2)) return 0;

@@ -57,7 +57,17 @@ struct Problem {
   // forward states kept for backward (fastmax_fwd_ex / fastmax_bwd_ex): forward writes its boundary
   // states here instead of into the workspace; backward reads them instead of rebuilding them
   void* saved_states = nullptr;
+  // grouped-query attention (lit_gpt/model.py:408-416): k, v are (B, Hkv, N, D) and every group of H / Hkv query
+  // heads shares one (b, kv head).  0 = no grouping (Hkv == H).  Moment path only (fastmax_*_gqa).
+  int Hkv = 0;
+  int kv_heads() const { return Hkv > 0 ? Hkv : H; }
 };
+
+// index of the (b, kv head) that query head bh = b * H + h reads: head h belongs to group h / (H / Hkv), the
+// order in which model.py:418-420 flattens (B, n_query_groups, q_per_kv, T, hs)
+__host__ __device__ __forceinline__ int kv_index(int bh, int H, int Hkv) {
+  return Hkv == H ? bh : (bh / H) * Hkv + (bh % H) / (H / Hkv);
+}
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -99,6 +109,9 @@ int intra_dkdv(const Problem& pb, int L, int Npad, const void* k, const void* v,
 bool seg_fwd_usable(const Problem& pb, int L);
 int seg_fwd(const Problem& pb, int L, const void* q, const void* k, const void* v, float* o_part, float* g,
             const uint8_t* state);
+// fused q/k/v assembly in front of the op (fm_prologue.cu; model.py:392-425) and its transpose
+int qkv_prologue(const void* qkv, const void* cos, const void* sin, void* q, void* k, void* v, int B, int T, int G,
+                 int qpk, int hs, int rope_n, int dtype, int dtype_cs, int backward, cudaStream_t stream);
 namespace mom { struct ApplyDesc; }
 int launch_apply_gen(const Problem& pb, int BH, int nrec, const char* name, const mom::ApplyDesc& d, int variant);
 // first-order causal FastMax as one fused scan per (b,h) (fm_p1scan.cu)
@@ -138,14 +151,14 @@ int decode_attend(const void* state, const void* q, void* o, int B, int H, int T
                   float count_term, int dtype, cudaStream_t stream);
 int moments_seg_len(int B, int H, int N, int p);
 size_t moments_state_bytes(int B, int H);
-size_t moments_saved_state_bytes(int B, int H, int N, int p, int causal);
+size_t moments_saved_state_bytes(int B, int H, int N, int p, int causal, int Hkv = 0);
 size_t moments_local_state_workspace_bytes(int B, int H, int N);
 int moments_local_state(const Problem& pb, const void* x, const void* w, const void* w2, void* state_out, void* ws);
 int moments_local_state_rev(const Problem& pb, const void* q, const void* o, const float* g, const void* d_o,
                             void* state_out, void* ws);
 size_t moments_local_state_rev_workspace_bytes(int B, int H, int N);
 int moments_reduce_states(const void* gathered, int G, int rank, int dir, void* out, int B, int H, cudaStream_t stream);
-size_t moments_workspace_bytes(int B, int H, int N, int p, int causal, bool bwd);
+size_t moments_workspace_bytes(int B, int H, int N, int p, int causal, bool bwd, int Hkv = 0);
 void moments_flops(int B, int H, int N, int p, int causal, double* fwd, double* bwd, double* rebuild);
 int moments_fwd(const Problem& pb, const void* q, const void* k, const void* v, void* o, float* g, void* ws);
 int moments_bwd(const Problem& pb, const void* q, const void* k, const void* v, const void* o, const float* g,

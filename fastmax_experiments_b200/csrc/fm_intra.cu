@@ -47,6 +47,7 @@ struct IntraParams {
                            // is applied (g; the -dlt(N1 + a N2 q) part of dq; the RN1 + a RN2 k part of dk)
   int edge_state;          // sequence parallel: the first (FWD, DQ) / last (DKDV) local segment has a state too
   float count_offset;      // tokens of earlier ranks (normaliser count term)
+  int H, Hkv;              // grouped-query attention: query heads / kv heads per batch entry (fm_common.cuh kv_index)
 };
 
 template <int MODE> struct IntraCfg {
@@ -172,7 +173,12 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
   const bool has_norm =
       P.state != nullptr &&
       (P.noncausal || (MODE == INTRA_DKDV ? (seg < P.nseg - 1 || P.edge_state) : (seg > 0 || P.edge_state)));
-  const int rec_idx = P.noncausal ? bh : bh * P.nseg + seg;
+  // grouped queries: k, v and the forward states belong to the (b, kv head); q, u, dlt, the reverse states and every
+  // output to the query head.  FWD / DQ: resident = q (, u), streamed = k, v; DKDV: resident = k, v, streamed = q, u
+  const int kvh = kv_index(bh, P.H, P.Hkv);
+  const int bh_res = MODE == INTRA_DKDV ? kvh : bh, bh_str = MODE == INTRA_DKDV ? bh : kvh;
+  const int bh_st = MODE == INTRA_DKDV ? bh : kvh;
+  const int rec_idx = P.noncausal ? bh_st : bh_st * P.nseg + seg;
 
   if (warp == 0) {
     tmem_alloc(tmem_slot, 512);
@@ -219,17 +225,17 @@ intra_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ C
       if (has_norm) tma_load_3d(norm_s, &tmS, res_full, 0, (P.fused ? 64 : 65) * 64, rec_idx);
       for (int o = 0; o < C::OUT_TILES; ++o)
         for (int h = 0; h < 2; ++h) {
-          tma_load_3d(res + o * 16384 + h * 8192, &tmR1, res_full, 0, c0 + o * 128 + h * 64, bh);
+          tma_load_3d(res + o * 16384 + h * 8192, &tmR1, res_full, 0, c0 + o * 128 + h * 64, bh_res);
           if (C::RES_OPS == 2)
-            tma_load_3d(res + (C::OUT_TILES + o) * 16384 + h * 8192, &tmR2, res_full, 0, c0 + o * 128 + h * 64, bh);
+            tma_load_3d(res + (C::OUT_TILES + o) * 16384 + h * 8192, &tmR2, res_full, 0, c0 + o * 128 + h * 64, bh_res);
         }
       for (int jt = 0; jt < nstream; ++jt) {
         const int st = jt % C::STAGES, ph = (jt / C::STAGES) & 1;
         mbar_wait(&empty[st], ph ^ 1);
         uint8_t* sp = ring + st * C::STAGE_STRIDE;
         mbar_arrive_expect_tx(&full[st], C::STAGE_BYTES);
-        tma_load_3d(sp, &tmT1, &full[st], 0, st0 + jt * 64, bh);
-        tma_load_3d(sp + 8192, &tmT2, &full[st], 0, st0 + jt * 64, bh);
+        tma_load_3d(sp, &tmT1, &full[st], 0, st0 + jt * 64, bh_str);
+        tma_load_3d(sp + 8192, &tmT2, &full[st], 0, st0 + jt * 64, bh_str);
         if (MODE == INTRA_DKDV) {
           const float* src = P.dlt + (size_t)bh * P.Npad + st0 + jt * 64;
           asm volatile(
@@ -632,11 +638,12 @@ static int launch_intra_t(const Problem& pb, int L, int Npad, const void* r1, co
                           const void* t2, const float* dlt, float* out0, float* out1, float* g,
                           const uint8_t* state, const char* name, void* final0 = nullptr, void* final1 = nullptr) {
   using C = IntraCfg<MODE>;
-  const int BH = pb.B * pb.H;
+  const int BH = pb.B * pb.H, BHkv = pb.B * pb.kv_heads();
+  const int BHres = MODE == INTRA_DKDV ? BHkv : BH, BHstr = MODE == INTRA_DKDV ? BH : BHkv;
   CUtensorMap m[4];
   const void* ptr[4] = {r1, r2 ? r2 : r1, t1, t2};
   for (int i = 0; i < 4; ++i) {
-    int rc = make_tmap_bf16_3d(&m[i], ptr[i], 64, pb.N, BH, 128, (uint64_t)pb.N * 128, 64, 64);
+    int rc = make_tmap_bf16_3d(&m[i], ptr[i], 64, pb.N, i < 2 ? BHres : BHstr, 128, (uint64_t)pb.N * 128, 64, 64);
     if (rc) return rc;
   }
   IntraParams P{};
@@ -646,10 +653,12 @@ static int launch_intra_t(const Problem& pb, int L, int Npad, const void* r1, co
   P.nseg = pb.causal ? (pb.N + L - 1) / L : 1;
   P.edge_state = MODE == INTRA_DKDV ? pb.sp_init_rev != nullptr : pb.sp_init_fwd != nullptr;
   P.count_offset = (float)pb.sp_offset;
+  P.H = pb.H, P.Hkv = pb.kv_heads();
   P.state = (P.nseg > 1 || P.edge_state || P.noncausal) ? state : nullptr;
   CUtensorMap tmS = m[0];
   if (P.state) {
-    int rc = make_tmap_bf16_3d(&tmS, state, 64, NSLAB * 64, (uint64_t)BH * P.nseg, 128, REC_BYTES, 64, 64);
+    int rc = make_tmap_bf16_3d(&tmS, state, 64, NSLAB * 64, (uint64_t)(MODE == INTRA_DKDV ? BH : BHkv) * P.nseg, 128,
+                               REC_BYTES, 64, 64);
     if (rc) return rc;
   }
   CUtensorMap tmB0 = m[0], tmB1 = m[0];   // bf16 outputs of the fused p = 1 mode (fp32 partials are plain bulk copies)

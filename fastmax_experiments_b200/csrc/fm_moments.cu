@@ -552,6 +552,8 @@ struct ApplyParams {
   float coef_reg, coef64, out_scale;
   int vec_sel;              // -1 none, 0: vec[0:64), 1: vec[64:128)
   int edge_state;           // sequence parallel: first (forward states) / last (reverse) local segment has a state
+  int H, Hkv;               // grouped-query attention: heads per batch entry of the outputs / of k, v
+  int state_kv, xy_kv;      // 1: the state records / the X and Y operands are indexed by (b, kv head)
   const bf16* X;            // per-token scalars
   const float* partial;     // (BH, N, 64) fp32 intra-segment partial (nullable)
   const float* gden;        // (BH, N) fp32: divide rows by it (forward) (nullable)
@@ -602,7 +604,9 @@ apply_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CU
   const int seg = t0 / P.L;
   const bool has_state =
       !P.causal || (P.state_reverse ? (seg < P.nseg - 1 || P.edge_state) : (seg > 0 || P.edge_state));
-  const int rec_idx = P.causal ? bh * P.nseg + seg : bh;
+  const int kvh = kv_index(bh, P.H, P.Hkv);
+  const int bh_st = P.state_kv ? kvh : bh, bh_xy = P.xy_kv ? kvh : bh;
+  const int rec_idx = P.causal ? bh_st * P.nseg + seg : bh_st;
   const int ngroups = (P.p == 2 ? 32 : 0) + 1;     // 32 pairs of second-order slabs + slab 64
 
   if (warp == 18) {
@@ -650,7 +654,7 @@ apply_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CU
       auto load_tile = [&](int t) {
         mbar_arrive_expect_tx(&res_full[t], 16384);
         for (int h = 0; h < 2; ++h)
-          tma_load_3d(res + t * 16384 + h * 8192, &tmY, &res_full[t], 0, t0 + t * 128 + h * 64, bh);
+          tma_load_3d(res + t * 16384 + h * 8192, &tmY, &res_full[t], 0, t0 + t * 128 + h * 64, bh_xy);
       };
       load_tile(0);
       for (int gi = 0; gi < ngroups; ++gi) {
@@ -710,7 +714,7 @@ apply_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CU
     // (the normaliser of the row is fetched here, not in the tail where its latency would be exposed)
     const float inv_g = (valid && P.gden) ? 1.f / __ldg(P.gden + grow) : 1.f;
     if (has_state) {
-      const uint32_t* xrow = reinterpret_cast<const uint32_t*>(P.X + (valid ? grow : 0) * 64);
+      const uint32_t* xrow = reinterpret_cast<const uint32_t*>(P.X + (valid ? (size_t)bh_xy * P.N + i : 0) * 64);
       // the pair of X coefficients of the NEXT group is fetched one iteration ahead (ncu: 8 % of the
       // kernel's stall samples sat on this load when it was issued at the point of use)
       uint32_t xw_next = (valid && ngroups > 1) ? __ldg(xrow) : 0u;
@@ -815,6 +819,34 @@ __global__ void __launch_bounds__(256) prep_bwd_kernel(const bf16* __restrict__ 
   if (c == 0) dlt[(row / N) * Npad + row % N] = dl;   // (BH, Npad) layout, pad stays zero
 }
 
+// =============================================================================================
+// grouped queries: dk, dv of a (b, kv head) = sum over the query heads of its group (fp32 sum of the bf16 rows).
+// HBM-bound: reads 2 x (q_per_kv x N x 64) bf16 and writes 2 x (N x 64) per (b, kv head).
+// =============================================================================================
+__global__ void __launch_bounds__(256) group_sum_kernel(const bf16* __restrict__ dk_h, const bf16* __restrict__ dv_h,
+                                                        bf16* __restrict__ dk, bf16* __restrict__ dv, int q_per_kv, int N,
+                                                        size_t n8) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;       // chunk of 8 features of one (b, kv head, token)
+  if (i >= n8) return;
+  const size_t per_head = (size_t)N * 8;
+  const size_t kvh = i / per_head, rem = i % per_head;
+#pragma unroll
+  for (int which = 0; which < 2; ++which) {
+    const uint4* src = reinterpret_cast<const uint4*>(which ? dv_h : dk_h) + kvh * q_per_kv * per_head + rem;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int h = 0; h < q_per_kv; ++h) {
+      const uint4 x = __ldg(src + (size_t)h * per_head);
+      const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[2 * j] += __uint_as_float(w[j] << 16), acc[2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+    }
+    uint4 o;
+    o.x = pack_bf16x2(acc[0], acc[1]), o.y = pack_bf16x2(acc[2], acc[3]);
+    o.z = pack_bf16x2(acc[4], acc[5]), o.w = pack_bf16x2(acc[6], acc[7]);
+    reinterpret_cast<uint4*>(which ? dv : dk)[i] = o;
+  }
+}
+
 }  // namespace mom
 
 // =============================================================================================
@@ -823,13 +855,20 @@ __global__ void __launch_bounds__(256) prep_bwd_kernel(const bf16* __restrict__ 
 using namespace mom;
 
 struct MomLayout {
-  int BH, N, Npad, L, nseg, nrec;
-  size_t off_xt, off_xt2, off_state, off_state2, off_part, off_part2, off_part3, off_u, off_qd, off_dlt, total;
+  int BH, BHkv, N, Npad, L, nseg, nrec;   // BHkv: (b, kv head) pairs = owners of k, v and of the forward states
+  size_t off_xt, off_xt2, off_state, off_state2, off_part, off_part2, off_part3, off_u, off_qd, off_dlt;
+  size_t off_dkh, off_dvh;                // grouped queries: per-query-head dk, dv before the sum over the group
+  size_t total;
+  MomLayout kv() const {                  // the same layout seen by the kernels that run once per (b, kv head)
+    MomLayout k = *this;
+    k.BH = BHkv;
+    return k;
+  }
 };
 
-static MomLayout mom_layout(int B, int H, int N, int L, int causal, bool bwd) {
+static MomLayout mom_layout(int B, int H, int N, int L, int causal, bool bwd, int Hkv = 0) {
   MomLayout m{};
-  m.BH = B * H, m.N = N, m.Npad = (int)align_up(N, 64), m.L = L;
+  m.BH = B * H, m.BHkv = B * (Hkv > 0 ? Hkv : H), m.N = N, m.Npad = (int)align_up(N, 64), m.L = L;
   m.nseg = (N + L - 1) / L;
   m.nrec = causal ? m.nseg : 1;
   size_t off = 0;
@@ -840,8 +879,8 @@ static MomLayout mom_layout(int B, int H, int N, int L, int causal, bool bwd) {
   };
   const size_t tens = (size_t)m.BH * N * 64;
   const size_t part_floats = (size_t)m.BH * ((N + 127) / 128) * PART_TILE_FLOATS;   // whole 128-token tiles
-  m.off_xt = take((size_t)m.BH * 64 * m.Npad * 2);
-  m.off_state = take((size_t)m.BH * m.nrec * REC_BYTES);
+  m.off_xt = take((size_t)m.BHkv * 64 * m.Npad * 2);
+  m.off_state = take((size_t)m.BHkv * m.nrec * REC_BYTES);
   m.off_part = take(part_floats * 4);
   if (bwd) {
     m.off_xt2 = take((size_t)m.BH * 64 * m.Npad * 2);
@@ -851,6 +890,7 @@ static MomLayout mom_layout(int B, int H, int N, int L, int causal, bool bwd) {
     m.off_u = take(tens * 2);
     m.off_qd = take(tens * 2);
     m.off_dlt = take((size_t)m.BH * m.Npad * 4);
+    if (m.BHkv != m.BH) m.off_dkh = take(tens * 2), m.off_dvh = take(tens * 2);
   }
   m.total = off;
   return m;
@@ -870,8 +910,8 @@ int moments_seg_len(int B, int H, int N, int p) {
   return L;
 }
 
-size_t moments_workspace_bytes(int B, int H, int N, int p, int causal, bool bwd) {
-  return mom_layout(B, H, N, moments_seg_len(B, H, N, p), causal, bwd).total;
+size_t moments_workspace_bytes(int B, int H, int N, int p, int causal, bool bwd, int Hkv) {
+  return mom_layout(B, H, N, moments_seg_len(B, H, N, p), causal, bwd, Hkv).total;
 }
 
 // developer switch: FASTMAX_P1=chunked keeps first-order causal problems on the chunked scan (round-1 path)
@@ -962,7 +1002,7 @@ static int apply_variant() {
 }
 
 static int launch_apply(const Problem& pb, const MomLayout& m, const char* name, ApplyParams P, const void* Y) {
-  if (apply_variant() >= 0 && pb.p == 2) {
+  if (apply_variant() >= 0 && pb.p == 2 && m.BHkv == m.BH) {
     ApplyDesc d{};
     d.L = m.L, d.nseg = m.nseg, d.state_reverse = P.state_reverse, d.b_kmajor = P.b_kmajor, d.edge_state = P.edge_state;
     d.vec_sel = P.vec_sel, d.coef_reg = P.coef_reg, d.coef64 = P.coef64, d.out_scale = P.out_scale;
@@ -971,8 +1011,12 @@ static int launch_apply(const Problem& pb, const MomLayout& m, const char* name,
   }
   CUtensorMap tmS, tmY, tmOut;
   int rc;
-  if ((rc = make_tmap_bf16_3d(&tmS, P.state, 64, NSLAB * 64, (uint64_t)m.BH * m.nrec, 128, REC_BYTES, 64, 64))) return rc;
-  if ((rc = make_tmap_bf16_3d(&tmY, Y, 64, m.N, m.BH, 128, (uint64_t)m.N * 128, 64, 64))) return rc;
+  // grouped queries: forward states (o, dq) and the k, v operands (dv, dk) live once per (b, kv head)
+  P.H = pb.H, P.Hkv = pb.kv_heads();
+  P.state_kv = P.mode == APPLY_FWD || P.mode == APPLY_DQ, P.xy_kv = !P.state_kv;
+  const uint64_t bh_st = P.state_kv ? m.BHkv : m.BH, bh_xy = P.xy_kv ? m.BHkv : m.BH;
+  if ((rc = make_tmap_bf16_3d(&tmS, P.state, 64, NSLAB * 64, bh_st * m.nrec, 128, REC_BYTES, 64, 64))) return rc;
+  if ((rc = make_tmap_bf16_3d(&tmY, Y, 64, m.N, bh_xy, 128, (uint64_t)m.N * 128, 64, 64))) return rc;
   if ((rc = make_tmap_bf16_3d(&tmOut, P.out, 64, m.N, m.BH, 128, (uint64_t)m.N * 128, 64, 64))) return rc;
   P.N = m.N, P.L = m.L, P.nseg = m.nseg, P.causal = pb.causal, P.p = pb.p;
   FM_CUDA(cudaFuncSetAttribute(apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A_SMEM));
@@ -983,7 +1027,9 @@ static int launch_apply(const Problem& pb, const MomLayout& m, const char* name,
 
 
 int moments_fwd(const Problem& pb, const void* q, const void* k, const void* v, void* o, float* g, void* ws) {
-  const MomLayout m = mom_layout(pb.B, pb.H, pb.N, moments_seg_len(pb.B, pb.H, pb.N, pb.p), pb.causal, false);
+  const MomLayout m = mom_layout(pb.B, pb.H, pb.N, moments_seg_len(pb.B, pb.H, pb.N, pb.p), pb.causal, false, pb.Hkv);
+  Problem pk = pb;                 // the problem as the per-(b, kv head) kernels see it
+  pk.H = pb.kv_heads(), pk.Hkv = 0;
   uint8_t* w8 = (uint8_t*)ws;
   int rc;
   const float a = pb.inv_c;
@@ -992,8 +1038,8 @@ int moments_fwd(const Problem& pb, const void* q, const void* k, const void* v, 
   if (p1_scan_enabled() && p1full_usable(pb)) return p1full_fwd(pb, q, k, v, o, g, state);
   float* part = (float*)(w8 + m.off_part);
   // 1. K^T and the boundary states (forward direction)
-  if ((rc = launch_transpose(pb, k, w8 + m.off_xt, m.Npad))) return rc;
-  if ((rc = launch_build(pb, m, w8 + m.off_xt, v, k, state, 0, pb.sp_init_fwd))) return rc;
+  if ((rc = launch_transpose(pk, k, w8 + m.off_xt, m.Npad))) return rc;
+  if ((rc = launch_build(pk, m.kv(), w8 + m.off_xt, v, k, state, 0, pb.sp_init_fwd))) return rc;
   // 2. intra-segment part (causal only) and the normaliser
   // intra-segment scores + the normaliser (its moment part rides along as one more score MMA); non-causal:
   // only that MMA runs (no intra-segment part, no partial)
@@ -1015,7 +1061,10 @@ int moments_fwd(const Problem& pb, const void* q, const void* k, const void* v, 
 
 int moments_bwd(const Problem& pb, const void* q, const void* k, const void* v, const void* o, const float* g,
                 const void* d_o, void* dq, void* dk, void* dv, void* ws) {
-  const MomLayout m = mom_layout(pb.B, pb.H, pb.N, moments_seg_len(pb.B, pb.H, pb.N, pb.p), pb.causal, true);
+  const MomLayout m = mom_layout(pb.B, pb.H, pb.N, moments_seg_len(pb.B, pb.H, pb.N, pb.p), pb.causal, true, pb.Hkv);
+  Problem pk = pb;                 // the problem as the per-(b, kv head) kernels see it
+  pk.H = pb.kv_heads(), pk.Hkv = 0;
+  const bool grouped = m.BHkv != m.BH;
   uint8_t* w8 = (uint8_t*)ws;
   int rc;
   const float a = pb.inv_c;
@@ -1047,8 +1096,8 @@ int moments_bwd(const Problem& pb, const void* q, const void* k, const void* v, 
                 (const bf16*)q, (const bf16*)o, (const bf16*)d_o, g, u, dlt, qd, rows, m.N, m.Npad));
   // 2. forward-direction states of (k, v) (recomputed, not saved) and reverse-direction states of (q, u)
   if (!pb.saved_states) {
-    if ((rc = launch_transpose(pb, k, w8 + m.off_xt, m.Npad))) return rc;
-    if ((rc = launch_build(pb, m, w8 + m.off_xt, v, k, S, 0, pb.sp_init_fwd))) return rc;
+    if ((rc = launch_transpose(pk, k, w8 + m.off_xt, m.Npad))) return rc;
+    if ((rc = launch_build(pk, m.kv(), w8 + m.off_xt, v, k, S, 0, pb.sp_init_fwd))) return rc;
   }
   if ((rc = launch_transpose(pb, q, w8 + m.off_xt2, m.Npad))) return rc;
   if ((rc = launch_build(pb, m, w8 + m.off_xt2, u, qd, R, 1, pb.sp_init_rev))) return rc;
@@ -1070,8 +1119,12 @@ int moments_bwd(const Problem& pb, const void* q, const void* k, const void* v, 
   ap = ApplyParams{};
   ap.mode = APPLY_DV, ap.state_reverse = 1, ap.b_kmajor = 0, ap.edge_state = pb.sp_init_rev != nullptr;
   ap.coef_reg = 0.5f * a * a, ap.coef64 = a, ap.out_scale = 1.f, ap.vec_sel = 0;
+  // grouped queries: dk, dv of every query head first (its own reverse states against the shared k, v), then the
+  // sum over the group -- what autograd does with the expand() of model.py:408-416, without the expanded copies
+  bf16* dk_h = grouped ? (bf16*)(w8 + m.off_dkh) : (bf16*)dk;
+  bf16* dv_h = grouped ? (bf16*)(w8 + m.off_dvh) : (bf16*)dv;
   ap.X = (const bf16*)k, ap.partial = pb.causal ? dv_part : nullptr, ap.gden = nullptr;
-  ap.out = (bf16*)dv, ap.state = R;
+  ap.out = dv_h, ap.state = R;
   if ((rc = launch_apply(pb, m, "mom_apply_dv", ap, k))) return rc;
 
   ap = ApplyParams{};
@@ -1079,8 +1132,15 @@ int moments_bwd(const Problem& pb, const void* q, const void* k, const void* v, 
   ap.mode = APPLY_DK, ap.state_reverse = 1, ap.b_kmajor = 1, ap.edge_state = pb.sp_init_rev != nullptr;
   ap.coef_reg = a, ap.coef64 = 1.f, ap.out_scale = a, ap.vec_sel = -1;
   ap.X = (const bf16*)k, ap.partial = dk_part, ap.gden = nullptr;
-  ap.out = (bf16*)dk, ap.state = R;
-  return launch_apply(pb, m, "mom_apply_dk", ap, v);
+  ap.out = dk_h, ap.state = R;
+  if ((rc = launch_apply(pb, m, "mom_apply_dk", ap, v))) return rc;
+  if (grouped) {
+    const size_t n8 = (size_t)m.BHkv * m.N * 8;       // 16-byte chunks of one output tensor
+    FM_LAUNCH("mom_group_sum", pb.stream,
+              group_sum_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, pb.stream>>>(dk_h, dv_h, (bf16*)dk, (bf16*)dv,
+                                                                                   pb.H / pb.kv_heads(), m.N, n8));
+  }
+  return FASTMAX_OK;
 }
 
 // =============================================================================================
@@ -1088,9 +1148,9 @@ int moments_bwd(const Problem& pb, const void* q, const void* k, const void* v, 
 // =============================================================================================
 size_t moments_state_bytes(int B, int H) { return (size_t)B * H * REC_BYTES; }
 
-size_t moments_saved_state_bytes(int B, int H, int N, int p, int causal) {
-  const MomLayout m = mom_layout(B, H, N, moments_seg_len(B, H, N, p), causal, false);
-  return (size_t)m.BH * m.nrec * REC_BYTES;
+size_t moments_saved_state_bytes(int B, int H, int N, int p, int causal, int Hkv) {
+  const MomLayout m = mom_layout(B, H, N, moments_seg_len(B, H, N, p), causal, false, Hkv);
+  return (size_t)m.BHkv * m.nrec * REC_BYTES;
 }
 
 size_t moments_local_state_workspace_bytes(int B, int H, int N) {

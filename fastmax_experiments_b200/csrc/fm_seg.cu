@@ -60,6 +60,7 @@ struct Descs {
 
 struct Params {
   int N, L, nseg, edge_state;
+  int H, Hkv;                // grouped-query attention (fm_common.cuh kv_index): k, v and the states per (b, kv head)
   float a, count_offset;
   float* out;                // blocked fp32 partial
   float* g;
@@ -142,7 +143,8 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
   const int tq = min(QT, (P.N - c0 + 127) / 128);                     // live q tiles
   const int nstream = joff + tq;                                      // stream tiles [st0, c0 + 128 tq)
   const bool has_norm = P.state != nullptr && (seg > 0 || P.edge_state);
-  const int rec_idx = bh * P.nseg + seg;
+  const int kvh = kv_index(bh, P.H, P.Hkv);
+  const int rec_idx = kvh * P.nseg + seg;
   const bool whole = tq == QT && joff == 0;
   // pairs (j, t), j ascending, t = max(0, j - joff) .. tq-1
   auto tmin = [&](int j) { return max(0, j - joff); };
@@ -155,10 +157,10 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
     const int s = j % NST;
     mbar_arrive_expect_tx(&full[s], STAGE);
     uint8_t* dst = smem + OFF_RING + s * STAGE;
-    tma_load_3d(dst, &tmK, &full[s], 0, st0 + j * 128, bh);
+    tma_load_3d(dst, &tmK, &full[s], 0, st0 + j * 128, kvh);
 #pragma unroll
     for (int m = 0; m < 8; ++m)
-      tma_load_3d(dst + 16384 + m * 2048, &tmV, &full[s], 0, st0 + j * 128 + 16 * (m >> 1) + 64 * (m & 1), bh);
+      tma_load_3d(dst + 16384 + m * 2048, &tmV, &full[s], 0, st0 + j * 128 + 16 * (m >> 1) + 64 * (m & 1), kvh);
   };
   if (warp == NCW) {
     // ---------------------------------------------------------------- TMA producer, first part
@@ -432,18 +434,19 @@ bool seg_fwd_usable(const Problem& pb, int L) {
 // drop-in for intra_fwd (p = 2, causal): o_part fp32 blocked partial, g, boundary states (nullable)
 int seg_fwd(const Problem& pb, int L, const void* q, const void* k, const void* v, float* o_part, float* g,
             const uint8_t* state) {
-  const int BH = pb.B * pb.H;
+  const int BH = pb.B * pb.H, BHkv = pb.B * pb.kv_heads();
   CUtensorMap tQ, tK, tV, tS;
   int rc;
   if ((rc = make_tmap_bf16_3d(&tQ, q, 64, pb.N, BH, 128, (uint64_t)pb.N * 128, 64, 128))) return rc;
-  if ((rc = make_tmap_bf16_3d(&tK, k, 64, pb.N, BH, 128, (uint64_t)pb.N * 128, 64, 128))) return rc;
-  if ((rc = make_tmap_bf16_3d(&tV, v, 64, pb.N, BH, 128, (uint64_t)pb.N * 128, 64, 16))) return rc;
+  if ((rc = make_tmap_bf16_3d(&tK, k, 64, pb.N, BHkv, 128, (uint64_t)pb.N * 128, 64, 128))) return rc;
+  if ((rc = make_tmap_bf16_3d(&tV, v, 64, pb.N, BHkv, 128, (uint64_t)pb.N * 128, 64, 16))) return rc;
   Params P{};
   P.N = pb.N, P.L = L, P.nseg = (pb.N + L - 1) / L, P.edge_state = pb.sp_init_fwd != nullptr;
   P.a = pb.inv_c, P.count_offset = (float)pb.sp_offset, P.out = o_part, P.g = g;
+  P.H = pb.H, P.Hkv = pb.kv_heads();
   P.state = (P.nseg > 1 || P.edge_state) ? state : nullptr;
   tS = tQ;
-  if (P.state && (rc = make_tmap_bf16_3d(&tS, state, 64, NSLAB * 64, (uint64_t)BH * P.nseg, 128, REC_BYTES, 64, 64))) return rc;
+  if (P.state && (rc = make_tmap_bf16_3d(&tS, state, 64, NSLAB * 64, (uint64_t)BHkv * P.nseg, 128, REC_BYTES, 64, 64))) return rc;
   Descs D{};
   const uint32_t base = sm100::FM_SMEM_BASE;
   for (int kk = 0; kk < 4; ++kk) {

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define FASTMAX_B200_ABI_VERSION 3
+#define FASTMAX_B200_ABI_VERSION 4
 
 /* error codes */
 #define FASTMAX_OK              0
@@ -116,6 +116,39 @@ int fastmax_bwd_ex(const void* q, const void* k, const void* v, const void* o, c
                    const void* d_o, void* dq, void* dk, void* dv, const void* saved_states,
                    int B, int H, int N, int D, int p, int causal, float inv_c, int dtype, int algo,
                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- grouped-query attention and the fused q/k/v prologue --------------------------------
+ * lit_gpt/model.py:408-416 copies k, v over the q_per_kv query heads of a group (expand + reshape) before the
+ * attention op sees them.  fastmax_*_gqa take k, v as (B, Hkv, N, D) instead: the forward moment states -- and the
+ * memory that keeping them costs -- exist once per (b, kv head) (H / Hkv times less state-update work), every
+ * kernel reads the shared rows in place, and dk, dv come back summed over the group, (B, Hkv, N, D): what autograd
+ * does with the expand(), without the expanded copies.  Query head h reads kv head h / (H / Hkv), the order of
+ * model.py:418-420.  Supported: bf16, D = 64, p = 2 (FASTMAX_ALGO_MOMENTS), causal or not; otherwise
+ * FASTMAX_ERR_UNSUPPORTED (the Python op then expands k, v and calls fastmax_fwd / fastmax_bwd).
+ * saved_states may be NULL (backward then rebuilds the forward states), else fastmax_gqa_saved_state_bytes bytes. */
+size_t fastmax_gqa_workspace_bytes(int B, int H, int Hkv, int N, int D, int p, int causal, int dtype, int backward);
+size_t fastmax_gqa_saved_state_bytes(int B, int H, int Hkv, int N, int D, int p, int causal, int dtype);
+int fastmax_fwd_gqa(const void* q, const void* k, const void* v, void* o, float* g, void* saved_states,
+                    int B, int H, int Hkv, int N, int D, int p, int causal, float inv_c, int dtype,
+                    void* workspace, size_t workspace_bytes, void* stream);
+int fastmax_bwd_gqa(const void* q, const void* k, const void* v, const void* o, const float* g, const void* d_o,
+                    void* dq, void* dk, void* dv, const void* saved_states,
+                    int B, int H, int Hkv, int N, int D, int p, int causal, float inv_c, int dtype,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* q/k/v assembly between the qkv projection and the attention call, lit_gpt/model.py:398-425 in one pass:
+ * qkv (B, T, n_query_groups, q_per_kv + 2, head_size) -> q (B, n_query_groups * q_per_kv, T, head_size),
+ * k, v (B, n_query_groups, T, head_size) (not expanded: see fastmax_*_gqa), rotary embedding (apply_rope,
+ * model.py:702-708) on the first rope_n_elem features of q and k with the caller's cos / sin tables
+ * (T, rope_n_elem).  Bit-exact against the reference's eager arithmetic (per-op rounding when the tables share the
+ * tensors' dtype, one rounding under fp32 promotion).  _bwd is its transpose: dq, dk, dv -> dqkv.
+ * Whole 16-byte chunks only: head_size and rope_n_elem / 2 multiples of 8 (bf16) / 4 (fp32), else UNSUPPORTED. */
+int fastmax_qkv_prologue(const void* qkv, const void* cos, const void* sin, void* q, void* k, void* v,
+                         int B, int T, int n_query_groups, int q_per_kv, int head_size, int rope_n_elem,
+                         int dtype, int dtype_cos_sin, void* stream);
+int fastmax_qkv_prologue_bwd(const void* dq, const void* dk, const void* dv, const void* cos, const void* sin,
+                             void* dqkv, int B, int T, int n_query_groups, int q_per_kv, int head_size,
+                             int rope_n_elem, int dtype, int dtype_cos_sin, void* stream);
 
 /* ---- sequence parallelism (no reference counterpart; BASELINE.json north_star) ----------
  * A long sequence is split by contiguous token ranges over the GPUs of one box.  Outputs are linear

@@ -219,6 +219,73 @@ def main_model() -> None:
         print(f"{name}: wrote {os.path.getsize(path)/1e6:.2f} MB  loss={float(loss):.6f} grad_norm={float(gnorm):.6f}")
 
 
+# grouped-query attention module of the reference (tiny-llama-1.1b preset, lit_gpt/config.py:1394-1410, shrunk:
+# 1 layer, 4 heads of 64 in 2 query groups), fp32 and bf16: q, k, v as the unmodified CausalSelfAttention.forward
+# hands them to its attention method (after view / permute / split / expand / reshape / RoPE, model.py:396-425), its
+# output, and the gradient it sends back into the qkv projection.  (name, T, seed, rotary_percentage)
+GQA_CASES = [
+    ("gqa_prologue_t256", 256, 41, 1.0),
+    ("gqa_prologue_t256_rot25", 256, 42, 0.25),
+]
+
+
+def main_gqa() -> None:
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    from oracle import ref_loader as rl
+
+    for name, T, seed, rot in GQA_CASES:
+        if NAMES and name not in NAMES:
+            continue
+        out = dict(T=T, seed=seed, rot=rot)
+        for dtype, tag in ((torch.float32, "f32"), (torch.bfloat16, "bf16")):
+            with rl.cuda_hop_neutralised():
+                model, cfg = rl.build_gpt("tiny-llama-1.1b", attn_alg="fastmax", block_size=T, seed=seed, n_layer=1,
+                                          n_embd=256, n_head=4, n_query_groups=2, intermediate_size=256,
+                                          rotary_percentage=rot)
+                model = model.to(dtype)
+                attn = model.transformer.h[0].attn
+                cap = {}
+                inner = attn.fastmax                      # the reference's own method; only observed, not replaced
+
+                def spy(q, k, v, input_pos, _inner=inner, _cap=cap):
+                    _cap["q"], _cap["k"], _cap["v"] = q, k, v
+                    q.retain_grad(), k.retain_grad(), v.retain_grad()
+                    return _inner(q, k, v, input_pos)
+                attn.fastmax = spy
+
+                def keep_qkv(m, i, o, _cap=cap):
+                    _cap["qkv"] = o
+                    o.retain_grad()
+                hook = attn.attn.register_forward_hook(keep_qkv)
+                g = torch.Generator().manual_seed(seed + 1)
+                x = torch.randn(1, T, cfg.n_embd, generator=g).to(dtype)
+                cos, sin = model.cos[:T].to(dtype), model.sin[:T].to(dtype)
+                y = attn(x, cos, sin)
+                dy = torch.randn(y.shape, generator=g).to(dtype)
+                y.backward(dy)
+                hook.remove()
+            q_per_kv = cfg.n_head // cfg.n_query_groups
+            k, v = cap["k"], cap["v"]
+            assert torch.equal(k[:, ::q_per_kv].repeat_interleave(q_per_kv, 1), k)      # the expand is a plain copy
+            enc = (lambda t: t.detach().numpy()) if dtype == torch.float32 else (lambda t: bf16_bits(t.detach().float()))
+            B_, Hh, T_, hs_ = k.shape
+            gsum = lambda t: t.grad.double().view(B_, Hh // q_per_kv, q_per_kv, T_, hs_).sum(2).float().numpy()
+            # (x and dy are re-created from the seed by the tests: torch.Generator().manual_seed(seed + 1), randn x then dy)
+            out.update({f"{tag}_qkv": enc(cap["qkv"]),
+                        f"{tag}_q": enc(cap["q"]), f"{tag}_k": enc(k[:, ::q_per_kv]), f"{tag}_v": enc(v[:, ::q_per_kv]),
+                        f"{tag}_y": enc(y), f"{tag}_dqkv": enc(cap["qkv"].grad),
+                        # upstream gradients of the prologue: dq as is, dk / dv summed over the group in fp64 (the
+                        # reference accumulates them in the working dtype inside autograd's expand backward)
+                        f"{tag}_dq": enc(cap["q"].grad),
+                        f"{tag}_dk": gsum(k), f"{tag}_dv": gsum(v),
+                        f"{tag}_cos": enc(cos), f"{tag}_sin": enc(sin)})
+            out.update(n_embd=cfg.n_embd, n_head=cfg.n_head, n_query_groups=cfg.n_query_groups, head_size=cfg.head_size,
+                       rope_n_elem=cfg.rope_n_elem)
+        path = os.path.join(OUT_DIR, name + ".npz")
+        np.savez_compressed(path, **out)
+        print(f"{name}: wrote {os.path.getsize(path)/1e6:.2f} MB")
+
+
 NAMES: set = set()
 
 if __name__ == "__main__":
@@ -231,6 +298,8 @@ if __name__ == "__main__":
         main_linearmax_rect()
     if which in ("all", "model"):
         main_model()
+    if which in ("all", "gqa"):
+        main_gqa()
     if which in ("all", "square"):
         main()
     if which in ("all", "rect") or "--rect-only" in sys.argv:

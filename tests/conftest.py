@@ -38,7 +38,7 @@ def _is_rect(n):
 
 def golden_names():
     """Square fixtures (q, k, v of one shape; forward + backward)."""
-    return [n for n in _all_golden() if not _is_rect(n) and not n.startswith(("linearmax", "model_"))]
+    return [n for n in _all_golden() if not _is_rect(n) and not n.startswith(("linearmax", "model_", "gqa_"))]
 
 
 def golden_rect_names():
@@ -54,6 +54,29 @@ def golden_linearmax_names():
 def golden_linearmax_rect_names():
     """linearmax over a KV cache (N_q != N_k, forward only; count term N_k, fastmax_hack.py:21)."""
     return [n for n in _all_golden() if n.startswith("linearmax") and _is_rect(n)]
+
+
+def golden_gqa_names():
+    """q/k/v assembly + grouped-query attention module of the reference (oracle/make_golden.py::main_gqa)."""
+    return [n for n in _all_golden() if n.startswith("gqa_")]
+
+
+def load_golden_gqa(name: str, tag: str) -> dict:
+    """tag: "f32" or "bf16" (the reference module run in that dtype).  Tensors come back in that dtype; dk, dv (sums
+    over the query group, taken in float64) as float32."""
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    dt = torch.float32 if tag == "f32" else torch.bfloat16
+    dec = (lambda a: torch.from_numpy(a)) if tag == "f32" else (lambda a: _from_bf16_bits(a).to(torch.bfloat16))
+    out = dict(name=name, dtype=dt, **{k: int(z[k]) for k in ("T", "seed", "n_embd", "n_head", "n_query_groups",
+                                                                  "head_size", "rope_n_elem")}, rot=float(z["rot"]))
+    for key in ("qkv", "q", "k", "v", "y", "dqkv", "dq", "cos", "sin"):
+        out[key] = dec(z[f"{tag}_{key}"])
+    for key in ("dk", "dv"):
+        out[key] = torch.from_numpy(z[f"{tag}_{key}"])
+    g = torch.Generator().manual_seed(out["seed"] + 1)       # as in the minting script: x, then dy
+    out["x"] = torch.randn(1, out["T"], out["n_embd"], generator=g).to(dt)
+    out["dy"] = torch.randn(out["y"].shape, generator=g).to(dt)
+    return out
 
 
 def golden_model_names():

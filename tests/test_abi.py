@@ -30,7 +30,7 @@ def test_library_builds_and_exports_header_symbols():
 
 def test_abi_version_and_error_strings():
     lib = _lib.load()
-    assert lib.fastmax_abi_version() == _lib.ABI_VERSION == 3
+    assert lib.fastmax_abi_version() == _lib.ABI_VERSION == 4
     assert lib.fastmax_error_string(0) == b"ok"
     assert b"unsupported" in lib.fastmax_error_string(_lib.ERR_UNSUPPORTED)
 
