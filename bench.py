@@ -193,7 +193,9 @@ def run_model(args, local: int) -> None:
     lora = LORA if name.startswith("Llama-2") else None
     rl.reference_model()
     from lit_gpt.model import CausalSelfAttention
-    patch_causal_self_attention(CausalSelfAttention)
+    # --fused: the one-pass q/k/v prologue + grouped-query states instead of model.py:396-451; for the
+    # LoRA model the projection is lit_gpt.lora's own class, so only the stock CausalSelfAttention is rebound
+    patch_causal_self_attention(CausalSelfAttention, fused=args.fused)
     model, cfg = rl.build_gpt(name, attn_alg="fastmax", block_size=T, lora=lora, device=dev, dtype=torch.bfloat16)
     opt = None
     if lora:
@@ -235,7 +237,8 @@ def run_model(args, local: int) -> None:
                                f"with fastmax p=2 causal attention on the CUDA path, B=1, seq {T}, forward+backward"
                                f"{' + AdamW step on the LoRA parameters' if lora else ''}",
                    "model": name, "seq": T, "n_layer": cfg.n_layer, "n_head": cfg.n_head,
-                   "n_query_groups": cfg.n_query_groups, "head_size": cfg.head_size, "attn_alg": "fastmax"},
+                   "n_query_groups": cfg.n_query_groups, "head_size": cfg.head_size, "attn_alg": "fastmax",
+                   "fused_prologue_gqa": bool(args.fused)},
         "clocks": clocks, "loss": float(loss), "gpu_launches": len(recs) * args.steps,
         "attention": {"ms_per_step": round(attn_ms, 3), "share_of_step": round(attn_ms / ms_step, 4),
                       "kernels": {n: {"launches": a[0], "ms": round(a[1], 3)} for n, a in
@@ -473,6 +476,8 @@ def main() -> None:
     ap.add_argument("--algo", default="auto", choices=["auto", "exact", "moments"])
     ap.add_argument("--seq", type=int, default=HL["N"], help="override N (diagnostics only)")
     ap.add_argument("--batch", type=int, default=HL["B"], help="override B (diagnostics only)")
+    ap.add_argument("--fused", action="store_true",
+                    help="--workload model: rebind CausalSelfAttention.forward to the fused prologue + grouped-query path")
     ap.add_argument("--workload", default="headline", choices=["headline", "sp", "model"],
                     help="headline: (b,h)-sharded op at B=8,H=32,N=16k (default); sp: sequence-parallel "
                          "long-context scan, B=1,H=32, --seq tokens split over the ranks (BASELINE config 5); "

@@ -782,41 +782,56 @@ apply_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CU
 // =============================================================================================
 // backward prep: u = do/g (bf16), dlt = (do.o)/g (fp32), qd = -dlt*q (bf16).  HBM-bound pass.
 // =============================================================================================
+constexpr int PREP_ROWS = 128;   // rows per CTA
 template <bool QD>   // QD = false: only u and dlt (the first-order scan kernels do not use qd and q is not read)
 __global__ void __launch_bounds__(256) prep_bwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ o,
                                                         const bf16* __restrict__ d_o, const float* __restrict__ g,
                                                         bf16* __restrict__ u, float* __restrict__ dlt,
                                                         bf16* __restrict__ qd, size_t rows, int N, int Npad) {
-  // eight threads per row, 16 bytes (8 features) each; 32 rows per CTA
-  const size_t row = (size_t)blockIdx.x * 32 + (threadIdx.x >> 3);
+  // eight threads per row, 16 bytes (8 features) each; a CTA covers 128 rows in four sweeps of 32 whose loads are all
+  // issued before the first use (four times the bytes in flight per thread: the pass is latency-bound otherwise)
+  constexpr int SW = PREP_ROWS / 32;
   const int c = threadIdx.x & 7;
-  const bool live = row < rows;
-  const size_t off = (live ? row : 0) * 64 + 8 * c;
-  const uint4 dv = __ldg(reinterpret_cast<const uint4*>(d_o + off));
-  const uint4 ov = __ldg(reinterpret_cast<const uint4*>(o + off));
-  const uint4 qv = QD ? __ldg(reinterpret_cast<const uint4*>(q + off)) : make_uint4(0u, 0u, 0u, 0u);
-  const float ig = 1.f / g[live ? row : 0];
-  const uint32_t dw[4] = {dv.x, dv.y, dv.z, dv.w}, ow[4] = {ov.x, ov.y, ov.z, ov.w}, qw[4] = {qv.x, qv.y, qv.z, qv.w};
-  float d[8], qf[8], s = 0.f;
+  uint4 dv[SW], ov[SW], qv[SW];
+  float gg[SW];
+  size_t row[SW];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    d[2 * j] = __uint_as_float(dw[j] << 16), d[2 * j + 1] = __uint_as_float(dw[j] & 0xffff0000u);
-    qf[2 * j] = __uint_as_float(qw[j] << 16), qf[2 * j + 1] = __uint_as_float(qw[j] & 0xffff0000u);
-    s = fmaf(d[2 * j], __uint_as_float(ow[j] << 16), s);
-    s = fmaf(d[2 * j + 1], __uint_as_float(ow[j] & 0xffff0000u), s);
+  for (int s = 0; s < SW; ++s) {
+    row[s] = (size_t)blockIdx.x * PREP_ROWS + 32 * s + (threadIdx.x >> 3);
+    const size_t off = (row[s] < rows ? row[s] : 0) * 64 + 8 * c;
+    dv[s] = __ldg(reinterpret_cast<const uint4*>(d_o + off));
+    ov[s] = __ldg(reinterpret_cast<const uint4*>(o + off));
+    qv[s] = QD ? __ldg(reinterpret_cast<const uint4*>(q + off)) : make_uint4(0u, 0u, 0u, 0u);
+    gg[s] = g[row[s] < rows ? row[s] : 0];
   }
 #pragma unroll
-  for (int x = 4; x; x >>= 1) s += __shfl_xor_sync(0xffffffffu, s, x);
-  const float dl = s * ig;
-  if (!live) return;
-  uint4 uo, qo;
-  uo.x = pack_bf16x2(d[0] * ig, d[1] * ig), uo.y = pack_bf16x2(d[2] * ig, d[3] * ig);
-  uo.z = pack_bf16x2(d[4] * ig, d[5] * ig), uo.w = pack_bf16x2(d[6] * ig, d[7] * ig);
-  qo.x = pack_bf16x2(-dl * qf[0], -dl * qf[1]), qo.y = pack_bf16x2(-dl * qf[2], -dl * qf[3]);
-  qo.z = pack_bf16x2(-dl * qf[4], -dl * qf[5]), qo.w = pack_bf16x2(-dl * qf[6], -dl * qf[7]);
-  *reinterpret_cast<uint4*>(u + off) = uo;
-  if (QD) *reinterpret_cast<uint4*>(qd + off) = qo;
-  if (c == 0) dlt[(row / N) * Npad + row % N] = dl;   // (BH, Npad) layout, pad stays zero
+  for (int s = 0; s < SW; ++s) {
+    const bool live = row[s] < rows;
+    const size_t off = (live ? row[s] : 0) * 64 + 8 * c;
+    const float ig = 1.f / gg[s];
+    const uint32_t dw[4] = {dv[s].x, dv[s].y, dv[s].z, dv[s].w}, ow[4] = {ov[s].x, ov[s].y, ov[s].z, ov[s].w};
+    const uint32_t qw[4] = {qv[s].x, qv[s].y, qv[s].z, qv[s].w};
+    float d[8], qf[8], sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      d[2 * j] = __uint_as_float(dw[j] << 16), d[2 * j + 1] = __uint_as_float(dw[j] & 0xffff0000u);
+      qf[2 * j] = __uint_as_float(qw[j] << 16), qf[2 * j + 1] = __uint_as_float(qw[j] & 0xffff0000u);
+      sum = fmaf(d[2 * j], __uint_as_float(ow[j] << 16), sum);
+      sum = fmaf(d[2 * j + 1], __uint_as_float(ow[j] & 0xffff0000u), sum);
+    }
+#pragma unroll
+    for (int x = 4; x; x >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, x);
+    const float dl = sum * ig;
+    if (!live) continue;
+    uint4 uo, qo;
+    uo.x = pack_bf16x2(d[0] * ig, d[1] * ig), uo.y = pack_bf16x2(d[2] * ig, d[3] * ig);
+    uo.z = pack_bf16x2(d[4] * ig, d[5] * ig), uo.w = pack_bf16x2(d[6] * ig, d[7] * ig);
+    qo.x = pack_bf16x2(-dl * qf[0], -dl * qf[1]), qo.y = pack_bf16x2(-dl * qf[2], -dl * qf[3]);
+    qo.z = pack_bf16x2(-dl * qf[4], -dl * qf[5]), qo.w = pack_bf16x2(-dl * qf[6], -dl * qf[7]);
+    *reinterpret_cast<uint4*>(u + off) = uo;
+    if (QD) *reinterpret_cast<uint4*>(qd + off) = qo;
+    if (c == 0) dlt[(row[s] / N) * Npad + row[s] % N] = dl;   // (BH, Npad) layout, pad stays zero
+  }
 }
 
 // =============================================================================================
@@ -1081,18 +1096,18 @@ int moments_bwd(const Problem& pb, const void* q, const void* k, const void* v, 
   FM_CUDA(cudaMemsetAsync(dlt, 0, (size_t)m.BH * m.Npad * 4, pb.stream));
   if (p1_scan_enabled() && p1scan_usable(pb)) {
     FM_LAUNCH("mom_prep_bwd", pb.stream,
-              prep_bwd_kernel<false><<<(unsigned)((rows + 31) / 32), 256, 0, pb.stream>>>(
+              prep_bwd_kernel<false><<<(unsigned)((rows + PREP_ROWS - 1) / PREP_ROWS), 256, 0, pb.stream>>>(
                   (const bf16*)q, (const bf16*)o, (const bf16*)d_o, g, u, dlt, qd, rows, m.N, m.Npad));
     return p1scan_bwd(pb, m.Npad, q, k, v, u, dlt, dq, dk, dv, w8 + m.off_state, R);
   }
   if (p1_scan_enabled() && p1full_usable(pb)) {
     FM_LAUNCH("mom_prep_bwd", pb.stream,
-              prep_bwd_kernel<false><<<(unsigned)((rows + 31) / 32), 256, 0, pb.stream>>>(
+              prep_bwd_kernel<false><<<(unsigned)((rows + PREP_ROWS - 1) / PREP_ROWS), 256, 0, pb.stream>>>(
                   (const bf16*)q, (const bf16*)o, (const bf16*)d_o, g, u, dlt, qd, rows, m.N, m.Npad));
     return p1full_bwd(pb, m.Npad, q, k, v, u, dlt, dq, dk, dv, S, pb.saved_states != nullptr, R);
   }
   FM_LAUNCH("mom_prep_bwd", pb.stream,
-            prep_bwd_kernel<true><<<(unsigned)((rows + 31) / 32), 256, 0, pb.stream>>>(
+            prep_bwd_kernel<true><<<(unsigned)((rows + PREP_ROWS - 1) / PREP_ROWS), 256, 0, pb.stream>>>(
                 (const bf16*)q, (const bf16*)o, (const bf16*)d_o, g, u, dlt, qd, rows, m.N, m.Npad));
   // 2. forward-direction states of (k, v) (recomputed, not saved) and reverse-direction states of (q, u)
   if (!pb.saved_states) {
@@ -1189,7 +1204,7 @@ int moments_local_state_rev(const Problem& pb_in, const void* q, const void* o, 
   const size_t rows = (size_t)m.BH * m.N;
   FM_CUDA(cudaMemsetAsync(dlt, 0, (size_t)m.BH * m.Npad * 4, pb.stream));
   FM_LAUNCH("mom_prep_bwd", pb.stream,
-            prep_bwd_kernel<true><<<(unsigned)((rows + 31) / 32), 256, 0, pb.stream>>>(
+            prep_bwd_kernel<true><<<(unsigned)((rows + PREP_ROWS - 1) / PREP_ROWS), 256, 0, pb.stream>>>(
                 (const bf16*)q, (const bf16*)o, (const bf16*)d_o, g, u, dlt, qd, rows, m.N, m.Npad));
   int rc;
   if ((rc = launch_transpose(pb, q, w8, m.Npad))) return rc;

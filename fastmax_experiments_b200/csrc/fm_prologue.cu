@@ -68,58 +68,70 @@ template <typename T, typename CS, bool BWD> __device__ __forceinline__ float rn
 
 // BWD = false:  y_i = x_i c_i - x_{i+h} s_i (i < h),  y_i = x_i c_i + x_{i-h} s_i (h <= i < 2h)      apply_rope :702-708
 // BWD = true :  dx_i = dy_i c_i + dy_{i+h} s_{i+h} (i < h),  dx_i = dy_i c_i - dy_{i-h} s_{i-h}        (its autograd)
+//
+// One thread moves TWO 16-byte chunks of a head row: inside the rotary part a chunk and its partner h elements
+// further (each is the other's "rotated" operand, so nothing is read twice), outside it two neighbouring pass-through
+// chunks.  32 bytes in flight per thread and 2048 threads per SM cover the HBM latency-bandwidth product.
 template <typename T, typename CS, bool BWD>
 __global__ void __launch_bounds__(256) qkv_kernel(const Params P) {
   constexpr int EL = Chunk<T>::EL;
-  const int cpr = P.hs / EL;                                  // chunks per head row
+  const int spr = P.hs / EL / 2;                              // two-chunk slots per head row
+  const int rope_slots = P.rope_n / EL / 2;                   // ... of which rotary
   const int rows_per_tok = P.G * (P.qpk + 2);
-  const size_t total = (size_t)P.B * P.T * rows_per_tok * cpr;
+  const size_t total = (size_t)P.B * P.T * rows_per_tok * spr;
   const size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x;
   if (idx >= total) return;
-  const int c = (int)(idx % cpr);
-  size_t row = idx / cpr;                                     // (b, t, g, j) in the projection's order
+  const int s = (int)(idx % spr);
+  size_t row = idx / spr;                                     // (b, t, g, j) in the projection's order
+  const size_t lin_row = row;
   const int j = (int)(row % (P.qpk + 2));
   row /= (P.qpk + 2);
   const int g = (int)(row % P.G);
   row /= P.G;
   const int t = (int)(row % P.T);
   const int b = (int)(row / P.T);
-  T* lin = (T*)P.qkv + idx * EL;                              // this chunk inside qkv / dqkv
+  T* lin = (T*)P.qkv + lin_row * P.hs;                        // this row inside qkv / dqkv
   T* head;                                                    // ... and inside q / k / v (dq / dk / dv)
   if (j < P.qpk) head = (T*)P.q + (((size_t)b * P.G * P.qpk + (size_t)g * P.qpk + j) * P.T + t) * P.hs;
   else head = (T*)(j == P.qpk ? P.k : P.v) + (((size_t)b * P.G + g) * P.T + t) * P.hs;
-  head += c * EL;
   const T* src = BWD ? head : lin;
   T* dst = BWD ? lin : head;
-  const int e0 = c * EL, h = P.rope_n / 2;
-  float x[EL];
-  load_chunk<T>(src, x);
-  if (j <= P.qpk && e0 < P.rope_n) {                          // q and k rows, rotary part (whole chunks: h % EL == 0)
-    const bool low = e0 < h;
-    float xp[EL], cs[EL], sn[EL];
-    load_chunk<T>(low ? src + h : src - h, xp);
-    // cos / sin of this chunk (forward) -- backward needs sin at the partner's position, which is the same value:
-    // build_rope_cache repeats the angles over the two halves (:697), but the caller's table is read as given
+  const int h = P.rope_n / 2;
+  const bool rotary = s < rope_slots;
+  // element offsets of the two chunks
+  const int e0 = rotary ? s * EL : P.rope_n + (s - rope_slots) * 2 * EL;
+  const int e1 = rotary ? e0 + h : e0 + EL;
+  float x0[EL], x1[EL];
+  load_chunk<T>(src + e0, x0);
+  load_chunk<T>(src + e1, x1);
+  if (rotary && j <= P.qpk) {                                 // q and k rows only
+    float c0[EL], c1[EL], s0[EL], s1[EL];
     const CS* ct = (const CS*)P.cos + (size_t)t * P.rope_n;
     const CS* st = (const CS*)P.sin + (size_t)t * P.rope_n;
+    // the caller's tables are read as given (build_rope_cache happens to repeat the angles over the two halves, :697)
     if constexpr (sizeof(CS) == sizeof(T)) {
-      load_chunk<CS>(ct + e0, cs);
-      load_chunk<CS>(st + (BWD ? (low ? e0 + h : e0 - h) : e0), sn);
+      load_chunk<CS>(ct + e0, c0), load_chunk<CS>(ct + e1, c1);
+      load_chunk<CS>(st + e0, s0), load_chunk<CS>(st + e1, s1);
     } else {                                                  // fp32 tables with bf16 tensors: two chunks of four
-      load_chunk<CS>(ct + e0, cs), load_chunk<CS>(ct + e0 + 4, cs + 4);
-      const int so = BWD ? (low ? e0 + h : e0 - h) : e0;
-      load_chunk<CS>(st + so, sn), load_chunk<CS>(st + so + 4, sn + 4);
+      load_chunk<CS>(ct + e0, c0), load_chunk<CS>(ct + e0 + 4, c0 + 4), load_chunk<CS>(ct + e1, c1), load_chunk<CS>(ct + e1 + 4, c1 + 4);
+      load_chunk<CS>(st + e0, s0), load_chunk<CS>(st + e0 + 4, s0 + 4), load_chunk<CS>(st + e1, s1), load_chunk<CS>(st + e1 + 4, s1 + 4);
     }
 #pragma unroll
     for (int i = 0; i < EL; ++i) {
-      const float a = rnd<T, CS, BWD>(__fmul_rn(x[i], cs[i]));
-      // forward: rotated = (-x2, x1);  backward: d/dx of the rotated term = (+dy2 s2, -dy1 s1)
-      const float pr = rnd<T, CS, BWD>(__fmul_rn(xp[i], sn[i]));
-      const float bterm = (low != BWD) ? -pr : pr;
-      x[i] = __fadd_rn(a, bterm);
+      const float lo = x0[i], hi = x1[i];
+      if constexpr (!BWD) {
+        // rotated = (-x2, x1):  y_lo = lo c_lo - hi s_lo ,  y_hi = hi c_hi + lo s_hi
+        x0[i] = __fadd_rn(rnd<T, CS, BWD>(__fmul_rn(lo, c0[i])), -rnd<T, CS, BWD>(__fmul_rn(hi, s0[i])));
+        x1[i] = __fadd_rn(rnd<T, CS, BWD>(__fmul_rn(hi, c1[i])), rnd<T, CS, BWD>(__fmul_rn(lo, s1[i])));
+      } else {
+        // dx_lo = dy_lo c_lo + dy_hi s_hi ,  dx_hi = dy_hi c_hi - dy_lo s_lo
+        x0[i] = __fadd_rn(rnd<T, CS, BWD>(__fmul_rn(lo, c0[i])), rnd<T, CS, BWD>(__fmul_rn(hi, s1[i])));
+        x1[i] = __fadd_rn(rnd<T, CS, BWD>(__fmul_rn(hi, c1[i])), -rnd<T, CS, BWD>(__fmul_rn(lo, s0[i])));
+      }
     }
   }
-  store_chunk<T>(dst, x);
+  store_chunk<T>(dst + e0, x0);
+  store_chunk<T>(dst + e1, x1);
 }
 
 }  // namespace prologue
@@ -131,10 +143,11 @@ int qkv_prologue(const void* qkv, const void* cos, const void* sin, void* q, voi
   using namespace prologue;
   const int el = dtype == FASTMAX_DTYPE_BF16 ? 8 : 4;
   if (B <= 0 || T <= 0 || G <= 0 || qpk <= 0 || hs <= 0 || rope_n < 0 || rope_n > hs) return FASTMAX_ERR_BAD_ARG;
-  if (hs % el || (rope_n / 2) % el || rope_n % 2) return FASTMAX_ERR_UNSUPPORTED;        // whole 16-byte chunks only
+  // whole 16-byte chunks, moved in pairs: the rotary half and the pass-through remainder are whole chunk pairs
+  if (hs % (2 * el) || (rope_n / 2) % el || rope_n % 2 || (hs - rope_n) % (2 * el)) return FASTMAX_ERR_UNSUPPORTED;
   if (dtype == FASTMAX_DTYPE_F32 && dtype_cs != FASTMAX_DTYPE_F32) return FASTMAX_ERR_UNSUPPORTED;
   Params P{B, T, G, qpk, hs, rope_n, qkv, cos, sin, q, k, v};
-  const size_t total = (size_t)B * T * G * (qpk + 2) * (hs / el);
+  const size_t total = (size_t)B * T * G * (qpk + 2) * (hs / el / 2);
   const unsigned grid = (unsigned)((total + 255) / 256);
 #define FM_PRO(TT, CC)                                                                                         \
   do {                                                                                                         \

@@ -174,8 +174,8 @@ def _prologue_native(qkv, cos, hs, rope_n) -> bool:
         return False
     if qkv.dtype == torch.float32 and cos.dtype != torch.float32:
         return False
-    el = 8 if qkv.dtype == torch.bfloat16 else 4
-    return hs % el == 0 and rope_n % 2 == 0 and (rope_n // 2) % el == 0
+    el = 8 if qkv.dtype == torch.bfloat16 else 4        # elements per 16-byte chunk; the kernel moves chunk pairs
+    return hs % (2 * el) == 0 and rope_n % 2 == 0 and (rope_n // 2) % el == 0 and (hs - rope_n) % (2 * el) == 0
 
 
 def qkv_prologue(qkv, cos, sin, n_query_groups: int, q_per_kv: int, head_size: int, rope_n_elem: int):

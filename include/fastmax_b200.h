@@ -142,7 +142,8 @@ int fastmax_bwd_gqa(const void* q, const void* k, const void* v, const void* o, 
  * model.py:702-708) on the first rope_n_elem features of q and k with the caller's cos / sin tables
  * (T, rope_n_elem).  Bit-exact against the reference's eager arithmetic (per-op rounding when the tables share the
  * tensors' dtype, one rounding under fp32 promotion).  _bwd is its transpose: dq, dk, dv -> dqkv.
- * Whole 16-byte chunks only: head_size and rope_n_elem / 2 multiples of 8 (bf16) / 4 (fp32), else UNSUPPORTED. */
+ * Whole 16-byte chunks moved in pairs: rope_n_elem / 2 a multiple of 8 (bf16) / 4 (fp32) elements, head_size and
+ * head_size - rope_n_elem multiples of 16 / 8, else UNSUPPORTED. */
 int fastmax_qkv_prologue(const void* qkv, const void* cos, const void* sin, void* q, void* k, void* v,
                          int B, int T, int n_query_groups, int q_per_kv, int head_size, int rope_n_elem,
                          int dtype, int dtype_cos_sin, void* stream);
