@@ -112,6 +112,10 @@ int seg_fwd(const Problem& pb, int L, const void* q, const void* k, const void* 
 // fused q/k/v assembly in front of the op (fm_prologue.cu; model.py:392-425) and its transpose
 int qkv_prologue(const void* qkv, const void* cos, const void* sin, void* q, void* k, void* v, int B, int T, int G,
                  int qpk, int hs, int rope_n, int dtype, int dtype_cs, int backward, cudaStream_t stream);
+// ... and of the dk / dv intra-segment kernel (fm_seg_bwd.cu): same contract as intra_dkdv
+bool seg_dkdv_usable(const Problem& pb, int L);
+int seg_dkdv(const Problem& pb, int L, int Npad, const void* k, const void* v, const void* q, const void* u,
+             const float* dlt, float* dk_part, float* dv_part, const uint8_t* rstate);
 namespace mom { struct ApplyDesc; }
 int launch_apply_gen(const Problem& pb, int BH, int nrec, const char* name, const mom::ApplyDesc& d, int variant);
 // first-order causal FastMax as one fused scan per (b,h) (fm_p1scan.cu)

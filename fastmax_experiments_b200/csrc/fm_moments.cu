@@ -1123,7 +1123,11 @@ int moments_bwd(const Problem& pb, const void* q, const void* k, const void* v, 
     return intra_dkdv(pb, m.L, m.Npad, k, v, q, u, dlt, nullptr, nullptr, R, dk, dv);
   }
   if ((rc = intra_dq(pb, m.L, m.Npad, q, u, k, v, dlt, dq_part, S))) return rc;
-  if ((rc = intra_dkdv(pb, m.L, m.Npad, k, v, q, u, dlt, dk_part, pb.causal ? dv_part : nullptr, R))) return rc;
+  if (seg_kernels_enabled() && seg_dkdv_usable(pb, m.L)) {
+    if ((rc = seg_dkdv(pb, m.L, m.Npad, k, v, q, u, dlt, dk_part, dv_part, R))) return rc;
+  } else if ((rc = intra_dkdv(pb, m.L, m.Npad, k, v, q, u, dlt, dk_part, pb.causal ? dv_part : nullptr, R))) {
+    return rc;
+  }
   // 4. inter-segment parts
   ApplyParams ap{};
   ap.mode = APPLY_DQ, ap.state_reverse = 0, ap.b_kmajor = 1, ap.edge_state = pb.sp_init_fwd != nullptr;
