@@ -24,6 +24,17 @@
 
 FM_TIMING_DEFINE(moments)
 
+#ifdef FM_TRACE
+// developer build: event times of one apply CTA, [event][slab pair]
+static __device__ long long fm_trace_apply2[8][40];
+extern "C" int fastmax_debug_trace_fetch_apply2(long long* out) {
+  return cudaMemcpyFromSymbol(out, fm_trace_apply2, sizeof(fm_trace_apply2)) == cudaSuccess ? 0 : -4;
+}
+#define FM_TRA(ev, j) do { if (blockIdx.x == 5 && blockIdx.y == 100 && (j) < 40) fm_trace_apply2[ev][j] = clock64(); } while (0)
+#else
+#define FM_TRA(ev, j) ((void)0)
+#endif
+
 namespace fm {
 namespace mom {
 using namespace sm100;
@@ -561,6 +572,14 @@ struct ApplyParams {
   const uint8_t* state;
 };
 
+// Shared-memory descriptors of the apply kernel's MMA operands, built on the host (constant bank: one thread then
+// issues an MMA in ~50 cycles instead of ~110 with descriptors assembled in registers; event trace of one CTA: the
+// four MMAs + commit of a (tile, slab pair) step took ~500 cycles of a ~1800-cycle step)
+struct ApplyDescs {
+  unsigned long long aK[4][4];        // resident Y tile t, K-major, k-step kk
+  unsigned long long bD[6][4];        // ring stage, k-step kk: slabs read MN-major (o, dv) or K-major (dq, dk)
+};
+
 constexpr int A_STAGES = 6;
 constexpr int A_STAGE_BYTES = 2 * 8192;                  // two slabs per MMA (N = 128)
 constexpr int A_TOK = APPLY_TOK;                         // 4 token tiles per CTA
@@ -584,7 +603,7 @@ constexpr int A_THREADS = 19 * 32;                       // 16 epilogue warps, 2
 // memory 3.2-5.2.
 __global__ void __launch_bounds__(A_THREADS, 1)
 apply_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmY,
-             const __grid_constant__ CUtensorMap tmOut, const ApplyParams P) {
+             const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ ApplyDescs DS, const ApplyParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* res = smem;                       // [4 tiles][16 KiB]
@@ -646,6 +665,7 @@ apply_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CU
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  assert_bases(tmem, smem);
 
   if (warp == 18) {
     // ---------------------------------------------------------------- TMA producer
@@ -675,31 +695,37 @@ apply_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CU
     }
   } else if (warp >= 16) {
     // ---------------------------------------------------------------- MMA issuers (tiles 0,1 | tiles 2,3)
-    // one thread sustains one tcgen05.mma per ~110 cycles; a 128x128x16 MMA occupies the pipe for ~64
-    if (lane == 0 && has_state) {
+    // converged warps, one elected lane issues; descriptors from the constant bank through indexed loads
+    if (has_state) {
       const int tb = (warp - 16) * 2;
       const uint32_t id128 = make_idesc_bf16(128, 128, false, !P.b_kmajor);
       const uint32_t id64 = make_idesc_bf16(128, 64, false, !P.b_kmajor);
-      const uint32_t kstep = P.b_kmajor ? 2 : 128;
+#pragma unroll 1
       for (int gi = 0; gi < ngroups; ++gi) {
         const int st = gi % A_STAGES;
         const bool last = gi == ngroups - 1;
-        mbar_wait(&full[st], (gi / A_STAGES) & 1, 2000 + gi);
-        const uint32_t sb = smem_u32(ring + st * A_STAGE_BYTES);
-        const uint64_t bd = P.b_kmajor ? desc_kmajor_sw128(sb) : desc_mnmajor_sw128(sb, 8192);
         const uint32_t idesc = last ? id64 : id128;
+        if (lane == 0) mbar_wait(&full[st], (gi / A_STAGES) & 1, 2000 + gi);
 #pragma unroll
         for (int tt = 0; tt < 2; ++tt) {
           const int t = tb + tt;
-          if (gi > 0) mbar_wait(&t_free[t], (gi - 1) & 1, 3000 + gi);
-          else mbar_wait(&res_full[t], 0, 5000 + t);
+          if (lane == 0) {
+            if (t == 0) FM_TRA(0, gi);
+            if (gi > 0) mbar_wait(&t_free[t], (gi - 1) & 1, 3000 + gi);
+            else mbar_wait(&res_full[t], 0, 5000 + t);
+          }
+          __syncwarp();
           tc_fence_after();
-          const uint64_t ad = desc_kmajor_sw128(smem_u32(res + t * 16384));
+          if (t == 0 && lane == 0) FM_TRA(1, gi);
+          if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) umma_ss(tmem + 128 * t, ad + kk * 2, bd + kk * kstep, idesc, kk > 0);
-          umma_commit(&t_full[t]);
+            for (int kk = 0; kk < 4; ++kk) umma_ss(128 * t, DS.aK[t][kk], DS.bD[st][kk], idesc, kk > 0);
+            umma_commit(&t_full[t]);
+            if (tt == 1) umma_commit(&empty[st]);
+            if (t == 0) FM_TRA(2, gi);
+          }
+          __syncwarp();
         }
-        umma_commit(&empty[st]);
       }
     }
   } else {
@@ -730,8 +756,10 @@ apply_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CU
         } else {
           xs[0] = P.coef64, xs[1] = 0.f;
         }
+        if (warp == 0 && lane == 0) FM_TRA(3, gi);
         mbar_wait(&t_full[t], gi & 1, 4000 + gi);
         tc_fence_after();
+        if (warp == 0 && lane == 0) FM_TRA(4, gi);
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           if (j > 0 && last) break;
@@ -747,6 +775,8 @@ apply_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CU
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&t_free[t]);
+        if (warp == 0 && lane == 0) FM_TRA(5, gi);
+        if (warp == 3 && lane == 0) FM_TRA(6, gi);
       }
     }
     // The bf16 rows leave through shared memory: the tile's own resident Y tile is free once its last T tile
@@ -1036,7 +1066,16 @@ static int launch_apply(const Problem& pb, const MomLayout& m, const char* name,
   P.N = m.N, P.L = m.L, P.nseg = m.nseg, P.causal = pb.causal, P.p = pb.p;
   FM_CUDA(cudaFuncSetAttribute(apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A_SMEM));
   dim3 grid((m.N + A_TOK - 1) / A_TOK, m.BH);
-  FM_LAUNCH(name, pb.stream, apply_kernel<<<grid, A_THREADS, A_SMEM, pb.stream>>>(tmS, tmY, tmOut, P));
+  ApplyDescs DS{};
+  for (int kk = 0; kk < 4; ++kk) {
+    for (int t = 0; t < 4; ++t) DS.aK[t][kk] = sm100::desc_kmajor_sw128_const(sm100::FM_SMEM_BASE + t * 16384) + kk * 2;
+    for (int st = 0; st < A_STAGES; ++st) {
+      const uint32_t sb = sm100::FM_SMEM_BASE + A_RES_BYTES + st * A_STAGE_BYTES;
+      DS.bD[st][kk] = P.b_kmajor ? sm100::desc_kmajor_sw128_const(sb) + kk * 2
+                                 : sm100::desc_mnmajor_sw128_const(sb, 8192) + kk * 128;
+    }
+  }
+  FM_LAUNCH(name, pb.stream, apply_kernel<<<grid, A_THREADS, A_SMEM, pb.stream>>>(tmS, tmY, tmOut, DS, P));
   return FASTMAX_OK;
 }
 
