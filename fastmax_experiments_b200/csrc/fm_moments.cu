@@ -585,7 +585,9 @@ constexpr int A_STAGE_BYTES = 2 * 8192;                  // two slabs per MMA (N
 constexpr int A_TOK = APPLY_TOK;                         // 4 token tiles per CTA
 constexpr int A_RES_BYTES = 4 * 16384;                   // four resident 128x64 Y tiles
 constexpr int A_SMEM = A_RES_BYTES + A_STAGES * A_STAGE_BYTES + 1024 + 1024;
-constexpr int A_THREADS = 19 * 32;                       // 16 epilogue warps, 2 MMA issuers, TMA producer
+constexpr int A_ISSUERS = 2;   // (4, one per tile: 4.2 ms per launch instead of 2.2 -- a 21st warp costs every thread registers)
+constexpr int A_PRODUCER = 16 + A_ISSUERS;               // warp index of the TMA producer
+constexpr int A_THREADS = (17 + A_ISSUERS) * 32;         // 16 epilogue warps, MMA issuers, TMA producer
 
 // Each token tile owns a private 128-column T buffer in tensor memory and its own barrier pair.
 // In-kernel cycle counters (-DFM_TIMING, tools/timing.py) at the headline shape: per tile and slab pair
@@ -628,12 +630,12 @@ apply_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CU
   const int rec_idx = P.causal ? bh_st * P.nseg + seg : bh_st;
   const int ngroups = (P.p == 2 ? 32 : 0) + 1;     // 32 pairs of second-order slabs + slab 64
 
-  if (warp == 18) {
+  if (warp == A_PRODUCER) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
   if (tid == 0) {
-    for (int i = 0; i < A_STAGES; ++i) mbar_init(&full[i], 1), mbar_init(&empty[i], 2);
+    for (int i = 0; i < A_STAGES; ++i) mbar_init(&full[i], 1), mbar_init(&empty[i], A_ISSUERS);
     for (int i = 0; i < 4; ++i) mbar_init(&t_full[i], 1), mbar_init(&t_free[i], 4);
     for (int i = 0; i < 4; ++i) mbar_init(&res_full[i], 1);
     fence_barrier_init();
@@ -667,7 +669,7 @@ apply_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CU
   const uint32_t tmem = *tmem_slot;
   assert_bases(tmem, smem);
 
-  if (warp == 18) {
+  if (warp == A_PRODUCER) {
     // ---------------------------------------------------------------- TMA producer
     if (lane == 0 && has_state) {
       // operands of the very first MMAs first: Y tile 0, slab pair 0, then the other tiles
@@ -697,7 +699,8 @@ apply_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CU
     // ---------------------------------------------------------------- MMA issuers (tiles 0,1 | tiles 2,3)
     // converged warps, one elected lane issues; descriptors from the constant bank through indexed loads
     if (has_state) {
-      const int tb = (warp - 16) * 2;
+      constexpr int TPI = 4 / A_ISSUERS;            // tiles per issuer
+      const int tb = (warp - 16) * TPI;
       const uint32_t id128 = make_idesc_bf16(128, 128, false, !P.b_kmajor);
       const uint32_t id64 = make_idesc_bf16(128, 64, false, !P.b_kmajor);
 #pragma unroll 1
@@ -707,7 +710,7 @@ apply_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CU
         const uint32_t idesc = last ? id64 : id128;
         if (lane == 0) mbar_wait(&full[st], (gi / A_STAGES) & 1, 2000 + gi);
 #pragma unroll
-        for (int tt = 0; tt < 2; ++tt) {
+        for (int tt = 0; tt < TPI; ++tt) {
           const int t = tb + tt;
           if (lane == 0) {
             if (t == 0) FM_TRA(0, gi);
@@ -721,7 +724,7 @@ apply_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CU
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) umma_ss(128 * t, DS.aK[t][kk], DS.bD[st][kk], idesc, kk > 0);
             umma_commit(&t_full[t]);
-            if (tt == 1) umma_commit(&empty[st]);
+            if (tt == TPI - 1) umma_commit(&empty[st]);
             if (t == 0) FM_TRA(2, gi);
           }
           __syncwarp();
@@ -806,7 +809,7 @@ apply_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CU
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 18) tmem_dealloc(tmem, 512);
+  if (warp == A_PRODUCER) tmem_dealloc(tmem, 512);
 }
 
 // =============================================================================================
