@@ -760,7 +760,7 @@ apply_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CU
           xs[0] = P.coef64, xs[1] = 0.f;
         }
         if (warp == 0 && lane == 0) FM_TRA(3, gi);
-        mbar_wait(&t_full[t], gi & 1, 4000 + gi);
+        mbar_wait_spin(&t_full[t], gi & 1);
         tc_fence_after();
         if (warp == 0 && lane == 0) FM_TRA(4, gi);
 #pragma unroll

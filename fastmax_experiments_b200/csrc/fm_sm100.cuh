@@ -91,6 +91,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
   }
 }
 
+// wait without the time-out / diagnostic path (no printf arguments, no stack frame): for inner loops of kernels whose
+// protocol is covered by the tests, where the registers the diagnostic path keeps live matter
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {}
+}
+
 // Warp-collective wait: one lane polls, the warp reconverges.  Every polling thread costs an
 // operation on the SM's (serial) mbarrier unit, so hundreds of threads spinning on the same
 // barrier throttle every arrive/wait of the CTA; one poller per warp is enough.
