@@ -124,7 +124,8 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_MISC);
-  uint64_t* q_full = bars;
+  uint64_t* q_full = bars;         // q tiles 1.. , normaliser slab, fp32 vectors
+  uint64_t* q0_full = bars + 13;   // q tile 0 alone: the first scores do not wait for the rest
   uint64_t* full = bars + 1;       // [3]
   uint64_t* empty = bars + 4;      // [3]
   uint64_t* s_ready = bars + 7;    // [2]
@@ -166,7 +167,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
     // ---------------------------------------------------------------- TMA producer, first part
     // (its own barriers are set up here so the first loads leave before the CTA-wide set-up barrier)
     if (lane == 0) {
-      mbar_init(q_full, 1);
+      mbar_init(q_full, 1), mbar_init(q0_full, 1);
       for (int s = 0; s < NST; ++s) mbar_init(&full[s], 1), mbar_init(&empty[s], 1);
       fence_barrier_init();
     }
@@ -174,8 +175,9 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
     // the producer only ARRIVES on the set-up barrier: its ~40 bulk-tensor instructions run under the others' set-up
     asm volatile("bar.arrive 2, %0;" ::"r"(THREADS) : "memory");
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, tq * 16384 + (has_norm ? 8192 + 512 : 0));
-      tma_load_3d(smem + OFF_Q, &tmQ, q_full, 0, c0, bh);
+      mbar_arrive_expect_tx(q0_full, 16384);
+      tma_load_3d(smem + OFF_Q, &tmQ, q0_full, 0, c0, bh);
+      mbar_arrive_expect_tx(q_full, (tq - 1) * 16384 + (has_norm ? 8192 + 512 : 0));
       load_stream(0);
       for (int t = 1; t < tq; ++t) tma_load_3d(smem + OFF_Q + t * 16384, &tmQ, q_full, 0, c0 + t * 128, bh);
       if (has_norm) {
@@ -213,7 +215,10 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
     }
   } else if (warp == NCW + 1) {
     // ---------------------------------------------------------------- MMA issuer
-    if (lane == 0) mbar_wait(q_full, 0, 300);
+    if (lane == 0) {
+      mbar_wait(q0_full, 0, 299);
+      if (!whole) mbar_wait(q_full, 0, 300);
+    }
     __syncwarp();
     if (lane == 0) FM_TRS(0, 2);
     if (whole) {
@@ -224,6 +229,11 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
       if (elect_one()) {
         issue_scores<0, 0, 0>(D);
         umma_commit(&s_ready[0]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_wait(q_full, 0, 300);
+      __syncwarp();
+      if (elect_one()) {
         issue_scores<1, 0, 1>(D);
         umma_commit(&s_ready[1]);
       }
