@@ -107,7 +107,7 @@ dkdv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUt
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
   float* vec_s = reinterpret_cast<float*>(smem + OFF_MISC + 256);    // [128] R0 | RN1 of the boundary state
   // pair schedule, one word per pair: m | t << 8 | (first pair of key tile t) << 16 | (last pair on stream tile m) << 17
-  uint32_t* sched = reinterpret_cast<uint32_t*>(smem + OFF_MISC + 1024);   // [<= 2 * 8 pairs]
+  uint32_t* sched = reinterpret_cast<uint32_t*>(smem + OFF_MISC + 1024);   // [256]: 14 pairs at L = 512, 254 at L = 8192
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) FM_TRB(0, 0);
   const int bh = blockIdx.y;
@@ -351,7 +351,8 @@ dkdv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUt
 using namespace segb;
 
 bool seg_dkdv_usable(const Problem& pb, int L) {
-  return pb.p == 2 && pb.causal && pb.D == 64 && pb.dtype == FASTMAX_DTYPE_BF16 && L % 512 == 0;
+  // (L <= 8192: the pair schedule of a CTA -- at most 2 * L / 64 - 2 words -- has 256 words of shared memory)
+  return pb.p == 2 && pb.causal && pb.D == 64 && pb.dtype == FASTMAX_DTYPE_BF16 && L % 512 == 0 && L <= 8192;
 }
 
 // drop-in for intra_dkdv (p = 2, causal): fp32 blocked partials of dk and dv, reverse boundary states (nullable)

@@ -147,3 +147,28 @@ def test_fused_attention_forward_matches_reference_module(name):
     assert orc.rel_err(y.double().cpu(), gd["y"].double()) <= 2e-2
     # the host reference keeps every cumulative sum in bf16 (its own error vs fp64 is 6e-3 .. 1.9e-2)
     assert torch.isfinite(x.grad).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(1, 1, 1, 257), (1, 2, 1, 1025), (1, 1, 1, 2047), (1, 2, 2, 2049), (1, 2, 1, 2689), (1, 4, 2, 4097)],
+                         ids=lambda s: "B%d-H%d-Hkv%d-N%d" % s)
+def test_ragged_shapes_second_generation_intra_kernels(shape):
+    """Ragged tails around the tile / segment sizes of csrc/fm_seg.cu and csrc/fm_seg_bwd.cu (a last CTA with one live
+    tile, one dense segment of 1024 / 2048 tokens with CTAs deep inside it, one token past a segment boundary), with and
+    without grouped keys, against the fp64 dense formula."""
+    from fastmax_experiments_b200 import fastmax_gqa
+    from fastmax_experiments_b200.gqa import expand_kv
+    B, H, Hkv, N = shape
+    g = torch.Generator().manual_seed(N)
+    q = torch.randn(B, H, N, 64, generator=g).to(torch.bfloat16)
+    k, v = (torch.randn(B, Hkv, N, 64, generator=g).to(torch.bfloat16) for _ in range(2))
+    do = torch.randn(B, H, N, 64, generator=g).to(torch.bfloat16)
+    qa, ka, va = (t.cuda().requires_grad_(True) for t in (q, k, v))
+    o = fastmax_gqa(qa, ka, va, mask=True, p=2)
+    o.backward(do.cuda())
+    ke, ve = (expand_kv(t, H // Hkv).double() for t in (k, v))
+    ro, _, rdq, rdk, rdv = orc.dense_fwd_bwd(q.double(), ke, ve, do.double(), mask=True, p=2)
+    fold = lambda t: t.view(B, Hkv, H // Hkv, N, 64).sum(2)
+    for nm, x, r in (("o", o, ro), ("dq", qa.grad, rdq), ("dk", ka.grad, fold(rdk)), ("dv", va.grad, fold(rdv))):
+        err = orc.rel_err(x.double().cpu(), r)
+        assert err <= 2e-2, (shape, nm, err)
