@@ -325,7 +325,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
     for (int np = 0; np < npairs; ++np) {
       const int b = np & 1;
       if (tid == 0) FM_TRS(1, np);
-      mbar_wait_warp(&s_ready[b], (np >> 1) & 1);
+      mbar_wait_spin(&s_ready[b], (np >> 1) & 1);      // every lane polls: fastest wake-up (measured)
       tc_fence_after();
       if (tid == 0) FM_TRS(2, np);
       FM_TRW(0, warp, np);
