@@ -712,11 +712,9 @@ apply_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CU
 #pragma unroll
         for (int tt = 0; tt < TPI; ++tt) {
           const int t = tb + tt;
-          if (lane == 0) {
-            if (t == 0) FM_TRA(0, gi);
-            if (gi > 0) mbar_wait(&t_free[t], (gi - 1) & 1, 3000 + gi);
-            else mbar_wait(&res_full[t], 0, 5000 + t);
-          }
+          if (t == 0 && lane == 0) FM_TRA(0, gi);
+          if (gi > 0) mbar_wait_spin(&t_free[t], (gi - 1) & 1);                // (every lane polls)
+          else mbar_wait_spin(&res_full[t], 0);
           __syncwarp();
           tc_fence_after();
           if (t == 0 && lane == 0) FM_TRA(1, gi);

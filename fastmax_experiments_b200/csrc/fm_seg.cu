@@ -245,10 +245,8 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
         const int j = (int)(FULL_J_TAB >> (4 * np)) & 15, t = (int)(FULL_T_TAB >> (4 * np)) & 15, b = np & 1;
         const bool more = np + 2 < FULL_PAIRS;
         const int j2 = (int)(FULL_J_TAB >> (4 * np + 8)) & 15, t2 = (int)(FULL_T_TAB >> (4 * np + 8)) & 15;
-        if (lane == 0) {
-          mbar_wait(&p_ready[b], (np >> 1) & 1, 500 + np);
-          if (more && t2 == j2) mbar_wait(&full[j2 % NST], (j2 / NST) & 1, 400 + j2);   // first use of stream tile j2
-        }
+        mbar_wait_spin(&p_ready[b], (np >> 1) & 1);                                   // (every lane polls)
+        if (more && t2 == j2) mbar_wait_spin(&full[j2 % NST], (j2 / NST) & 1);        // first use of stream tile j2
         __syncwarp();
         tc_fence_after();
         if (lane == 0) FM_TRS(8, np);

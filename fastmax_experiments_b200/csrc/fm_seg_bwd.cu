@@ -219,10 +219,8 @@ dkdv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUt
       const bool more = np + 2 < npairs;
       const uint32_t wa = sched[np], ws = sched[more ? np + 2 : np];
       const int ma = wa & 255, ta = (wa >> 8) & 255, ms = ws & 255, ts = (ws >> 8) & 255;
-      if (lane == 0) {
-        mbar_wait(&p_ready[b], (np >> 1) & 1, 500 + np);
-        if (more && ts == 0) mbar_wait(&full[ms & (NST - 1)], (ms / NST) & 1, 400 + ms);   // first use of stream tile ms
-      }
+      mbar_wait_spin(&p_ready[b], (np >> 1) & 1);                                          // (every lane polls)
+      if (more && ts == 0) mbar_wait_spin(&full[ms & (NST - 1)], (ms / NST) & 1);          // first use of stream tile ms
       __syncwarp();
       tc_fence_after();
       if (lane == 0) FM_TRB(5, np);
