@@ -116,6 +116,9 @@ int qkv_prologue(const void* qkv, const void* cos, const void* sin, void* q, voi
 bool seg_dkdv_usable(const Problem& pb, int L);
 int seg_dkdv(const Problem& pb, int L, int Npad, const void* k, const void* v, const void* q, const void* u,
              const float* dlt, float* dk_part, float* dv_part, const uint8_t* rstate);
+bool seg_dq_usable(const Problem& pb, int L);
+int seg_dq(const Problem& pb, int L, int Npad, const void* q, const void* u, const void* k, const void* v,
+           const float* dlt, float* dq_part, const uint8_t* state);
 namespace mom { struct ApplyDesc; }
 int launch_apply_gen(const Problem& pb, int BH, int nrec, const char* name, const mom::ApplyDesc& d, int variant);
 // first-order causal FastMax as one fused scan per (b,h) (fm_p1scan.cu)

@@ -1162,7 +1162,11 @@ int moments_bwd(const Problem& pb, const void* q, const void* k, const void* v, 
     if ((rc = intra_dq(pb, m.L, m.Npad, q, u, k, v, dlt, nullptr, S, dq))) return rc;
     return intra_dkdv(pb, m.L, m.Npad, k, v, q, u, dlt, nullptr, nullptr, R, dk, dv);
   }
-  if ((rc = intra_dq(pb, m.L, m.Npad, q, u, k, v, dlt, dq_part, S))) return rc;
+  if (seg_kernels_enabled() && seg_dq_usable(pb, m.L)) {
+    if ((rc = seg_dq(pb, m.L, m.Npad, q, u, k, v, dlt, dq_part, S))) return rc;
+  } else if ((rc = intra_dq(pb, m.L, m.Npad, q, u, k, v, dlt, dq_part, S))) {
+    return rc;
+  }
   if (seg_kernels_enabled() && seg_dkdv_usable(pb, m.L)) {
     if ((rc = seg_dkdv(pb, m.L, m.Npad, k, v, q, u, dlt, dk_part, dv_part, R))) return rc;
   } else if ((rc = intra_dkdv(pb, m.L, m.Npad, k, v, q, u, dlt, dk_part, pb.causal ? dv_part : nullptr, R))) {

@@ -346,6 +346,333 @@ dkdv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUt
 
 }  // namespace segb
 
+
+// =============================================================================================
+// dq: same organisation with the roles swapped -- rows = queries of the CTA's four tiles (q, u resident), 64-token
+// k / v tiles streamed from the start of the segment:
+//   S = Q_i K_j^T ,  dP = U_i V_j^T ,  E = f'(S)/a o (dP - dlt_i) o mask (key <= query) ,  dQ_i += E K_j
+// plus the normaliser column of the forward boundary state, dq_part -= dlt_i (N1 + a N2 q_i)   (intra_kernel<INTRA_DQ>)
+// Four accumulators (4 x 64 columns) + two (S | dP) buffers (2 x 128 columns).  1.31 -> 1.21 ms at the headline shape
+// (same box, same run); with 128-token stream tiles only ONE (S | dP) buffer fits next to the accumulators and the
+// issuer and the compute warps strictly alternate: 1.59 ms.
+// =============================================================================================
+namespace segq {
+using namespace sm100;
+using namespace mom;
+
+constexpr int NCW = 16;
+constexpr int THREADS = (NCW + 2) * 32;
+constexpr int QT = 4;                              // query tiles per CTA
+constexpr int NST = 4;
+constexpr int STAGE = 2 * 8192;                    // K tile | V tile (64 tokens each)
+constexpr int OFF_Q = 0;
+constexpr int OFF_U = QT * 16384;
+constexpr int OFF_RING = 2 * QT * 16384;
+constexpr int OFF_NORM = OFF_RING + NST * STAGE;
+constexpr int OFF_MISC = OFF_NORM + 8192;
+constexpr int SMEM = OFF_MISC + 2048 + 1024;
+
+struct Descs {
+  unsigned long long qK[QT][4], uK[QT][4];        // resident query / u tiles, K-major (A of the score MMAs)
+  unsigned long long kK[NST][4], vK[NST][4];      // stream tiles, K-major (B of the score MMAs, 64 rows)
+  unsigned long long kMN[NST][4];                 // stream K tile read MN-major (B of the accumulating MMAs)
+  unsigned long long normK[4];
+};
+
+struct Params {
+  int N, Npad, L, nseg, edge_state;
+  int H, Hkv;
+  float a;
+  const float* dlt;
+  float* out;                // blocked fp32 partial of dq
+  const uint8_t* state;      // forward boundary states, nullable
+};
+
+// pair np -> (stream tile m, query tile t): m ascending, t = max(0, m / 2 - J) .. tq - 1   (J: query tiles of the
+// segment in front of the CTA)
+struct PairIt {
+  int m = 0, t = 0;
+  __device__ __forceinline__ void next(int tq, int J) {
+    if (t + 1 < tq) ++t;
+    else ++m, t = max(0, (m >> 1) - J);
+  }
+};
+
+__device__ __forceinline__ void issue_scores(const Descs& D, int t, int st, int b) {
+  constexpr uint32_t ID = make_idesc_bf16(128, 64, false, false);
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) umma_ss(256 + 128 * b, D.qK[t][kk], D.kK[st][kk], ID, kk > 0);
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) umma_ss(256 + 128 * b + 64, D.uK[t][kk], D.vK[st][kk], ID, kk > 0);
+}
+// E (bf16) of warp cb sits in columns [16 cb, +8) of the score buffer: k-step cb starts there
+__device__ __forceinline__ void issue_acc(const Descs& D, int t, int st, int b, uint32_t acc) {
+  constexpr uint32_t ID = make_idesc_bf16(128, 64, false, true);
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) umma_ts(64 * t, 256 + 128 * b + 16 * kk, D.kMN[st][kk], ID, (acc || kk > 0) ? 1 : 0);
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmU,
+          const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+          const __grid_constant__ CUtensorMap tmS, const __grid_constant__ Descs D, const Params P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_MISC);
+  uint64_t* res_full = bars;
+  uint64_t* full = bars + 1;        // [4]
+  uint64_t* empty = bars + 5;       // [4]
+  uint64_t* s_ready = bars + 9;     // [2]
+  uint64_t* p_ready = bars + 11;    // [2] count NCW
+  uint64_t* acc_done = bars + 13;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  float* vec_s = reinterpret_cast<float*>(smem + OFF_MISC + 256);    // [128] S0 | N1 of the boundary state
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int bh = blockIdx.y;
+  const int kvh = kv_index(bh, P.H, P.Hkv);
+  const int c0 = blockIdx.x * (QT * 128);
+  const int seg = c0 / P.L;
+  const int st0 = seg * P.L;
+  const int J = (c0 - st0) / 128;
+  const int tq = min(QT, (P.N - c0 + 127) / 128);          // live query tiles
+  const int M = 2 * (J + tq);                              // stream tiles [st0, c0 + 128 tq)
+  const bool has_norm = P.state != nullptr && (seg > 0 || P.edge_state);
+  const int rec_idx = kvh * P.nseg + seg;
+  int npairs = 0;
+  for (int m = 0; m < M; ++m) npairs += tq - max(0, (m >> 1) - J);
+
+  auto load_stream = [&](int m) {
+    const int s = m % NST;
+    uint8_t* dst = smem + OFF_RING + s * STAGE;
+    mbar_arrive_expect_tx(&full[s], STAGE);
+    tma_load_3d(dst, &tmK, &full[s], 0, st0 + m * 64, kvh);
+    tma_load_3d(dst + 8192, &tmV, &full[s], 0, st0 + m * 64, kvh);
+  };
+  if (warp == NCW) {
+    if (lane == 0) {
+      mbar_init(res_full, 1);
+      for (int s = 0; s < NST; ++s) mbar_init(&full[s], 1), mbar_init(&empty[s], 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    asm volatile("bar.arrive 2, %0;" ::"r"(THREADS) : "memory");
+    if (lane == 0) {
+      mbar_arrive_expect_tx(res_full, 2 * tq * 16384 + (has_norm ? 8192 + 512 : 0));
+      tma_load_3d(smem + OFF_Q, &tmQ, res_full, 0, c0, bh);
+      tma_load_3d(smem + OFF_U, &tmU, res_full, 0, c0, bh);
+      load_stream(0);
+      for (int t = 1; t < tq; ++t) {
+        tma_load_3d(smem + OFF_Q + t * 16384, &tmQ, res_full, 0, c0 + t * 128, bh);
+        tma_load_3d(smem + OFF_U + t * 16384, &tmU, res_full, 0, c0 + t * 128, bh);
+      }
+      if (has_norm) {
+        tma_load_3d(smem + OFF_NORM, &tmS, res_full, 0, 65 * 64, rec_idx);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_u32(vec_s)), "l"(P.state + (size_t)rec_idx * REC_BYTES + VEC_OFF), "r"(512), "r"(smem_u32(res_full))
+                     : "memory");
+      }
+      for (int m = 1; m < min(M, NST); ++m) load_stream(m);
+    }
+  } else if (warp == NCW + 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  if (tid == 0) {
+    mbar_init(acc_done, 1);
+    for (int s = 0; s < 2; ++s) mbar_init(&s_ready[s], 1), mbar_init(&p_ready[s], NCW);
+    fence_barrier_init();
+  }
+  tc_fence_before();
+  if (warp != NCW) named_barrier_sync(2, THREADS);
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  assert_bases(tmem, smem);
+
+  if (warp == NCW) {
+    if (lane == 0) {
+      for (int m = NST; m < M; ++m) {
+        mbar_wait(&empty[m % NST], ((m / NST) - 1) & 1, 100 + m);
+        load_stream(m);
+      }
+    }
+  } else if (warp == NCW + 1) {
+    // ---------------------------------------------------------------- MMA issuer (see dkdv_kernel)
+    PairIt ps, pa;                  // next pair to issue scores for / to accumulate
+    mbar_wait_spin(res_full, 0);
+    if (npairs > 0) mbar_wait_spin(&full[0], 0);
+    __syncwarp();
+    tc_fence_after();
+    for (int ns = 0; ns < min(2, npairs); ++ns) {    // pairs 0 and 1: both on stream tile 0 unless the CTA has one query tile
+      if (ps.m > 0) mbar_wait_spin(&full[ps.m % NST], 0);
+      __syncwarp();
+      if (elect_one()) {
+        issue_scores(D, ps.t, ps.m % NST, ns);
+        umma_commit(&s_ready[ns]);
+      }
+      __syncwarp();
+      ps.next(tq, J);
+    }
+#pragma unroll 1
+    for (int np = 0; np < npairs; ++np) {
+      const int b = np & 1, st = pa.m % NST;
+      const bool more = np + 2 < npairs;
+      const bool fresh = more && ps.t == max(0, (ps.m >> 1) - J);      // first pair on stream tile ps.m
+      mbar_wait_spin(&p_ready[b], (np >> 1) & 1);                       // (every lane polls)
+      if (fresh) mbar_wait_spin(&full[ps.m % NST], (ps.m / NST) & 1);
+      __syncwarp();
+      tc_fence_after();
+      if (elect_one()) {
+        issue_acc(D, pa.t, st, b, pa.m > 0 ? 1u : 0u);
+        if (pa.t == tq - 1) umma_commit(&empty[st]);                   // last pair on this stream tile
+        if (more) {
+          issue_scores(D, ps.t, ps.m % NST, b);
+          umma_commit(&s_ready[b]);
+        }
+      }
+      __syncwarp();
+      pa.next(tq, J);
+      ps.next(tq, J);
+    }
+    // normaliser column of the boundary state: T_t = Q_t . N2 into the (drained) score columns [256 + 64 t, +64)
+    tc_fence_after();
+    if (elect_one()) {
+      if (has_norm) {
+        constexpr uint32_t IDK = make_idesc_bf16(128, 64, false, false);
+        for (int t = 0; t < tq; ++t) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) umma_ss(256 + 64 * t, D.qK[t][kk], D.normK[kk], IDK, kk > 0);
+        }
+      }
+      umma_commit(acc_done);
+    }
+    __syncwarp();
+  } else if (warp < NCW) {
+    // ---------------------------------------------------------------- compute warps: query row x 16 key columns
+    const int q4 = warp & 3, cb = warp >> 2;
+    const int r = 32 * q4 + lane;
+    const uint32_t lane_addr = tmem + ((uint32_t)(32 * q4) << 16);
+    const float a = P.a;
+    float dl0, dl1, dl2, dl3;       // dlt of this thread's row in each query tile
+    {
+      const float* dsrc = P.dlt + (size_t)bh * P.Npad + c0 + r;
+      dl0 = c0 + r < P.N ? dsrc[0] : 0.f;
+      dl1 = c0 + 128 + r < P.N ? dsrc[128] : 0.f;
+      dl2 = c0 + 256 + r < P.N ? dsrc[256] : 0.f;
+      dl3 = c0 + 384 + r < P.N ? dsrc[384] : 0.f;
+    }
+    PairIt pc;
+    for (int np = 0; np < npairs; ++np) {
+      const int b = np & 1;
+      const uint32_t sbuf = lane_addr + 256 + 128 * b;
+      mbar_wait_spin(&s_ready[b], (np >> 1) & 1);      // every lane polls: fastest wake-up (measured)
+      tc_fence_after();
+      uint32_t sv[16], dv[16], w[8];
+      tmem_ld16(sbuf + 16 * cb, sv);
+      tmem_ld16(sbuf + 64 + 16 * cb, dv);
+      tmem_wait_ld();
+      const float dl = pc.t == 0 ? dl0 : pc.t == 1 ? dl1 : pc.t == 2 ? dl2 : dl3;
+      const int qrow = 128 * (pc.t + J) + r;               // relative to the start of the segment
+      const int col0 = 64 * pc.m + 16 * cb;                // key of this thread's first column, same origin
+      const bool diag = pc.m >= 2 * (pc.t + J);            // the tile reaches above the diagonal
+      if (diag) {
+#pragma unroll
+        for (int c = 0; c < 16; c += 2) {
+          float e0 = fmaf(a, __uint_as_float(sv[c]), 1.f) * (__uint_as_float(dv[c]) - dl);
+          float e1 = fmaf(a, __uint_as_float(sv[c + 1]), 1.f) * (__uint_as_float(dv[c + 1]) - dl);
+          e0 = col0 + c <= qrow ? e0 : 0.f, e1 = col0 + c + 1 <= qrow ? e1 : 0.f;      // key <= query
+          w[c >> 1] = pack_bf16x2(e0, e1);
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 16; c += 2) {
+          const float e0 = fmaf(a, __uint_as_float(sv[c]), 1.f) * (__uint_as_float(dv[c]) - dl);
+          const float e1 = fmaf(a, __uint_as_float(sv[c + 1]), 1.f) * (__uint_as_float(dv[c + 1]) - dl);
+          w[c >> 1] = pack_bf16x2(e0, e1);
+        }
+      }
+      tmem_st8(sbuf + 16 * cb, w);      // inside the S columns this warp has just read: no warp waits for another
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_ready[b]);
+      pc.next(tq, J);
+    }
+    // ---------------------------------------------------------------- epilogue: fp32 partial straight from registers
+    mbar_wait_warp(acc_done, 0);
+    mbar_wait_warp(res_full, 0);
+    tc_fence_after();
+#pragma unroll
+    for (int t = 0; t < QT; ++t) {
+      if (t >= tq) break;
+      uint32_t o[16];
+      tmem_ld16(lane_addr + 64 * t + 16 * cb, o);
+      if (has_norm) {               // dq_part[l] -= dlt (N1[l] + a T[l])
+        uint32_t tn[16];
+        tmem_ld16(lane_addr + 256 + 64 * t + 16 * cb, tn);
+        tmem_wait_ld();
+        const float dl = t == 0 ? dl0 : t == 1 ? dl1 : t == 2 ? dl2 : dl3;
+#pragma unroll
+        for (int c = 0; c < 16; ++c)
+          o[c] = __float_as_uint(__uint_as_float(o[c]) - dl * fmaf(a, __uint_as_float(tn[c]), vec_s[64 + 16 * cb + c]));
+      } else {
+        tmem_wait_ld();
+      }
+      const size_t tile = (size_t)bh * ((P.N + 127) / 128) + (size_t)(c0 / 128 + t);
+      uint4* dst = reinterpret_cast<uint4*>(P.out + tile * PART_TILE_FLOATS) + (4 * cb) * 128 + r;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dst[i * 128] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == NCW + 1) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace segq
+
+bool seg_dq_usable(const Problem& pb, int L) {
+  return pb.p == 2 && pb.causal && pb.D == 64 && pb.dtype == FASTMAX_DTYPE_BF16 && L % 512 == 0;
+}
+
+// drop-in for intra_dq (p = 2, causal): fp32 blocked partial of dq, forward boundary states (nullable)
+int seg_dq(const Problem& pb, int L, int Npad, const void* q, const void* u, const void* k, const void* v,
+           const float* dlt, float* dq_part, const uint8_t* state) {
+  const int BH = pb.B * pb.H, BHkv = pb.B * pb.kv_heads();
+  CUtensorMap tQ, tU, tK, tV, tS;
+  int rc;
+  if ((rc = make_tmap_bf16_3d(&tQ, q, 64, pb.N, BH, 128, (uint64_t)pb.N * 128, 64, 128))) return rc;
+  if ((rc = make_tmap_bf16_3d(&tU, u, 64, pb.N, BH, 128, (uint64_t)pb.N * 128, 64, 128))) return rc;
+  if ((rc = make_tmap_bf16_3d(&tK, k, 64, pb.N, BHkv, 128, (uint64_t)pb.N * 128, 64, 64))) return rc;
+  if ((rc = make_tmap_bf16_3d(&tV, v, 64, pb.N, BHkv, 128, (uint64_t)pb.N * 128, 64, 64))) return rc;
+  segq::Params P{};
+  P.N = pb.N, P.Npad = Npad, P.L = L, P.nseg = (pb.N + L - 1) / L, P.edge_state = pb.sp_init_fwd != nullptr;
+  P.H = pb.H, P.Hkv = pb.kv_heads();
+  P.a = pb.inv_c, P.dlt = dlt, P.out = dq_part;
+  P.state = (P.nseg > 1 || P.edge_state) ? state : nullptr;
+  tS = tQ;
+  if (P.state && (rc = make_tmap_bf16_3d(&tS, state, 64, mom::NSLAB * 64, (uint64_t)BHkv * P.nseg, 128, mom::REC_BYTES, 64, 64))) return rc;
+  segq::Descs D{};
+  const uint32_t base = sm100::FM_SMEM_BASE;
+  for (int kk = 0; kk < 4; ++kk) {
+    for (int t = 0; t < segq::QT; ++t) {
+      D.qK[t][kk] = sm100::desc_kmajor_sw128_const(base + segq::OFF_Q + t * 16384) + kk * 2;
+      D.uK[t][kk] = sm100::desc_kmajor_sw128_const(base + segq::OFF_U + t * 16384) + kk * 2;
+    }
+    for (int s = 0; s < segq::NST; ++s) {
+      const uint32_t ka = base + segq::OFF_RING + s * segq::STAGE, va = ka + 8192;
+      D.kK[s][kk] = sm100::desc_kmajor_sw128_const(ka) + kk * 2;
+      D.vK[s][kk] = sm100::desc_kmajor_sw128_const(va) + kk * 2;
+      D.kMN[s][kk] = sm100::desc_mnmajor_sw128_const(ka, 8192) + kk * 128;
+    }
+    D.normK[kk] = sm100::desc_kmajor_sw128_const(base + segq::OFF_NORM) + kk * 2;
+  }
+  FM_CUDA(cudaFuncSetAttribute(segq::dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, segq::SMEM));
+  dim3 grid((pb.N + segq::QT * 128 - 1) / (segq::QT * 128), BH);
+  FM_LAUNCH("mom_seg_dq", pb.stream,
+            segq::dq_kernel<<<grid, segq::THREADS, segq::SMEM, pb.stream>>>(tQ, tU, tK, tV, tS, D, P));
+  return FASTMAX_OK;
+}
+
 using namespace segb;
 
 bool seg_dkdv_usable(const Problem& pb, int L) {
