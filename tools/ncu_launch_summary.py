@@ -9,7 +9,7 @@ rows = list(csv.DictReader(l for l in open(sys.argv[1]) if l.startswith('"')))
 agg = collections.OrderedDict()
 for r in rows:
     n = r["Kernel Name"]
-    if not any(t in n for t in ("fm::", "mom::", "seg::", "segb::", "p1::", "p1f::", "d128::", "prologue::", "exact::", "dec::")):
+    if not any(t in n for t in ("fm::", "mom::", "seg::", "segb::", "segq::", "p1::", "p1f::", "d128::", "prologue::", "exact::", "dec::")):
         continue
     v, u = float(r["Metric Value"].replace(",", "")), r["Metric Unit"]
     ms = v * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(u, 1e-6)

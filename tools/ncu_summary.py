@@ -15,7 +15,7 @@ KEEP = [
     "lts__t_sector_hit_rate.pct", "sm__inst_executed.sum.per_cycle_elapsed", "sm__cycles_elapsed.max",
 ]
 import json
-FM_KERNELS = ("fm::", "seg::fwd_kernel", "dkdv_kernel", "qkv_kernel", "group_sum_kernel", "apply_kernel", "build_kernel", "intra_kernel", "prep_bwd_kernel", "transpose_kernel", "scan_kernel",
+FM_KERNELS = ("fm::", "seg::fwd_kernel", "dkdv_kernel", "dq_kernel", "qkv_kernel", "group_sum_kernel", "apply_kernel", "build_kernel", "intra_kernel", "prep_bwd_kernel", "transpose_kernel", "scan_kernel",
               "reduce_kernel", "applyfull_kernel", "finalize_kernel")
 rows = list(csv.reader(open(sys.argv[1])))
 hdr, units = rows[0], rows[1]
