@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-echo skip-tests
+( timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -3 )
 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -1
 python bench.py > gpurun_out/r2_bench_full.json 2> gpurun_out/bench.err; tail -2 gpurun_out/bench.err; wc -c gpurun_out/r2_bench_full.json
 python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > gpurun_out/plain_bench.log 2>&1 &&
