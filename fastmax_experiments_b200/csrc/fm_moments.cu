@@ -585,6 +585,9 @@ constexpr int A_STAGE_BYTES = 2 * 8192;                  // two slabs per MMA (N
 constexpr int A_TOK = APPLY_TOK;                         // 4 token tiles per CTA
 constexpr int A_RES_BYTES = 4 * 16384;                   // four resident 128x64 Y tiles
 constexpr int A_SMEM = A_RES_BYTES + A_STAGES * A_STAGE_BYTES + 1024 + 1024;
+#ifndef FM_APPLY_NAP
+#define FM_APPLY_NAP 40
+#endif
 constexpr int A_ISSUERS = 2;   // (4, one per tile: 4.2 ms per launch instead of 2.2 -- a 21st warp costs every thread registers)
 constexpr int A_PRODUCER = 16 + A_ISSUERS;               // warp index of the TMA producer
 constexpr int A_THREADS = (17 + A_ISSUERS) * 32;         // 16 epilogue warps, MMA issuers, TMA producer
@@ -758,7 +761,9 @@ apply_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CU
           xs[0] = P.coef64, xs[1] = 0.f;
         }
         if (warp == 0 && lane == 0) FM_TRA(3, gi);
-        mbar_wait_spin(&t_full[t], gi & 1);
+        // a short nap between polls: the step runs at the power cap, and 512 threads re-polling for about half of the
+        // kernel's time cost more than the ~40 ns of wake-up latency (sustained bench 18.8 -> 18.4 ms on the same box)
+        while (!mbar_try_wait(&t_full[t], gi & 1)) __nanosleep(FM_APPLY_NAP);
         tc_fence_after();
         if (warp == 0 && lane == 0) FM_TRA(4, gi);
 #pragma unroll
