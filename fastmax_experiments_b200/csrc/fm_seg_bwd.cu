@@ -290,14 +290,15 @@ dkdv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUt
           w[8 + (c >> 1)] = pack_bf16x2(e0, e1);
         }
       } else {
+        // interior tile: packed fp32 arithmetic (fm_sm100.cuh), half the instructions of the scalar loop
+        const f32x2 C2 = pack2(c2, c2), A2 = pack2(a, a), ONE2 = pack2(1.f, 1.f);
 #pragma unroll
         for (int c = 0; c < 16; c += 2) {
-          const float s0 = __uint_as_float(sv[c]), s1 = __uint_as_float(sv[c + 1]);
-          const float p0 = fmaf(s0, fmaf(c2, s0, a), 1.f), p1 = fmaf(s1, fmaf(c2, s1, a), 1.f);
-          const float e0 = fmaf(a, s0, 1.f) * (__uint_as_float(dv[c]) - dl[c]);
-          const float e1 = fmaf(a, s1, 1.f) * (__uint_as_float(dv[c + 1]) - dl[c + 1]);
-          w[c >> 1] = pack_bf16x2(p0, p1);
-          w[8 + (c >> 1)] = pack_bf16x2(e0, e1);
+          const f32x2 s01 = pack2u(sv[c], sv[c + 1]);
+          const f32x2 p01 = fma2(s01, fma2(C2, s01, A2), ONE2);
+          const f32x2 e01 = mul2(fma2(A2, s01, ONE2), sub2(pack2u(dv[c], dv[c + 1]), pack2(dl[c], dl[c + 1])));
+          w[c >> 1] = pack_bf16x2_of(p01);
+          w[8 + (c >> 1)] = pack_bf16x2_of(e01);
         }
       }
       if (tid == 0) FM_TRB(3, np);
@@ -584,12 +585,10 @@ dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
           w[c >> 1] = pack_bf16x2(e0, e1);
         }
       } else {
+        const f32x2 A2 = pack2(a, a), ONE2 = pack2(1.f, 1.f), DL2 = pack2(dl, dl);      // packed fp32 arithmetic
 #pragma unroll
-        for (int c = 0; c < 16; c += 2) {
-          const float e0 = fmaf(a, __uint_as_float(sv[c]), 1.f) * (__uint_as_float(dv[c]) - dl);
-          const float e1 = fmaf(a, __uint_as_float(sv[c + 1]), 1.f) * (__uint_as_float(dv[c + 1]) - dl);
-          w[c >> 1] = pack_bf16x2(e0, e1);
-        }
+        for (int c = 0; c < 16; c += 2)
+          w[c >> 1] = pack_bf16x2_of(mul2(fma2(A2, pack2u(sv[c], sv[c + 1]), ONE2), sub2(pack2u(dv[c], dv[c + 1]), DL2)));
       }
       tmem_st8(sbuf + 16 * cb, w);      // inside the S columns this warp has just read: no warp waits for another
       tmem_wait_st();
