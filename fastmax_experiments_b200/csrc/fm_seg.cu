@@ -335,12 +335,13 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
       if (tid == 0) FM_TRS(3, np);
       float ps = 0.f;
       if (diag) {
+        const f32x2 C2 = pack2(c2, c2), A2 = pack2(a, a), ONE2 = pack2(1.f, 1.f);
 #pragma unroll
         for (int c = 0; c < 16; c += 2) {
-          const float s0 = __uint_as_float(v0[c]), s1 = __uint_as_float(v0[c + 1]);
-          const float s2 = __uint_as_float(v1[c]), s3 = __uint_as_float(v1[c + 1]);
-          float x0 = fmaf(fmaf(c2, s0, a), s0, 1.f), x1 = fmaf(fmaf(c2, s1, a), s1, 1.f);
-          float x2 = fmaf(fmaf(c2, s2, a), s2, 1.f), x3 = fmaf(fmaf(c2, s3, a), s3, 1.f);
+          const f32x2 s01 = pack2u(v0[c], v0[c + 1]), s23 = pack2u(v1[c], v1[c + 1]);
+          float x0, x1, x2, x3;
+          unpack2(fma2(fma2(C2, s01, A2), s01, ONE2), x0, x1);
+          unpack2(fma2(fma2(C2, s23, A2), s23, ONE2), x2, x3);
           x0 = 16 * cb + c <= r ? x0 : 0.f, x1 = 16 * cb + c + 1 <= r ? x1 : 0.f;
           x2 = 64 + 16 * cb + c <= r ? x2 : 0.f, x3 = 64 + 16 * cb + c + 1 <= r ? x3 : 0.f;
           ps += (x0 + x1) + (x2 + x3);

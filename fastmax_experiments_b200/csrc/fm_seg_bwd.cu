@@ -278,12 +278,13 @@ dkdv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUt
       const int col0 = 64 * pc.m + 16 * cb;                // query of this thread's first column, relative to c0
       const bool diag = pc.m < 2 * pc.t + 2;               // the tile reaches below the diagonal
       if (diag) {
+        const f32x2 C2 = pack2(c2, c2), A2 = pack2(a, a), ONE2 = pack2(1.f, 1.f);
 #pragma unroll
         for (int c = 0; c < 16; c += 2) {
-          const float s0 = __uint_as_float(sv[c]), s1 = __uint_as_float(sv[c + 1]);
-          float p0 = fmaf(s0, fmaf(c2, s0, a), 1.f), p1 = fmaf(s1, fmaf(c2, s1, a), 1.f);
-          float e0 = fmaf(a, s0, 1.f) * (__uint_as_float(dv[c]) - dl[c]);
-          float e1 = fmaf(a, s1, 1.f) * (__uint_as_float(dv[c + 1]) - dl[c + 1]);
+          const f32x2 s01 = pack2u(sv[c], sv[c + 1]);
+          float p0, p1, e0, e1;
+          unpack2(fma2(s01, fma2(C2, s01, A2), ONE2), p0, p1);
+          unpack2(mul2(fma2(A2, s01, ONE2), sub2(pack2u(dv[c], dv[c + 1]), pack2(dl[c], dl[c + 1]))), e0, e1);
           const bool v0 = col0 + c >= key, v1 = col0 + c + 1 >= key;      // query >= key
           p0 = v0 ? p0 : 0.f, p1 = v1 ? p1 : 0.f, e0 = v0 ? e0 : 0.f, e1 = v1 ? e1 : 0.f;
           w[c >> 1] = pack_bf16x2(p0, p1);
@@ -577,10 +578,11 @@ dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
       const int col0 = 64 * pc.m + 16 * cb;                // key of this thread's first column, same origin
       const bool diag = pc.m >= 2 * (pc.t + J);            // the tile reaches above the diagonal
       if (diag) {
+        const f32x2 A2 = pack2(a, a), ONE2 = pack2(1.f, 1.f), DL2 = pack2(dl, dl);
 #pragma unroll
         for (int c = 0; c < 16; c += 2) {
-          float e0 = fmaf(a, __uint_as_float(sv[c]), 1.f) * (__uint_as_float(dv[c]) - dl);
-          float e1 = fmaf(a, __uint_as_float(sv[c + 1]), 1.f) * (__uint_as_float(dv[c + 1]) - dl);
+          float e0, e1;
+          unpack2(mul2(fma2(A2, pack2u(sv[c], sv[c + 1]), ONE2), sub2(pack2u(dv[c], dv[c + 1]), DL2)), e0, e1);
           e0 = col0 + c <= qrow ? e0 : 0.f, e1 = col0 + c + 1 <= qrow ? e1 : 0.f;      // key <= query
           w[c >> 1] = pack_bf16x2(e0, e1);
         }
