@@ -200,9 +200,16 @@ def fused_attention_forward(self, x, cos, sin, mask=None, input_pos=None):
     alg = cfg.attn_alg[0] if isinstance(cfg.attn_alg, tuple) else cfg.attn_alg
     if input_pos is not None or alg not in ("fastmax", "fastmax_cuda") or not x.is_cuda:
         return self._reference_forward(x, cos, sin, mask, input_pos)
+    q_per_kv = cfg.n_head // cfg.n_query_groups
+    el = 8 if x.dtype == torch.bfloat16 else 4
+    chunked = (cfg.head_size % (2 * el) == 0 and cfg.rope_n_elem % 2 == 0 and (cfg.rope_n_elem // 2) % el == 0
+               and (cfg.head_size - cfg.rope_n_elem) % (2 * el) == 0)
+    if q_per_kv == 1 and not chunked:
+        # nothing to fuse and nothing to share (e.g. Pythia: 32-wide heads with 8 rotary features): the class's own
+        # forward with the rebound attention methods is the same work
+        return self._reference_forward(x, cos, sin, mask, input_pos)
     B, T, _ = x.size()
     qkv = self.attn(x)
-    q_per_kv = cfg.n_head // cfg.n_query_groups
     q, k, v = qkv_prologue(qkv, cos, sin, cfg.n_query_groups, q_per_kv, cfg.head_size, cfg.rope_n_elem)
     y = fastmax_gqa(q, k, v, mask=True, p=2)
     y = y.reshape(B, T, cfg.head_size * cfg.n_head)
